@@ -1,0 +1,1 @@
+from diffxpy_b200.testing import wald, lrt, wald_repeated, t_test, rank_test, two_sample

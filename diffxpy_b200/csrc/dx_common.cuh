@@ -1,0 +1,235 @@
+// dx_common.cuh -- device helpers shared by the dxb200 kernels (sm_100a).
+// Warp primitives, fp64 special functions (digamma, trigamma, stable lgamma ratio) and the tail
+// probabilities of scipy.stats used by /root/reference/diffxpy/stats/stats.py.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <float.h>
+
+#define DX_FULL_MASK 0xffffffffu
+
+// batchglm param_bounds (float64): log(nextafter(0,1)) / 2.5 and nextafter(log(DBL_MAX), -inf) / 2.5
+#define DX_ETA_MIN (-297.77580822352261)
+#define DX_ETA_MAX (283.91308089306964)
+#define DX_TINY 4.9406564584124654e-324
+#define DX_ETA_SCALE_FROZEN 34.5
+#define DX_CHOL_PIVOT_RTOL 8.8817841970012523e-16 /* 2^-50 */
+#define DX_NEWTON_MAX_STEP 5.0
+#define DX_NEWTON_MAX_HALVINGS 30
+
+__device__ __forceinline__ double dx_clip(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+
+__device__ __forceinline__ double dx_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(DX_FULL_MASK, v, o);
+    return v;
+}
+__device__ __forceinline__ double dx_warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(DX_FULL_MASK, v, o));
+    return v;
+}
+__device__ __forceinline__ long long dx_warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(DX_FULL_MASK, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned dx_warp_sum_u32(unsigned v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(DX_FULL_MASK, v, o);
+    return v;
+}
+// inclusive prefix sum across the warp
+__device__ __forceinline__ long long dx_warp_scan_ll(long long v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        long long t = __shfl_up_sync(DX_FULL_MASK, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// digamma / trigamma for x > 0 (recurrence up to x >= 10, then the asymptotic series)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dx_digamma(double x) {
+    double res = 0.0;
+    while (x < 10.0) { res -= 1.0 / x; x += 1.0; }
+    const double f = 1.0 / (x * x);
+    const double t = f * (-1.0 / 12.0 + f * (1.0 / 120.0 + f * (-1.0 / 252.0 + f * (1.0 / 240.0 + f * (-1.0 / 132.0 +
+                     f * (691.0 / 32760.0 + f * (-1.0 / 12.0)))))));
+    return res + log(x) - 0.5 / x + t;
+}
+__device__ __forceinline__ double dx_trigamma(double x) {
+    double res = 0.0;
+    while (x < 10.0) { res += 1.0 / (x * x); x += 1.0; }
+    const double f = 1.0 / (x * x);
+    const double t = 1.0 / 6.0 + f * (-1.0 / 30.0 + f * (1.0 / 42.0 + f * (-1.0 / 30.0 + f * (5.0 / 66.0 +
+                     f * (-691.0 / 2730.0 + f * (7.0 / 6.0))))));
+    return res + 1.0 / x + 0.5 * f + t * f / x;
+}
+// G(r, y) = lgamma(r + y) - lgamma(r) - y log r, stable for large r (second-order Stirling beyond 1e7)
+__device__ __forceinline__ double dx_lgamma_ratio(double r, double y) {
+    if (r >= 1e7) return y * (y - 1.0) / (2.0 * r) - y * (y - 1.0) * (2.0 * y - 1.0) / (12.0 * r * r);
+    return lgamma(r + y) - lgamma(r) - y * log(r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tail probabilities
+// ---------------------------------------------------------------------------------------------
+// scipy.stats.norm.cdf == special.ndtr (cephes): 0.5 erfc(-x/sqrt2) split at |x| = 1/sqrt2
+__device__ __forceinline__ double dx_ndtr(double a) {
+    const double x = a * 0.70710678118654752440;
+    const double z = fabs(x);
+    if (z < 0.70710678118654752440) return 0.5 + 0.5 * erf(x);
+    double y = 0.5 * erfc(z);
+    return x > 0 ? 1.0 - y : y;
+}
+// two-sided normal p-value the way stats.py:217 writes it, and its accurate logarithm
+__device__ __forceinline__ void dx_two_sided_normal(double z, double* p_ref, double* logp) {
+    z = fabs(z);
+    *p_ref = 2.0 * (1.0 - dx_ndtr(z));
+    const double x = z * 0.70710678118654752440;
+    *logp = isnan(z) ? z : (isinf(z) ? -INFINITY : log(erfcx(x)) - x * x);   // log(erfc(x)) = log(2 sf(z))
+}
+
+// regularized incomplete gamma: P (series) / Q (modified Lentz continued fraction)
+__device__ __forceinline__ double dx_igam_series(double a, double x) {
+    double ap = a, sum = 1.0 / a, del = sum;
+    for (int n = 0; n < 2000; ++n) {
+        ap += 1.0;
+        del *= x / ap;
+        sum += del;
+        if (fabs(del) < fabs(sum) * 1e-17) break;
+    }
+    return sum * exp(-x + a * log(x) - lgamma(a));
+}
+__device__ __forceinline__ double dx_igamc_cf(double a, double x, double* log_out) {
+    const double fpmin = 1e-300;
+    double b = x + 1.0 - a, c = 1.0 / fpmin, d = 1.0 / b, h = d;
+    for (int i = 1; i < 2000; ++i) {
+        const double an = -i * (i - a);
+        b += 2.0;
+        d = an * d + b; if (fabs(d) < fpmin) d = fpmin;
+        c = b + an / c; if (fabs(c) < fpmin) c = fpmin;
+        d = 1.0 / d;
+        const double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < 1e-16) break;
+    }
+    const double lg = -x + a * log(x) - lgamma(a) + log(h);
+    if (log_out) *log_out = lg;
+    return exp(lg);
+}
+// chi^2 survival: reference form 1 - cdf (stats.py:38, 281) and the accurate log of the upper tail
+__device__ __forceinline__ void dx_chi2_sf(double stat, double df, double* p_ref, double* logp) {
+    if (isnan(stat)) { *p_ref = stat; *logp = stat; return; }
+    const double a = 0.5 * df, x = 0.5 * stat;
+    if (!(x > 0.0)) { *p_ref = 1.0; *logp = 0.0; return; }
+    if (isinf(x)) { *p_ref = 0.0; *logp = -INFINITY; return; }
+    if (x > 1.0 && x > a) {
+        double lq;
+        const double q = dx_igamc_cf(a, x, &lq);
+        *p_ref = 1.0 - (1.0 - q);      // cdf = 1 - Q, then 1 - cdf
+        *logp = lq;
+    } else {
+        const double p = dx_igam_series(a, x);
+        *p_ref = 1.0 - p;
+        *logp = log1p(-p);
+    }
+}
+
+// regularized incomplete beta I_x(a, b) (continued fraction, Numerical-Recipes style Lentz)
+__device__ __forceinline__ double dx_betacf(double a, double b, double x) {
+    const double fpmin = 1e-300;
+    const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    double c = 1.0, d = 1.0 - qab * x / qap;
+    if (fabs(d) < fpmin) d = fpmin;
+    d = 1.0 / d;
+    double h = d;
+    for (int m = 1; m < 5000; ++m) {
+        const double m2 = 2.0 * m;
+        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+        d = 1.0 + aa * d; if (fabs(d) < fpmin) d = fpmin;
+        c = 1.0 + aa / c; if (fabs(c) < fpmin) c = fpmin;
+        d = 1.0 / d;
+        h *= d * c;
+        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+        d = 1.0 + aa * d; if (fabs(d) < fpmin) d = fpmin;
+        c = 1.0 + aa / c; if (fabs(c) < fpmin) c = fpmin;
+        d = 1.0 / d;
+        const double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < 1e-16) break;
+    }
+    return h;
+}
+// log Beta(a, b) with the large-argument cancellation removed
+__device__ __forceinline__ double dx_lbeta(double a, double b) {
+    if (a < b) { const double t = a; a = b; b = t; }
+    if (a > 1e6) return lgamma(b) - (dx_lgamma_ratio(a, b) + b * log(a));
+    return lgamma(a) + lgamma(b) - lgamma(a + b);
+}
+__device__ __forceinline__ double dx_betainc(double a, double b, double x) {
+    if (!(x > 0.0)) return 0.0;
+    if (x >= 1.0) return 1.0;
+    const double lbt = a * log(x) + b * log1p(-x) - dx_lbeta(a, b);
+    if (x < (a + 1.0) / (a + b + 2.0)) return exp(lbt) * dx_betacf(a, b, x) / a;
+    return 1.0 - exp(lbt) * dx_betacf(b, a, 1.0 - x) / b;
+}
+// 2 * scipy.stats.t.sf(t, df) for t >= 0  (stats.py:177)
+__device__ __forceinline__ double dx_two_sided_t(double t, double df) {
+    if (isnan(t) || isnan(df)) return NAN;
+    if (isinf(t)) return 0.0;
+    if (df > 1e15) { return erfc(fabs(t) * 0.70710678118654752440); }
+    const double t2 = t * t;
+    double x = df / (df + t2);
+    if (t2 > df * 1e300) x = 0.0;
+    // I_x(df/2, 1/2); for small t (x -> 1) evaluate through the complement for accuracy
+    if (t2 < df) {
+        const double y = t2 / (df + t2);
+        return 1.0 - dx_betainc(0.5, 0.5 * df, y);
+    }
+    return dx_betainc(0.5 * df, 0.5, x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// small SPD linear algebra in shared memory, one warp per matrix (n <= 32 in practice)
+// ---------------------------------------------------------------------------------------------
+// guarded Cholesky of the n x n SPD matrix M (row-major, smem) into Lm (lower); warp cooperative.
+__device__ __forceinline__ bool chol_warp(const double* M, double* Lm, int n, int lane) {
+    for (int e = lane; e < n * n; e += 32) Lm[e] = M[e];
+    __syncwarp();
+    bool ok = true;
+    for (int j = 0; j < n; ++j) {
+        const double v = Lm[j * n + j];
+        const double mjj = M[j * n + j];
+        if (!(isfinite(v) && v > DX_CHOL_PIVOT_RTOL * mjj && mjj > 0.0)) { ok = false; break; }
+        const double d = sqrt(v);
+        __syncwarp();
+        for (int i = j + lane; i < n; i += 32) Lm[i * n + j] = (i == j) ? d : Lm[i * n + j] / d;
+        __syncwarp();
+        for (int i = j + 1 + lane; i < n; i += 32) {
+            const double lij = Lm[i * n + j];
+            for (int cc = j + 1; cc <= i; ++cc) Lm[i * n + cc] -= lij * Lm[cc * n + j];
+        }
+        __syncwarp();
+    }
+    return ok;
+}
+
+// solve L L^T x = rhs serially (one lane); x may alias rhs
+__device__ __forceinline__ void chol_solve_serial(const double* Lm, int n, const double* rhs, double* x) {
+    for (int i = 0; i < n; ++i) {
+        double s = rhs[i];
+        for (int k = 0; k < i; ++k) s -= Lm[i * n + k] * x[k];
+        x[i] = s / Lm[i * n + i];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+        double s = x[i];
+        for (int k = i + 1; k < n; ++k) s -= Lm[k * n + i] * x[k];
+        x[i] = s / Lm[i * n + i];
+    }
+}
+

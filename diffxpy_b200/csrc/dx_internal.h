@@ -1,0 +1,40 @@
+// dx_internal.h -- launcher prototypes shared by the translation units of libdxb200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/dxb200.h"
+
+#define DX_INGEST_THREADS 128
+
+int dx_ingest_private_bins(int K);
+cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,
+                             const uint8_t* cell_group, int K, uint32_t* hist, int32_t* ovf_count,
+                             float* ovf_val, uint8_t* ovf_group, int sm_count, cudaStream_t stream);
+cudaError_t dx_launch_gene_moments(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,
+                                   const double* inv_sf, double* sum1, double* sum2, cudaStream_t stream);
+cudaError_t dx_launch_fit_grouped(int64_t n_genes, int K, int p, int ps,
+                                  const double* xu_loc, const double* xu_scale, const double* offset,
+                                  const double* n_k, const double* pinv_loc, const int32_t* loc_group, int n_loc_groups,
+                                  const uint32_t* tail, const int32_t* ovf_count, const int64_t* indptr,
+                                  const float* ovf_val, const uint8_t* ovf_group, const dx_fit_opts* opts,
+                                  double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
+                                  int32_t* niter, int32_t* flags, cudaStream_t stream);
+cudaError_t dx_launch_fit_percell(int64_t n_genes, int64_t n_cells, int p, int ps,
+                                  const double* design_loc, const double* design_scale, const double* log_sf,
+                                  const int64_t* indptr, const int32_t* rows, const float* vals,
+                                  const dx_fit_opts* opts,
+                                  double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
+                                  int32_t* niter, int32_t* flags, int sm_count, cudaStream_t stream);
+cudaError_t dx_launch_wald(int64_t n, const double* theta, const double* sd, double* pval, double* logp, cudaStream_t s);
+cudaError_t dx_launch_wald_from_fit(int64_t G, int p, int coef, const double* a_var, const double* fim_inv,
+                                    double* theta, double* sd, double* pval, double* logp, cudaStream_t s);
+cudaError_t dx_launch_wald_chisq(int64_t G, int k, const double* theta, const double* cov,
+                                 double* stat, double* pval, double* logp, cudaStream_t s);
+cudaError_t dx_launch_lrt(int64_t n, const double* llf, const double* llr, int ddf, double* pval, double* logp, cudaStream_t s);
+cudaError_t dx_launch_two_coef_z(int64_t n, const double* t0, const double* t1, const double* sd0, const double* sd1,
+                                 double* pval, cudaStream_t s);
+cudaError_t dx_launch_t_moments(int64_t n, const double* mu0, const double* mu1, const double* var0, const double* var1,
+                                double n0, double n1, double* pval, cudaStream_t s);
+cudaError_t dx_launch_two_group(int64_t G, double n0, double n1, const uint32_t* tail, const int32_t* ovf_count,
+                                const int64_t* indptr, const float* ovf_val, const uint8_t* ovf_group, int do_rank,
+                                double* out, int64_t* u1x2, int64_t* tie, int32_t* flags, cudaStream_t s);

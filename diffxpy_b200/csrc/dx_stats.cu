@@ -1,0 +1,309 @@
+// dx_stats.cu -- K_stats and K_twogroup.
+//  * /root/reference/diffxpy/stats/stats.py restated on device: wald_test (:181-218), wald_test_chisq
+//    (:221-282), likelihood_ratio_test (:9-39), two_coef_z_test (:285-326), t_test_moments (:116-178);
+//    every kernel writes the p-value in the reference's own floating-point form (1 - cdf, which
+//    saturates at 0 for |z| > 8.3) and, where asked, an accurate log p from the survival function.
+//  * /root/reference/diffxpy/testing/det.py:1545-1620 / 1672-1743: per-gene group moments, Welch t and
+//    the Mann-Whitney U test (scipy.stats.mannwhitneyu asymptotic method, tie + continuity corrected)
+//    computed from the 2-group tail counts of K_ingest with exact integer rank sums.
+#include "dx_common.cuh"
+#include "dx_internal.h"
+
+namespace {
+
+__global__ void dx_wald_kernel(int64_t n, const double* __restrict__ theta, const double* __restrict__ sd,
+                               double* __restrict__ pval, double* __restrict__ logp) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double s = fmax(sd[i], DX_TINY);      // stats.py:215
+    double p, lp;
+    dx_two_sided_normal(theta[i] / s, &p, &lp);
+    pval[i] = p;
+    if (logp) logp[i] = lp;
+}
+
+__global__ void dx_wald_from_fit_kernel(int64_t G, int p, int coef, const double* __restrict__ a_var,
+                                        const double* __restrict__ fim_inv, double* __restrict__ theta,
+                                        double* __restrict__ sd, double* __restrict__ pval, double* __restrict__ logp) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const double t = a_var[(int64_t)coef * G + g];
+    double v = fim_inv[g * (int64_t)p * p + coef * p + coef];
+    if (v < DX_TINY) v = DX_TINY;                // det.py:796 (NaN stays NaN)
+    const double s = sqrt(v);
+    double pv, lp;
+    dx_two_sided_normal(t / fmax(s, DX_TINY), &pv, &lp);
+    if (theta) theta[g] = t;
+    if (sd) sd[g] = s;
+    pval[g] = pv;
+    if (logp) logp[g] = lp;
+}
+
+// one warp per gene: stat = d^T cov^-1 d through the guarded Cholesky of cov
+__global__ void dx_wald_chisq_kernel(int64_t G, int k, const double* __restrict__ theta, const double* __restrict__ cov,
+                                     double* __restrict__ stat, double* __restrict__ pval, double* __restrict__ logp) {
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (g >= G) return;
+    double* M = sm + (size_t)warp * (2 * k * k + k);
+    double* L = M + k * k;
+    double* y = L + k * k;
+    bool fin = true;
+    for (int e = lane; e < k * k; e += 32) { M[e] = cov[g * (int64_t)k * k + e]; fin = fin && isfinite(M[e]); }
+    fin = __all_sync(DX_FULL_MASK, fin);
+    __syncwarp();
+    bool ok = fin && chol_warp(M, L, k, lane);
+    __syncwarp();
+    if (lane == 0) {
+        double w = NAN;
+        if (ok) {
+            w = 0.0;
+            for (int i = 0; i < k; ++i) {
+                double s = theta[(int64_t)i * G + g];
+                for (int j = 0; j < i; ++j) s -= L[i * k + j] * y[j];
+                y[i] = s / L[i * k + i];
+                w += y[i] * y[i];
+            }
+        }
+        double pv, lp;
+        dx_chi2_sf(w, (double)k, &pv, &lp);
+        if (stat) stat[g] = w;
+        pval[g] = pv;
+        if (logp) logp[g] = lp;
+    }
+}
+
+__global__ void dx_lrt_kernel(int64_t n, const double* __restrict__ llf, const double* __restrict__ llr, int ddf,
+                              double* __restrict__ pval, double* __restrict__ logp) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double dev = 2.0 * (llf[i] - llr[i]);
+    double pv, lp;
+    dx_chi2_sf(dev, (double)ddf, &pv, &lp);
+    pval[i] = pv;
+    if (logp) logp[i] = lp;
+}
+
+__global__ void dx_two_coef_z_kernel(int64_t n, const double* __restrict__ t0, const double* __restrict__ t1,
+                                     const double* __restrict__ sd0, const double* __restrict__ sd1,
+                                     double* __restrict__ pval) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double d = sd0[i] * sd0[i] + sd1[i] * sd1[i];
+    if (d < DX_TINY) d = DX_TINY;
+    double pv, lp;
+    dx_two_sided_normal(fabs(t0[i] - t1[i]) / sqrt(d), &pv, &lp);
+    pval[i] = pv;
+}
+
+__device__ __forceinline__ double dx_welch_p(double mu0, double mu1, double var0, double var1, double n0, double n1) {
+    const double a = var0 / n0, b = var1 / n1;
+    double s = sqrt(a + b);
+    s = dx_clip(s, DX_TINY, DBL_MAX);
+    const double t = fabs(mu0 - mu1) / s;
+    double div = a * a / (n0 - 1.0) + b * b / (n1 - 1.0);
+    div = dx_clip(div, DX_TINY, DBL_MAX);
+    double df = (a + b) * (a + b) / div;
+    df = dx_clip(df, DX_TINY, DBL_MAX);
+    return dx_two_sided_t(t, df);
+}
+
+__global__ void dx_t_moments_kernel(int64_t n, const double* __restrict__ mu0, const double* __restrict__ mu1,
+                                    const double* __restrict__ var0, const double* __restrict__ var1,
+                                    double n0, double n1, double* __restrict__ pval) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    pval[i] = dx_welch_p(mu0[i], mu1[i], var0[i], var1[i], n0, n1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// two-group tests from tail counts: one CTA of 128 threads per gene
+// ------------------------------------------------------------------------------------------------
+constexpr int TG_T = 128;
+constexpr int TG_CAP = 4096;      // distinct-value blocks the on-chip sort holds (65 count blocks + overflow)
+
+__device__ __forceinline__ unsigned dx_float_key(float v) {   // order-preserving map float -> uint32
+    unsigned u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(TG_T)
+dx_two_group_kernel(int64_t G, double n0, double n1, const uint32_t* __restrict__ tail_all,
+                    const int32_t* __restrict__ ovf_count, const int64_t* __restrict__ indptr,
+                    const float* __restrict__ ovf_val, const uint8_t* __restrict__ ovf_group, int do_rank,
+                    double* __restrict__ out, int64_t* __restrict__ u1x2_out, int64_t* __restrict__ tie_out,
+                    int32_t* __restrict__ flags_out) {
+    __shared__ unsigned s_cnt[2][DX_HIST_BINS + 1];   // [group][0] = zeros, [group][y] = #{count == y}
+    __shared__ double s_red[TG_T / 32][6];
+    __shared__ unsigned s_key[TG_CAP];
+    __shared__ unsigned s_idx[TG_CAP];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t g = blockIdx.x;
+    if (g >= G) return;
+    const uint32_t* tail = tail_all + g * 2 * DX_HIST_BINS;
+    const int novf = ovf_count[g];
+    const float* oval = ovf_val + indptr[g];
+    const uint8_t* ogrp = ovf_group + indptr[g];
+    // bins from tail counts
+    if (tid < 2 * DX_HIST_BINS) {
+        const int k = tid / DX_HIST_BINS, j = tid % DX_HIST_BINS;
+        const unsigned cj = tail[k * DX_HIST_BINS + j];
+        const unsigned cn = (j + 1 < DX_HIST_BINS) ? tail[k * DX_HIST_BINS + j + 1] : 0u;
+        s_cnt[k][j + 1] = cj - cn;
+    }
+    // moments: sum y, sum y^2, overflow counts per group
+    double s0 = 0, q0 = 0, s1 = 0, q1 = 0, c0 = 0, c1 = 0;
+    if (tid < 2 * DX_HIST_BINS) {
+        const int k = tid / DX_HIST_BINS, j = tid % DX_HIST_BINS;
+        const double cj = (double)tail[k * DX_HIST_BINS + j];
+        if (k == 0) { s0 += cj; q0 += cj * (2.0 * j + 1.0); } else { s1 += cj; q1 += cj * (2.0 * j + 1.0); }
+    }
+    for (int t = tid; t < novf; t += TG_T) {
+        const double y = (double)oval[t];
+        if (ogrp[t] == 0) { s0 += y; q0 += y * y; c0 += 1.0; } else { s1 += y; q1 += y * y; c1 += 1.0; }
+    }
+    s0 = dx_warp_sum(s0); q0 = dx_warp_sum(q0); s1 = dx_warp_sum(s1); q1 = dx_warp_sum(q1);
+    c0 = dx_warp_sum(c0); c1 = dx_warp_sum(c1);
+    if (lane == 0) { s_red[warp][0] = s0; s_red[warp][1] = q0; s_red[warp][2] = s1; s_red[warp][3] = q1; s_red[warp][4] = c0; s_red[warp][5] = c1; }
+    __syncthreads();
+    s0 = q0 = s1 = q1 = c0 = c1 = 0;
+    for (int w = 0; w < TG_T / 32; ++w) { s0 += s_red[w][0]; q0 += s_red[w][1]; s1 += s_red[w][2]; q1 += s_red[w][3]; c0 += s_red[w][4]; c1 += s_red[w][5]; }
+    const double mean0 = s0 / n0, mean1 = s1 / n1;
+    const double var0 = q0 / n0 - mean0 * mean0, var1 = q1 / n1 - mean1 * mean1;
+    if (tid == 0) {
+        s_cnt[0][0] = (unsigned)(n0 - (double)tail[0] - c0);
+        s_cnt[1][0] = (unsigned)(n1 - (double)tail[DX_HIST_BINS] - c1);
+    }
+    int flags = 0;
+    double p_rank = NAN;
+    long long r1x2 = 0, tie = 0;
+    if (do_rank) {
+        const int m = novf + DX_HIST_BINS + 1;
+        int mp = 1;
+        while (mp < m) mp <<= 1;
+        if (novf > 0 && mp > TG_CAP) {
+            flags |= DX_FLAG_RANK_OVERFLOW;
+        } else {
+            if (novf > 0) {
+                // blocks: idx 0..64 = count value idx; idx 65+t = overflow entry t; bitonic sort by value
+                for (int i = tid; i < mp; i += TG_T) {
+                    unsigned key = 0xffffffffu;
+                    if (i <= DX_HIST_BINS) key = dx_float_key((float)i);
+                    else if (i < m) key = dx_float_key(oval[i - DX_HIST_BINS - 1]);
+                    s_key[i] = key;
+                    s_idx[i] = (unsigned)i;
+                }
+                __syncthreads();
+                for (int k2 = 2; k2 <= mp; k2 <<= 1) {
+                    for (int j = k2 >> 1; j > 0; j >>= 1) {
+                        for (int i = tid; i < mp; i += TG_T) {
+                            const int l = i ^ j;
+                            if (l > i) {
+                                const bool up = ((i & k2) == 0);
+                                const unsigned ka = s_key[i], kb = s_key[l];
+                                if ((ka > kb) == up) {
+                                    s_key[i] = kb; s_key[l] = ka;
+                                    const unsigned t2 = s_idx[i]; s_idx[i] = s_idx[l]; s_idx[l] = t2;
+                                }
+                            }
+                        }
+                        __syncthreads();
+                    }
+                }
+            } else {
+                __syncthreads();
+            }
+            if (tid == 0) {
+                // serial merge of tie blocks in ascending value order (exact integers)
+                long long cum = 0;
+                int i = 0;
+                while (i < m) {
+                    long long ta = 0, tb = 0;
+                    const unsigned key = (novf > 0) ? s_key[i] : (unsigned)i;
+                    int e = i;
+                    while (e < m && ((novf > 0) ? s_key[e] : (unsigned)e) == key) {
+                        const unsigned id = (novf > 0) ? s_idx[e] : (unsigned)e;
+                        if (id <= DX_HIST_BINS) { ta += s_cnt[0][id]; tb += s_cnt[1][id]; }
+                        else if (ogrp[id - DX_HIST_BINS - 1] == 0) ta += 1; else tb += 1;
+                        ++e;
+                    }
+                    const long long t = ta + tb;
+                    if (t > 0) {
+                        r1x2 += ta * (2 * cum + t + 1);
+                        tie += t * t * t - t;
+                        cum += t;
+                    }
+                    i = e;
+                }
+                const double n = n0 + n1;
+                const double u1 = 0.5 * (double)r1x2 - n0 * (n0 + 1.0) * 0.5;
+                const double mu = n0 * n1 * 0.5;
+                const double s = sqrt(n0 * n1 / 12.0 * ((n + 1.0) - (double)tie / (n * (n - 1.0))));
+                double num = u1 - mu;
+                num -= 0.5 * (double)((num > 0.0) - (num < 0.0));
+                const double z = num / s;
+                p_rank = dx_clip(erfc(fabs(z) * 0.70710678118654752440), 0.0, 1.0);
+                if (isnan(z)) p_rank = NAN;
+            }
+        }
+    }
+    if (tid == 0) {
+        double* o = out + g * DX_TG_NCOL;
+        o[DX_TG_MEAN0] = mean0; o[DX_TG_MEAN1] = mean1; o[DX_TG_VAR0] = var0; o[DX_TG_VAR1] = var1;
+        o[DX_TG_PVAL_T] = dx_welch_p(mean0, mean1, var0, var1, n0, n1);
+        o[DX_TG_PVAL_RANK] = p_rank;
+        if (u1x2_out) u1x2_out[g] = r1x2 - (long long)(n0 * (n0 + 1.0));
+        if (tie_out) tie_out[g] = tie;
+        if (flags_out) flags_out[g] = flags;
+    }
+}
+
+inline unsigned grid1d(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+cudaError_t dx_launch_wald(int64_t n, const double* theta, const double* sd, double* pval, double* logp, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    dx_wald_kernel<<<grid1d(n, 256), 256, 0, s>>>(n, theta, sd, pval, logp);
+    return cudaGetLastError();
+}
+cudaError_t dx_launch_wald_from_fit(int64_t G, int p, int coef, const double* a_var, const double* fim_inv,
+                                    double* theta, double* sd, double* pval, double* logp, cudaStream_t s) {
+    if (G <= 0) return cudaSuccess;
+    dx_wald_from_fit_kernel<<<grid1d(G, 256), 256, 0, s>>>(G, p, coef, a_var, fim_inv, theta, sd, pval, logp);
+    return cudaGetLastError();
+}
+cudaError_t dx_launch_wald_chisq(int64_t G, int k, const double* theta, const double* cov,
+                                 double* stat, double* pval, double* logp, cudaStream_t s) {
+    if (G <= 0) return cudaSuccess;
+    const int wpb = 4;
+    const size_t smem = (size_t)wpb * (2 * k * k + k) * sizeof(double);
+    dx_wald_chisq_kernel<<<grid1d(G, wpb), wpb * 32, smem, s>>>(G, k, theta, cov, stat, pval, logp);
+    return cudaGetLastError();
+}
+cudaError_t dx_launch_lrt(int64_t n, const double* llf, const double* llr, int ddf, double* pval, double* logp, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    dx_lrt_kernel<<<grid1d(n, 256), 256, 0, s>>>(n, llf, llr, ddf, pval, logp);
+    return cudaGetLastError();
+}
+cudaError_t dx_launch_two_coef_z(int64_t n, const double* t0, const double* t1, const double* sd0, const double* sd1,
+                                 double* pval, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    dx_two_coef_z_kernel<<<grid1d(n, 256), 256, 0, s>>>(n, t0, t1, sd0, sd1, pval);
+    return cudaGetLastError();
+}
+cudaError_t dx_launch_t_moments(int64_t n, const double* mu0, const double* mu1, const double* var0, const double* var1,
+                                double n0, double n1, double* pval, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    dx_t_moments_kernel<<<grid1d(n, 128), 128, 0, s>>>(n, mu0, mu1, var0, var1, n0, n1, pval);
+    return cudaGetLastError();
+}
+cudaError_t dx_launch_two_group(int64_t G, double n0, double n1, const uint32_t* tail, const int32_t* ovf_count,
+                                const int64_t* indptr, const float* ovf_val, const uint8_t* ovf_group, int do_rank,
+                                double* out, int64_t* u1x2, int64_t* tie, int32_t* flags, cudaStream_t s) {
+    if (G <= 0) return cudaSuccess;
+    dx_two_group_kernel<<<(unsigned)G, TG_T, 0, s>>>(G, n0, n1, tail, ovf_count, indptr, ovf_val, ovf_group, do_rank,
+                                                     out, u1x2, tie, flags);
+    return cudaGetLastError();
+}

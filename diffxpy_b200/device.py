@@ -1,0 +1,171 @@
+"""
+Device-side containers: the gene-major (CSC) count shard that every kernel streams, and thin helpers
+that pass torch CUDA tensors to the C ABI as raw pointers.  PyTorch is plumbing here (allocation,
+streams, torch.distributed); all arithmetic happens in libdxb200.so.
+
+Layout in HBM (one shard = a contiguous gene range of the cells x genes matrix):
+    indptr  int64  [G+1]    start of every gene's run of non-zeros
+    rows    int32  [nnz]    cell index, ascending inside a gene
+    vals    float32[nnz]    count (exact for integers < 2^24)
+i.e. 8 algorithmic bytes per non-zero, the figure SURVEY.md section 8(d) charges against the HBM roofline.
+"""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse
+import torch
+
+from . import _lib
+
+
+def ptr(t):
+    """Raw device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "tensor passed to the C ABI must be contiguous"
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def cuda_device(device=None):
+    _lib.require_cuda()
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+class CountShard:
+    """Gene-major compressed counts of a gene range on one GPU."""
+
+    def __init__(self, indptr, rows, vals, n_cells, gene_offset=0):
+        self.indptr, self.rows, self.vals = indptr, rows, vals
+        self.n_cells = int(n_cells)
+        self.n_genes = int(indptr.shape[0] - 1)
+        self.gene_offset = int(gene_offset)
+        self.device = vals.device
+        self._nnz = None
+
+    @property
+    def nnz(self):
+        if self._nnz is None:
+            self._nnz = int(self.indptr[-1].item())
+        return self._nnz
+
+    @property
+    def algorithmic_bytes(self):
+        """Bytes one streaming pass must read: 8 per non-zero + the gene pointers."""
+        return 8 * self.nnz + 8 * (self.n_genes + 1)
+
+    # ---- constructors -----------------------------------------------------------------------------
+    @staticmethod
+    def from_host(data, device=None, gene_range=None):
+        """Accepts what diffxpy accepts as ``data`` (utils.py:20-33): dense ndarray, scipy sparse (CSR as
+        AnnData stores it, or CSC), an object with ``.X`` (AnnData / Raw) or a CountShard."""
+        if isinstance(data, CountShard):
+            return data
+        dev = cuda_device(device)
+        if hasattr(data, "X") and not isinstance(data, (np.ndarray, torch.Tensor)) and not scipy.sparse.issparse(data):
+            data = data.X
+        if isinstance(data, torch.Tensor):
+            return CountShard.from_dense_device(data.to(dev), gene_range)
+        if scipy.sparse.issparse(data):
+            n_cells = data.shape[0]
+            if scipy.sparse.isspmatrix_csc(data):
+                csc = data
+                if gene_range is not None:
+                    lo, hi = gene_range
+                    ip = np.asarray(csc.indptr[lo:hi + 1], dtype=np.int64)
+                    sl = slice(int(ip[0]), int(ip[-1]))
+                    indptr, indices, vals = ip - ip[0], csc.indices[sl], csc.data[sl]
+                else:
+                    indptr, indices, vals = np.asarray(csc.indptr, dtype=np.int64), csc.indices, csc.data
+                if not csc.has_sorted_indices:
+                    csc = csc.copy()
+                    csc.sort_indices()
+                    return CountShard.from_host(csc, dev, gene_range)
+                return CountShard(torch.from_numpy(np.ascontiguousarray(indptr)).to(dev),
+                                  torch.from_numpy(np.ascontiguousarray(indices, dtype=np.int32)).to(dev),
+                                  torch.from_numpy(np.ascontiguousarray(vals, dtype=np.float32)).to(dev),
+                                  n_cells, 0 if gene_range is None else gene_range[0])
+            csr = data.tocsr()
+            return CountShard.from_csr_device(
+                torch.from_numpy(np.asarray(csr.indptr, dtype=np.int64)).to(dev),
+                torch.from_numpy(np.ascontiguousarray(csr.indices, dtype=np.int32)).to(dev),
+                torch.from_numpy(np.ascontiguousarray(csr.data, dtype=np.float32)).to(dev),
+                csr.shape[1], gene_range)
+        arr = np.asarray(data)
+        if arr.ndim != 2:
+            raise ValueError("data must be a 2-d (cells x genes) matrix")
+        if gene_range is not None:
+            arr = arr[:, gene_range[0]:gene_range[1]]
+        shard = CountShard.from_dense_device(torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(dev))
+        shard.gene_offset = 0 if gene_range is None else gene_range[0]
+        return shard
+
+    @staticmethod
+    def from_dense_device(x, gene_range=None):
+        """Dense cells x genes tensor on the device -> shard (zeros dropped)."""
+        if gene_range is not None:
+            x = x[:, gene_range[0]:gene_range[1]]
+        xt = x.t().contiguous().to(torch.float32)
+        nz = xt != 0
+        counts = nz.sum(dim=1, dtype=torch.int64)
+        indptr = torch.zeros(xt.shape[0] + 1, dtype=torch.int64, device=x.device)
+        torch.cumsum(counts, 0, out=indptr[1:])
+        idx = nz.nonzero(as_tuple=False)
+        rows = idx[:, 1].to(torch.int32).contiguous()
+        vals = xt[nz].contiguous()
+        return CountShard(indptr, rows, vals, x.shape[0], 0 if gene_range is None else gene_range[0])
+
+    @staticmethod
+    def from_csr_device(indptr, cols, vals, n_genes, gene_range=None):
+        """Cell-major CSR on the device -> gene-major shard (stable sort by gene keeps cells ascending)."""
+        n_cells = indptr.shape[0] - 1
+        dev = vals.device
+        row_of = torch.repeat_interleave(torch.arange(n_cells, device=dev, dtype=torch.int32),
+                                         (indptr[1:] - indptr[:-1]))
+        if gene_range is not None:
+            lo, hi = gene_range
+            keep = (cols >= lo) & (cols < hi)
+            cols, vals, row_of = cols[keep] - lo, vals[keep], row_of[keep]
+            n_out = hi - lo
+        else:
+            n_out = n_genes
+        order = torch.sort(cols.to(torch.int64), stable=True).indices
+        counts = torch.bincount(cols.to(torch.int64), minlength=n_out)
+        out_ptr = torch.zeros(n_out + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts, 0, out=out_ptr[1:])
+        return CountShard(out_ptr, row_of[order].contiguous(), vals[order].to(torch.float32).contiguous(), n_cells,
+                          0 if gene_range is None else gene_range[0])
+
+    # ---- kernels ----------------------------------------------------------------------------------
+    def group_suffstats(self, cell_group, n_groups):
+        """K_ingest: tail counts [G][K][64] uint32 (as int32 storage) + overflow entries."""
+        g = self.n_genes
+        dev = self.device
+        tail = torch.empty((g, n_groups, _lib.DX_HIST_BINS), dtype=torch.int32, device=dev)
+        ovf_count = torch.empty(g, dtype=torch.int32, device=dev)
+        ovf_val = torch.empty(max(self.vals.shape[0], 1), dtype=torch.float32, device=dev)
+        ovf_group = torch.empty(max(self.vals.shape[0], 1), dtype=torch.uint8, device=dev)
+        _lib.call("dx_group_suffstats", g, ptr(self.indptr), ptr(self.rows), ptr(self.vals), ptr(cell_group),
+                  int(n_groups), ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), stream_ptr())
+        return SuffStats(self, tail, ovf_count, ovf_val, ovf_group, n_groups)
+
+    def gene_moments(self, inv_sf=None):
+        g = self.n_genes
+        s1 = torch.empty(g, dtype=torch.float64, device=self.device)
+        s2 = torch.empty(g, dtype=torch.float64, device=self.device)
+        _lib.call("dx_gene_moments", g, ptr(self.indptr), ptr(self.rows), ptr(self.vals), ptr(inv_sf), ptr(s1), ptr(s2),
+                  stream_ptr())
+        return s1, s2
+
+
+class SuffStats:
+    """Output of K_ingest for one shard."""
+
+    def __init__(self, shard, tail, ovf_count, ovf_val, ovf_group, n_groups):
+        self.shard, self.tail, self.ovf_count, self.ovf_val, self.ovf_group = shard, tail, ovf_count, ovf_val, ovf_group
+        self.n_groups = int(n_groups)

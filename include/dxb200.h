@@ -1,0 +1,173 @@
+/*
+ * dxb200.h -- C ABI of libdxb200.so: the B200 (sm_100a) implementation of diffxpy's per-gene
+ * negative-binomial GLM fit + Wald / LRT statistics and the model-free Welch-t / Wilcoxon tests.
+ *
+ * Boundary replaced: the batchglm Estimator protocol that diffxpy drives from
+ *   /root/reference/diffxpy/testing/tests.py:26-249   (_fit: InputDataGLM -> Estimator -> initialize ->
+ *                                                       train_sequence -> finalize)
+ * and the statistics that follow it
+ *   /root/reference/diffxpy/stats/stats.py:9-39, 42-75, 116-178, 181-218, 221-282
+ *   /root/reference/diffxpy/testing/det.py:783-811, 1545-1620, 1672-1743
+ *   /root/reference/diffxpy/testing/correction.py:5-24
+ *
+ * Conventions
+ *   - plain pointers and sizes; every pointer is DEVICE memory owned by the caller unless the
+ *     function name ends in _host; `stream` is a cudaStream_t passed as void*.
+ *   - all calls are stream-ordered and never synchronise, except *_host convenience entry points.
+ *   - return 0 on success, a DX_ERR_* code otherwise; dx_last_error() gives the message (thread local).
+ *   - the count matrix shard is gene-major compressed (CSC of the cells x genes matrix):
+ *       indptr[G+1] int64, rows[nnz] int32 (cell index, ascending inside a gene), vals[nnz] float32.
+ */
+#ifndef DXB200_H
+#define DXB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DX_OK 0
+#define DX_ERR_INVALID 1
+#define DX_ERR_CUDA 2
+#define DX_ERR_UNSUPPORTED 3
+
+/* per-gene status bits (column `err` of the Wald summary, det.py:839-840) */
+#define DX_FLAG_CONVERGED 1
+#define DX_FLAG_SINGULAR_FIM 2
+#define DX_FLAG_SCALE_FROZEN 4
+#define DX_FLAG_NONFINITE 8
+#define DX_FLAG_ALL_ZERO 16
+#define DX_FLAG_RANK_OVERFLOW 32 /* rank test: more distinct non-count values than the on-chip sort holds */
+
+#define DX_HIST_BINS 64      /* direct-addressed count bins y = 1..64 per (gene, design group) */
+#define DX_MAX_GROUPS 255    /* distinct design rows handled by the grouped path; group id 255 = skip cell */
+#define DX_SKIP_GROUP 255
+#define DX_MAX_COEF 32       /* max coefficients of the location / scale model */
+
+/* init modes: batchglm init_par (tests.py:36-37, 222-229) */
+#define DX_INIT_GIVEN 0        /* a_var / b_var hold the start values */
+#define DX_INIT_STANDARD 1     /* a: intercept = log(mean); b: intercept = log(method-of-moments size) */
+#define DX_INIT_CLOSED_FORM 2  /* a: pinv(unique design) @ log(group means)  (location model only) */
+#define DX_INIT_ALL_ZERO 3
+
+typedef struct dx_fit_opts {
+    int32_t max_steps;        /* train(): max_steps, DEFAULT strategy 1000 */
+    int32_t update_b_freq;    /* train(): update_b_freq, DEFAULT strategy 5 */
+    int32_t train_loc;        /* 0 when the closed-form location init is exact (saturated design) */
+    int32_t train_scale;      /* 0 == quick_scale */
+    int32_t init_a;           /* DX_INIT_* */
+    int32_t init_b;           /* DX_INIT_* (closed form for b is resolved by the host into GIVEN) */
+    int32_t newton_max_iter;  /* scale Newton iterations per scale step (100) */
+    int32_t reserved;
+    double lltol;             /* batchglm LLTOL_BY_FEATURE 1e-10 */
+    double newton_xtol;       /* 1e-8 */
+} dx_fit_opts;
+
+int dx_version(void);
+const char* dx_last_error(void);
+int dx_device_sm_count(int* out);
+
+/* ---- K_ingest: one pass over the CSC shard -> per (gene, design group) count histograms ---------
+ * Replaces the per-iteration dense passes of batchglm (tests.py:242-245) and x.mean / x.power(2).mean
+ * (det.py:1567-1584, 1693-1709) by sufficient statistics.
+ *   cell_group[n_cells] : design-group id of every cell (0..n_groups-1, 255 = ignore the cell)
+ *   hist[G][n_groups][64] uint32 : TAIL COUNTS c(j) = number of cells of the group whose count y is an
+ *                         integer with j < y <= 64 (j = 0..63).  The NB likelihood needs sum_j c(j) f(r + j);
+ *                         the bins are recovered as #{y == j+1} = c(j) - c(j+1).
+ *   ovf_*               : every other non-zero entry (non-integer, negative or > 64) of gene g is
+ *                         copied to ovf_val/ovf_group[indptr[g] .. indptr[g]+ovf_count[g]), in a
+ *                         deterministic order
+ */
+int dx_group_suffstats(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,
+                       const uint8_t* cell_group, int32_t n_groups,
+                       uint32_t* hist, int32_t* ovf_count, float* ovf_val, uint8_t* ovf_group,
+                       void* stream);
+
+/* ---- K_fit (grouped): the whole batchglm training schedule + finalize, one warp per gene ----------
+ * Replaces Estimator.initialize / train_sequence / finalize (tests.py:222-248) when the rows of
+ * [design_loc | design_scale | log size factor] take n_groups <= 255 distinct values.
+ *   xu_loc[n_groups][p_loc], xu_scale[n_groups][p_scale] : distinct design rows times constraints
+ *   offset[n_groups] (nullable) : log size factor of the group;  n_k[n_groups] : cells per group
+ *   closed-form location init (batchglm closedform_glm_mean): loc_group[n_groups] maps a group to its
+ *   distinct LOCATION design row (nullable = identity), pinv_loc[p_loc][n_loc_groups] is the pseudo-inverse
+ *   of those distinct rows; both nullable unless init_a == CLOSED_FORM
+ *   a_var[p_loc][G], b_var[p_scale][G] in/out;  fim_inv[G][p_loc][p_loc];  ll, jac [G];  niter, flags [G]
+ */
+int dx_nb_fit_grouped(int64_t n_genes, int32_t n_groups, int32_t p_loc, int32_t p_scale,
+                      const double* xu_loc, const double* xu_scale, const double* offset, const double* n_k,
+                      const double* pinv_loc, const int32_t* loc_group, int32_t n_loc_groups,
+                      const uint32_t* hist, const int32_t* ovf_count, const int64_t* indptr,
+                      const float* ovf_val, const uint8_t* ovf_group,
+                      const dx_fit_opts* opts,
+                      double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
+                      int32_t* niter, int32_t* flags, void* stream);
+
+/* ---- K_fit (per cell): same schedule, one CTA per gene, streams all cells every step --------------
+ * General path: arbitrary numeric design, per-cell size factors (tests.py:177-191 arguments).
+ *   design_loc[p_loc][n_cells], design_scale[p_scale][n_cells] (coefficient-major, constraints applied)
+ *   log_sf[n_cells] nullable.  a_var / b_var must hold the start values (DX_INIT_GIVEN).
+ */
+int dx_nb_fit_percell(int64_t n_genes, int64_t n_cells, int32_t p_loc, int32_t p_scale,
+                      const double* design_loc, const double* design_scale, const double* log_sf,
+                      const int64_t* indptr, const int32_t* rows, const float* vals,
+                      const dx_fit_opts* opts,
+                      double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
+                      int32_t* niter, int32_t* flags, void* stream);
+
+/* ---- column moments of the CSC shard (initialisation of the per-cell path, det.py:775-781 mean) ---
+ *   inv_sf[n_cells] nullable: moments of x / size_factor.  sum1, sum2, nnz: [G] */
+int dx_gene_moments(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,
+                    const double* inv_sf, double* sum1, double* sum2, void* stream);
+
+/* ---- K_stats: stats.py restated on device -------------------------------------------------------
+ * wald_test (stats.py:181-218): pval = 2 (1 - Phi(|theta/sd|)), log_pval = accurate log of the tail. */
+int dx_wald_test(int64_t n, const double* theta, const double* sd, double* pval, double* log_pval, void* stream);
+/* Wald rows straight from the fit: theta = a_var[coef], sd = sqrt(max(fim_inv[g][coef][coef], tiny))
+ * (det.py:792-802) */
+int dx_wald_from_fit(int64_t n_genes, int32_t p_loc, int32_t coef, const double* a_var, const double* fim_inv,
+                     double* theta, double* sd, double* pval, double* log_pval, void* stream);
+/* wald_test_chisq (stats.py:221-282): theta[k][G], cov[G][k][k]; NaN where cov is numerically singular */
+int dx_wald_chisq(int64_t n_genes, int32_t k, const double* theta, const double* cov,
+                  double* stat, double* pval, double* log_pval, void* stream);
+/* likelihood_ratio_test (stats.py:9-39) */
+int dx_lrt(int64_t n, const double* ll_full, const double* ll_reduced, int32_t delta_df,
+           double* pval, double* log_pval, void* stream);
+/* two_coef_z_test (stats.py:285-326) */
+int dx_two_coef_z(int64_t n, const double* t0, const double* t1, const double* sd0, const double* sd1,
+                  double* pval, void* stream);
+/* t_test_moments (stats.py:116-178) */
+int dx_t_test_moments(int64_t n, const double* mu0, const double* mu1, const double* var0, const double* var1,
+                      double n0, double n1, double* pval, void* stream);
+
+/* ---- K_twogroup: det.py:1545-1620 (Welch t) and det.py:1672-1743 (Mann-Whitney U) from the
+ * 2-group sufficient statistics of dx_group_suffstats (group 0 = first sample, group 1 = second).
+ * out[G][DX_TG_NCOL] doubles; u1x2 / tie are the exact integers 2*U1 and sum(t^3 - t). */
+#define DX_TG_MEAN0 0
+#define DX_TG_MEAN1 1
+#define DX_TG_VAR0 2
+#define DX_TG_VAR1 3
+#define DX_TG_PVAL_T 4
+#define DX_TG_PVAL_RANK 5
+#define DX_TG_NCOL 6
+int dx_two_group_tests(int64_t n_genes, double n0, double n1,
+                       const uint32_t* hist, const int32_t* ovf_count, const int64_t* indptr,
+                       const float* ovf_val, const uint8_t* ovf_group,
+                       int32_t do_rank, double* out, int64_t* u1x2, int64_t* tie, int32_t* flags, void* stream);
+
+/* ---- host-buffer entry point (what bench.py's e2e leg and a foreign-language binding call) ---------
+ * Full Wald test of one coefficient on a HOST CSC matrix with a grouped design: copies the inputs to
+ * the device, runs ingest + fit + Wald, copies the per-gene rows back.  Pointers are host memory
+ * (pinned for full PCIe rate).  out_* are [G] (a_var [p_loc][G], fim_inv [G][p_loc][p_loc]). */
+int dx_wald_grouped_host(int64_t n_cells, int64_t n_genes, const int64_t* indptr, const int32_t* rows,
+                         const float* vals, const uint8_t* cell_group, int32_t n_groups,
+                         int32_t p_loc, int32_t p_scale, const double* xu_loc, const double* xu_scale,
+                         const double* offset, const double* n_k, const double* pinv_loc,
+                         const int32_t* loc_group, int32_t n_loc_groups,
+                         const dx_fit_opts* opts, int32_t coef,
+                         double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
+                         int32_t* niter, int32_t* flags, double* pval, double* log_pval, double* sd);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DXB200_H */

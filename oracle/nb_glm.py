@@ -306,6 +306,8 @@ def fit_nb(x, design_loc, design_scale, constraints_loc=None, constraints_scale=
                     b_prop[:, idx] = _b_step_newton(model, a, b, idx, flags)
                 nll_prop = -model.ll_byfeature(a, b_prop, idx)
                 bad = nll_prop > nll[idx]
+                if not faithful:
+                    bad = bad | ~np.isfinite(nll_prop)
                 ok = ~bad
                 b[:, idx[ok]] = b_prop[:, idx[ok]]
                 nll_new[idx[ok]] = nll_prop[ok]
@@ -320,6 +322,8 @@ def fit_nb(x, design_loc, design_scale, constraints_loc=None, constraints_scale=
                 a_prop[:, idx] = np.clip(a[:, idx] + delta, ETA_MIN, ETA_MAX)
                 nll_prop = -model.ll_byfeature(a_prop, b, idx)
                 bad = nll_prop > nll[idx]
+                if not faithful:
+                    bad = bad | ~np.isfinite(nll_prop)
                 ok = ~bad
                 a[:, idx[ok]] = a_prop[:, idx[ok]]
                 nll_new[idx[ok]] = nll_prop[ok]

@@ -1,0 +1,55 @@
+"""CPU, world_size 2 over gloo: the gene-shard plan and the final all-gather of per-gene rows (the only
+collective of the path)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as td
+import torch.multiprocessing as mp
+
+from diffxpy_b200 import dist as dxdist
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, size, port, g, weights, outdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        w = dxdist.world("auto")
+        assert (w.rank, w.size) == (rank, size)
+        lo, hi = dxdist.gene_ranges(g, size, weights)[rank]
+        # fake per-gene rows: row value encodes the global gene index
+        rows = {
+            "a_var": torch.arange(lo, hi, dtype=torch.float64)[:, None] * torch.ones(1, 3, dtype=torch.float64),
+            "niter": torch.arange(lo, hi, dtype=torch.int32),
+            "fim": torch.arange(lo, hi, dtype=torch.float64)[:, None, None] * torch.ones(1, 2, 2, dtype=torch.float64),
+        }
+        full = dxdist.gather_genes(w, rows, g)
+        np.save(os.path.join(outdir, "a_%d.npy" % rank), full["a_var"].numpy())
+        np.save(os.path.join(outdir, "n_%d.npy" % rank), full["niter"].numpy())
+        np.save(os.path.join(outdir, "f_%d.npy" % rank), full["fim"].numpy())
+    finally:
+        td.destroy_process_group()
+
+
+def test_gather_genes_world_size_2(tmp_path):
+    g = 37
+    weights = np.concatenate([np.full(10, 50), np.full(27, 1)])     # unequal range lengths
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, g, weights, str(tmp_path)), nprocs=2, join=True)
+    for rank in range(2):
+        a = np.load(tmp_path / ("a_%d.npy" % rank))
+        n = np.load(tmp_path / ("n_%d.npy" % rank))
+        f = np.load(tmp_path / ("f_%d.npy" % rank))
+        np.testing.assert_array_equal(a[:, 0], np.arange(g))
+        np.testing.assert_array_equal(n, np.arange(g))
+        np.testing.assert_array_equal(f[:, 1, 1], np.arange(g))

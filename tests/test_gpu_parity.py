@@ -1,0 +1,478 @@
+"""GPU (-m gpu): parity of the CUDA path with the oracle and the golden fixtures, called through the C ABI
+(ctypes) and through the reference-shaped API.
+
+Tolerances (BASELINE.json north_star): <= 1e-5 relative on converged coefficients (absolute floor 2e-6 for
+coefficients near zero), <= 1e-4 relative on log p-values (where the reference's 1 - cdf form still carries
+digits), bit-exact rank sums / U statistics and convergence flags / niter (against oracle method_b="newton",
+the restatement of the algorithm the kernels run)."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+import scipy.sparse
+import scipy.stats
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+import oracle.nb_glm as onb          # noqa: E402
+import oracle.stats as ost           # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def de():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import diffxpy_b200.api as de_
+    return de_
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "stats_golden.npz"))
+
+
+COEF_RTOL, COEF_ATOL = 1e-5, 2e-6
+
+
+# ---------------------------------------------------------------------------------------------------
+# K_stats against the reference's own stats.py outputs
+# ---------------------------------------------------------------------------------------------------
+def test_wald_test_kernel(de, gold):
+    from diffxpy_b200.stats import stats as dstats
+    p, lp = dstats.wald_test_full(gold["wald_theta"], gold["wald_sd"])
+    np.testing.assert_allclose(p, gold["wald_p"], rtol=0, atol=4e-16)
+    assert p[2] == 0.0 and gold["wald_p"][2] == 0.0            # saturation of 1 - cdf kept
+    z = np.abs(gold["wald_theta"] / np.maximum(gold["wald_sd"], np.nextafter(0, 1)))
+    ok = np.isfinite(z)
+    ref_lp = np.log(2) + scipy.stats.norm.logsf(z[ok])
+    np.testing.assert_allclose(lp[ok], ref_lp, rtol=1e-12, atol=1e-14)
+    carries = gold["wald_p"] > 1e-11
+    np.testing.assert_allclose(lp[carries], np.log(gold["wald_p"][carries]), rtol=1e-4, atol=1e-12)
+
+
+def test_wald_chisq_kernel(de, gold):
+    p = de.stats.wald_test_chisq(gold["chisq_theta"], gold["chisq_cov"])
+    assert np.isnan(p[7])
+    ok = ~np.isnan(gold["chisq_p"])
+    np.testing.assert_allclose(p[ok], gold["chisq_p"][ok], rtol=1e-9, atol=1e-15)
+
+
+def test_lrt_kernel(de, gold):
+    p = de.stats.likelihood_ratio_test(gold["lrt_ll_full"], gold["lrt_ll_red"], int(gold["lrt_df"][0]), int(gold["lrt_df"][1]))
+    np.testing.assert_allclose(p, gold["lrt_p"], rtol=1e-10, atol=1e-15)
+
+
+def test_t_test_moments_kernel(de, gold):
+    p = de.stats.t_test_moments(gold["tt_mu0"], gold["tt_mu1"], gold["tt_var0"], gold["tt_var1"],
+                                int(gold["tt_n"][0]), int(gold["tt_n"][1]))
+    np.testing.assert_allclose(p, gold["tt_p"], rtol=1e-9, atol=1e-300)
+
+
+def test_two_coef_z_kernel(de, gold):
+    th, sd = gold["wald_theta"], gold["wald_sd"]
+    p = de.stats.two_coef_z_test(th, th[::-1].copy(), sd + 0.1, sd[::-1].copy() + 0.1)
+    np.testing.assert_allclose(p, gold["z_p"], rtol=0, atol=4e-16)
+
+
+def test_bh_on_device(de, gold):
+    from diffxpy_b200.testing import correction
+    q = correction.correct(gold["bh_p"])
+    np.testing.assert_allclose(q, gold["bh_q"], rtol=1e-14, atol=0)
+    p = gold["bh_p"].copy()
+    p[[3, 50]] = np.nan
+    np.testing.assert_allclose(correction.correct(p), ost.bh_correct(p), rtol=1e-14, atol=0, equal_nan=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# K_ingest: bit-exact sufficient statistics
+# ---------------------------------------------------------------------------------------------------
+def _ingest(x, grp, k):
+    from diffxpy_b200.device import CountShard
+    shard = CountShard.from_host(x)
+    cg = torch.from_numpy(np.ascontiguousarray(grp, dtype=np.uint8)).cuda()
+    suff = shard.group_suffstats(cg, k)
+    torch.cuda.synchronize()
+    return shard, suff
+
+
+@pytest.mark.parametrize("k", [1, 2, 16, 200])
+def test_ingest_tail_counts_bit_exact(de, k):
+    rng = np.random.default_rng(k)
+    n, g = 3000, 40
+    lam = np.exp(rng.uniform(np.log(0.02), np.log(30), g))
+    x = rng.poisson(rng.gamma(0.8, lam / 0.8, size=(n, g))).astype(np.float32)
+    x[:, 0] = 0
+    x[::7, 1] = 2.5            # non-integer -> overflow
+    x[::11, 2] = -1.0          # negative -> overflow
+    grp = rng.integers(0, k, n).astype(np.uint8)
+    grp[5:9] = 255             # ignored cells
+    shard, suff = _ingest(x, grp, k)
+    tail = suff.tail.cpu().numpy().view(np.uint32)
+    oc = suff.ovf_count.cpu().numpy()
+    indptr = shard.indptr.cpu().numpy()
+    ov, og = suff.ovf_val.cpu().numpy(), suff.ovf_group.cpu().numpy()
+    for gi in range(g):
+        col = x[:, gi]
+        for kk in range(k):
+            v = col[grp == kk]
+            isbin = (v >= 1) & (v <= 64) & (v == np.floor(v))
+            want = np.array([(v[isbin] > j).sum() for j in range(64)])
+            np.testing.assert_array_equal(tail[gi, kk], want)
+        keep = grp != 255
+        v = col[keep]
+        gk = grp[keep]
+        isovf = (v != 0) & ~((v >= 1) & (v <= 64) & (v == np.floor(v)))
+        assert oc[gi] == isovf.sum()
+        got = sorted(zip(ov[indptr[gi]:indptr[gi] + oc[gi]].tolist(), og[indptr[gi]:indptr[gi] + oc[gi]].tolist()))
+        assert got == sorted(zip(v[isovf].tolist(), gk[isovf].tolist()))
+
+
+def test_ingest_csr_csc_dense_inputs_agree(de):
+    rng = np.random.default_rng(0)
+    x = rng.poisson(0.7, size=(500, 30)).astype(np.float32)
+    grp = rng.integers(0, 3, 500)
+    outs = []
+    for data in (x, scipy.sparse.csr_matrix(x), scipy.sparse.csc_matrix(x)):
+        _, suff = _ingest(data, grp, 3)
+        outs.append(suff.tail.cpu().numpy())
+    np.testing.assert_array_equal(outs[0], outs[1])
+    np.testing.assert_array_equal(outs[0], outs[2])
+
+
+# ---------------------------------------------------------------------------------------------------
+# K_fit (grouped) against the oracle and the committed goldens
+# ---------------------------------------------------------------------------------------------------
+def _fit(de, y, xd, zd, **kw):
+    from diffxpy_b200.testing.tests import _fit as fit
+    g = y.shape[1]
+    return fit("nb", y, pd.DataFrame(xd, columns=["c%d" % i for i in range(xd.shape[1])]),
+               pd.DataFrame(zd, columns=["s%d" % i for i in range(zd.shape[1])]),
+               gene_names=["g%d" % i for i in range(g)], **kw)
+
+
+def _check_fit(est, ref, flags_exact=True, skip=None):
+    keep = np.ones(ref["a_var"].shape[1], dtype=bool) if skip is None else ~skip
+    np.testing.assert_allclose(est.a_var[:, keep], ref["a_var"][:, keep], rtol=COEF_RTOL, atol=COEF_ATOL)
+    fi_ref = ref["fisher_inv"][keep]
+    np.testing.assert_allclose(est.fisher_inv[keep], fi_ref, rtol=2e-5, atol=1e-12 + 2e-5 * np.abs(fi_ref).max(axis=(1, 2), keepdims=True))
+    np.testing.assert_allclose(est.log_likelihood[keep], ref["log_likelihood"][keep], rtol=1e-9)
+    if flags_exact:
+        np.testing.assert_array_equal(est.niter, ref["niter"])
+        np.testing.assert_array_equal(est.error_codes, ref["error_codes"])
+
+
+def test_cfg1_golden_and_oracle(de, golden_dir):
+    """BASELINE.json configs[0]: 2000 x 100, '~ 1 + condition' (saturated: closed-form location, scale only)."""
+    gd = np.load(os.path.join(golden_dir, "nbglm_cfg1.npz"))
+    y = gd["x"].astype(np.float64)
+    est = _fit(de, y, gd["design_loc"], gd["design_scale"])
+    newton = {k[7:]: gd[k] for k in gd.files if k.startswith("newton_")}
+    brent = {k[6:]: gd[k] for k in gd.files if k.startswith("brent_")}
+    _check_fit(est, newton, flags_exact=True)
+    _check_fit(est, brent, flags_exact=False)          # reference schedule with scipy brent
+    np.testing.assert_allclose(est.b_var, newton["b_var"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(est.jacobian, newton["jacobian"], rtol=1e-3, atol=1e-7)
+
+
+def test_batch_design_golden(de, golden_dir):
+    """'~ 1 + condition + batch', low counts; includes genes whose moment init sits on the Poisson plateau."""
+    gd = np.load(os.path.join(golden_dir, "nbglm_batch.npz"))
+    y = gd["x"].astype(np.float64)
+    est = _fit(de, y, gd["design_loc"], gd["design_scale"])
+    newton = {k[7:]: gd[k] for k in gd.files if k.startswith("newton_")}
+    brent = {k[6:]: gd[k] for k in gd.files if k.startswith("brent_")}
+    _check_fit(est, newton, flags_exact=True)
+    frozen = (newton["error_codes"] & onb.FLAG_SCALE_FROZEN) != 0
+    assert frozen.sum() > 0
+    # reference-faithful oracle: compare where the reference arithmetic is defined (off the plateau)
+    keep = ~frozen
+    np.testing.assert_allclose(est.a_var[:, keep], brent["a_var"][:, keep], rtol=COEF_RTOL, atol=COEF_ATOL)
+    np.testing.assert_array_equal(est.niter[keep], brent["niter"][keep])
+
+
+@pytest.mark.parametrize("fmt", ["dense", "csr"])
+def test_fit_size_factor_groups_and_scale_model(de, fmt):
+    """Scale model '~ 1 + batch' (several scale coefficients, joint Newton) and group-constant size factors."""
+    rng = np.random.default_rng(11)
+    n, g = 1200, 24
+    cond = rng.integers(0, 2, n)
+    batch = rng.integers(0, 3, n)
+    xd = np.concatenate([np.ones((n, 1)), cond[:, None], (batch[:, None] == np.arange(1, 3)[None])], axis=1).astype(float)
+    zd = np.concatenate([np.ones((n, 1)), (batch[:, None] == np.arange(1, 3)[None])], axis=1).astype(float)
+    sf = np.array([0.6, 1.0, 1.7])[batch]
+    mu = np.exp(rng.uniform(np.log(0.5), np.log(20), g))[None] * np.exp(0.5 * cond)[:, None] * sf[:, None]
+    r = np.exp(rng.uniform(-0.5, 1.0, (3, g)))[batch]
+    y = rng.poisson(rng.gamma(r, mu / r)).astype(np.float64)
+    data = y if fmt == "dense" else scipy.sparse.csr_matrix(y)
+    est = _fit(de, data, xd, zd, size_factors=sf)
+    ref = onb.fit_nb(y, xd, zd, size_factors=sf, method_b="newton")
+    _check_fit(est, ref, flags_exact=True)
+    np.testing.assert_allclose(est.b_var, ref["b_var"], rtol=1e-5, atol=1e-6)
+
+
+def test_fit_high_counts_overflow_path(de):
+    """Counts far above the 64 direct bins and non-integer values go through the overflow entries."""
+    rng = np.random.default_rng(4)
+    n, g = 800, 10
+    cond = rng.integers(0, 2, n)
+    batch = rng.integers(0, 2, n)
+    xd = np.stack([np.ones(n), cond, batch], axis=1).astype(float)
+    mu = np.exp(rng.uniform(np.log(30), np.log(3000), g))[None] * np.exp(0.3 * cond)[:, None]
+    y = rng.poisson(rng.gamma(2.0, mu / 2.0)).astype(np.float64)
+    y[:, 0] = y[:, 0] / 4.0         # non-integer "normalised" values
+    est = _fit(de, y, xd, np.ones((n, 1)))
+    ref = onb.fit_nb(y, xd, np.ones((n, 1)), method_b="newton")
+    _check_fit(est, ref, flags_exact=True)
+
+
+def test_quick_scale_and_given_init(de):
+    rng = np.random.default_rng(8)
+    n, g = 900, 12
+    cond = rng.integers(0, 2, n)
+    batch = rng.integers(0, 3, n)
+    xd = np.concatenate([np.ones((n, 1)), cond[:, None], (batch[:, None] == np.arange(1, 3)[None])], axis=1).astype(float)
+    mu = np.exp(rng.uniform(np.log(1), np.log(50), g))[None] * np.exp(0.3 * cond)[:, None]
+    y = rng.poisson(rng.gamma(1.5, mu / 1.5)).astype(np.float64)
+    est = _fit(de, y, xd, np.ones((n, 1)), quick_scale=True)
+    ref = onb.fit_nb(y, xd, np.ones((n, 1)), quick_scale=True, method_b="newton")
+    _check_fit(est, ref, flags_exact=True)
+    a0 = ref["a_var"] + 0.05
+    b0 = ref["b_var"] * 0 + 0.3
+    est2 = _fit(de, y, xd, np.ones((n, 1)), init_a=a0, init_b=b0)
+    ref2 = onb.fit_nb(y, xd, np.ones((n, 1)), init_a=a0, init_b=b0, method_b="newton")
+    _check_fit(est2, ref2, flags_exact=True)
+
+
+def test_all_zero_and_single_count_genes_do_not_crash(de):
+    rng = np.random.default_rng(2)
+    n = 600
+    cond = rng.integers(0, 2, n)
+    batch = rng.integers(0, 2, n)
+    xd = np.stack([np.ones(n), cond, batch], axis=1).astype(float)
+    y = rng.poisson(1.0, size=(n, 5)).astype(np.float64)
+    y[:, 0] = 0
+    y[:, 1] = 0
+    y[17, 1] = 1
+    est = _fit(de, y, xd, np.ones((n, 1)))
+    assert est.error_codes[0] & 16
+    assert np.all(np.isfinite(est.a_var[:, 2:]))
+    ref = onb.fit_nb(y[:, 2:], xd, np.ones((n, 1)), method_b="newton")
+    np.testing.assert_allclose(est.a_var[:, 2:], ref["a_var"], rtol=COEF_RTOL, atol=COEF_ATOL)
+
+
+# ---------------------------------------------------------------------------------------------------
+# de.test.wald / lrt through the reference-shaped API
+# ---------------------------------------------------------------------------------------------------
+def _sim_counts(seed, n, g, n_batch=4, lo=0.2, hi=20.0, frac_de=0.0):
+    rng = np.random.default_rng(seed)
+    cond = rng.integers(0, 2, n)
+    batch = rng.integers(0, n_batch, n)
+    beta = np.where(np.arange(g) < int(g * frac_de), rng.normal(0, 0.8, g), 0.0)
+    bb = rng.normal(0, 0.2, (n_batch, g))
+    bb[0] = 0
+    mu = np.exp(rng.uniform(np.log(lo), np.log(hi), g)[None] + cond[:, None] * beta[None] + bb[batch])
+    r = rng.uniform(0.7, 4, g)
+    y = rng.poisson(rng.gamma(r[None], mu / r[None])).astype(np.float64)
+    sd = pd.DataFrame({"condition": cond.astype(str), "batch": batch.astype(str)})
+    return y, sd, beta != 0
+
+
+def test_wald_summary_columns_pvalues_and_logp(de):
+    y, sd, _ = _sim_counts(21, 1000, 60, frac_de=0.5)
+    names = ["gene%d" % i for i in range(y.shape[1])]
+    res = de.test.wald(data=scipy.sparse.csr_matrix(y), formula_loc="~ 1 + condition + batch",
+                       factor_loc_totest="condition", sample_description=sd, gene_names=names)
+    summ = res.summary()
+    assert list(summ.columns) == ["gene", "pval", "qval", "log2fc", "mean", "zero_mean", "grad", "coef_mle",
+                                  "coef_sd", "ll", "err", "niter"]
+    from diffxpy_b200.data import design
+    xd = np.asarray(design.design_matrix(sd, "~ 1 + condition + batch"))
+    ref = onb.fit_nb(y, xd, np.ones((y.shape[0], 1)), method_b="brent")
+    ref_sd = np.sqrt(ref["fisher_inv"][:, 1, 1])
+    ref_p = ost.wald_test(ref["a_var"][1], ref_sd)
+    np.testing.assert_allclose(summ["coef_mle"].values, ref["a_var"][1], rtol=COEF_RTOL, atol=COEF_ATOL)
+    np.testing.assert_allclose(summ["coef_sd"].values, ref_sd, rtol=1e-5)
+    carries = ref_p > 1e-11
+    np.testing.assert_allclose(np.log(summ["pval"].values[carries]), np.log(ref_p[carries]), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(res.log_pval[carries], np.log(ref_p[carries]), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(summ["qval"].values, ost.bh_correct(summ["pval"].values), rtol=1e-13)
+    np.testing.assert_allclose(summ["mean"].values, y.mean(axis=0), rtol=1e-12)
+    np.testing.assert_array_equal(summ["log2fc"].values, summ["coef_mle"].values)     # det.py:742-765 quirk kept
+    # wald_repeated on the retained fit: multi-coefficient chi^2 test of the batch factor
+    rep = de.test.wald_repeated(res, factor_loc_totest="batch")
+    cov = ref["fisher_inv"][:, 2:5, 2:5]
+    p_chi = ost.wald_test_chisq(ref["a_var"][2:5], cov)
+    np.testing.assert_allclose(rep.pval, p_chi, rtol=2e-4, atol=1e-12)
+
+
+def test_dense_and_sparse_inputs_identical(de):
+    # unit_test/test_data_types.py:66-75
+    y, sd, _ = _sim_counts(5, 600, 20)
+    names = ["g%d" % i for i in range(y.shape[1])]
+    kw = dict(formula_loc="~ 1 + condition + batch", factor_loc_totest="condition", sample_description=sd, gene_names=names)
+    p_dense = de.test.wald(data=y, **kw).pval
+    p_csr = de.test.wald(data=scipy.sparse.csr_matrix(y), **kw).pval
+    p_csc = de.test.wald(data=scipy.sparse.csc_matrix(y), **kw).pval
+    np.testing.assert_array_equal(p_dense, p_csr)
+    np.testing.assert_array_equal(p_dense, p_csc)
+
+
+def test_wald_null_calibration_and_power(de):
+    # unit_test/test_single_null.py:12-62 (KS uniformity of null p-values) and test_single_de.py:46-64
+    y, sd, is_de = _sim_counts(1, 2000, 200, frac_de=0.0, lo=5, hi=200)
+    names = ["g%d" % i for i in range(y.shape[1])]
+    res = de.test.wald(data=y, formula_loc="~ 1 + condition + batch", factor_loc_totest="condition",
+                       sample_description=sd, gene_names=names)
+    ks = scipy.stats.kstest(res.pval, "uniform").pvalue
+    assert ks > 0.05, "null p-values are not uniform: KS p = %g" % ks
+    y, sd, is_de = _sim_counts(2, 2000, 200, frac_de=0.5, lo=5, hi=200)
+    res = de.test.wald(data=y, formula_loc="~ 1 + condition + batch", factor_loc_totest="condition",
+                       sample_description=sd, gene_names=names)
+    q = res.qval
+    assert np.mean(q[~is_de] < 0.05) <= 0.1 and np.mean(q[is_de] < 0.05) >= 0.5
+
+
+def test_lrt_against_oracle(de):
+    y, sd, _ = _sim_counts(9, 1000, 40, frac_de=0.5)
+    names = ["g%d" % i for i in range(y.shape[1])]
+    res = de.test.lrt(data=y, full_formula_loc="~ 1 + condition + batch", reduced_formula_loc="~ 1 + batch",
+                      sample_description=sd, gene_names=names)
+    from diffxpy_b200.data import design
+    xf = np.asarray(design.design_matrix(sd, "~ 1 + condition + batch"))
+    xr = np.asarray(design.design_matrix(sd, "~ 1 + batch"))
+    one = np.ones((y.shape[0], 1))
+    ff = onb.fit_nb(y, xf, one, method_b="newton")
+    fr = onb.fit_nb(y, xr, one, method_b="newton")
+    p_ref = ost.likelihood_ratio_test(ff["log_likelihood"], fr["log_likelihood"], 6, 5)
+    np.testing.assert_allclose(res.full_estim.log_likelihood, ff["log_likelihood"], rtol=1e-9)
+    np.testing.assert_allclose(res.reduced_estim.log_likelihood, fr["log_likelihood"], rtol=1e-9)
+    carries = p_ref > 1e-11
+    np.testing.assert_allclose(np.log(res.pval[carries]), np.log(p_ref[carries]), rtol=1e-4, atol=1e-5)
+    summ = res.summary()
+    assert list(summ.columns) == ["gene", "pval", "qval", "log2fc", "mean", "zero_mean", "grad", "grad_red"]
+    lfc = res.log_fold_change()
+    np.testing.assert_allclose(lfc, ff["a_var"][1], rtol=1e-5, atol=2e-6)
+
+
+def test_constrained_wald_runs(de):
+    # unit_test/test_constrained.py:101-145: batches nested in conditions
+    rng = np.random.default_rng(3)
+    n, g = 800, 30
+    cond = np.repeat([0, 1], n // 2)
+    batch = np.repeat([0, 1, 2, 3], n // 4)
+    mu = np.exp(rng.uniform(np.log(2), np.log(50), g))[None] * np.ones((n, 1))
+    y = rng.poisson(rng.gamma(2.0, mu / 2.0)).astype(np.float64)
+    sd = pd.DataFrame({"condition": cond.astype(str), "batch": batch.astype(str)})
+    names = ["g%d" % i for i in range(g)]
+    with pytest.raises(ValueError):
+        de.test.wald(data=y, formula_loc="~ 1 + condition + batch", factor_loc_totest="condition",
+                     sample_description=sd, gene_names=names)
+    res = de.test.wald(data=y, formula_loc="~ 1 + condition + batch", factor_loc_totest="condition",
+                       constraints_loc={"batch": "condition"}, sample_description=sd, gene_names=names)
+    assert res.model_estim.a_var.shape[0] == 4 and np.all(np.isfinite(res.pval))
+    from diffxpy_b200.data import design
+    dm, _, cmat, _ = design.constraint_system_from_star(sample_description=sd, formula="~ 1 + condition + batch",
+                                                       constraints={"batch": "condition"})
+    ref = onb.fit_nb(y, np.asarray(dm), np.ones((n, 1)), constraints_loc=cmat, method_b="newton")
+    np.testing.assert_allclose(res.model_estim.a_var, ref["a_var"], rtol=COEF_RTOL, atol=COEF_ATOL)
+
+
+# ---------------------------------------------------------------------------------------------------
+# model-free tests
+# ---------------------------------------------------------------------------------------------------
+def test_rank_and_t_against_reference_golden(de, gold):
+    x, grouping = gold["mwu_x"], gold["mwu_grouping"]
+    names = ["g%d" % i for i in range(x.shape[1])]
+    for data in (x, scipy.sparse.csr_matrix(x)):
+        res = de.test.rank_test(data=data, grouping=grouping, gene_names=names)
+        ref = ost.two_group_test(x, grouping, "rank")
+        np.testing.assert_array_equal(res.u_statistic[~np.isnan(ref["pval"])], gold["mwu_u1"][~np.isnan(ref["pval"])])
+        np.testing.assert_allclose(res.pval, ref["pval"], rtol=1e-12, atol=1e-300, equal_nan=True)
+        run = ~np.isnan(ref["pval"])
+        np.testing.assert_allclose(res.pval[run], gold["mwu_p_dense"][run], rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(res.summary()["log2fc"].values, ref["logfc"] / np.log(2), rtol=1e-12)
+        tt = de.test.t_test(data=data, grouping=grouping, gene_names=names)
+        ref_t = ost.two_group_test(x, grouping, "t")
+        np.testing.assert_allclose(tt.pval, ref_t["pval"], rtol=1e-8, atol=1e-300, equal_nan=True)
+
+
+def test_rank_and_t_against_scipy(de):
+    # unit_test/test_single_external_libs.py:25-112
+    rng = np.random.default_rng(1)
+    n, g = 2000, 100
+    cond = np.arange(n) % 2
+    mu = np.exp(rng.uniform(np.log(0.1), np.log(500), g))[None] * np.ones((n, 1))
+    x = rng.poisson(rng.gamma(1.5, mu / 1.5)).astype(np.float64)
+    names = ["g%d" % i for i in range(g)]
+    sd = pd.DataFrame({"condition": cond})
+    a, b = x[cond == 0], x[cond == 1]
+    tt = de.test.t_test(data=x, grouping="condition", sample_description=sd, gene_names=names)
+    p_t = scipy.stats.ttest_ind(a, b, axis=0, equal_var=False).pvalue
+    assert np.max(np.abs(tt.pval - p_t)) < 1e-3 and np.max(np.abs(np.log(tt.pval + 1e-200) - np.log(p_t + 1e-200))) < 1e-1
+    rk = de.test.rank_test(data=x, grouping="condition", sample_description=sd, gene_names=names)
+    mw = [scipy.stats.mannwhitneyu(a[:, i], b[:, i], use_continuity=True, alternative="two-sided") for i in range(g)]
+    np.testing.assert_array_equal(rk.u_statistic, np.array([m.statistic for m in mw]))      # bit exact
+    np.testing.assert_allclose(rk.pval, np.array([m.pvalue for m in mw]), rtol=1e-12, atol=1e-300)
+
+
+def test_extreme_values_rules(de):
+    # unit_test/test_extreme_values.py:11-73
+    rng = np.random.default_rng(1)
+    x = rng.poisson(3.0, size=(1000, 10)).astype(np.float64)
+    x[:, 0] = 0
+    x[:, 1] = 5
+    grouping = rng.integers(0, 2, 1000)
+    names = ["g%d" % i for i in range(10)]
+    for fn in (de.test.t_test, de.test.rank_test):
+        test = fn(data=x, grouping=grouping, gene_names=names, is_sig_zerovar=True)
+        assert np.isnan(test.pval[0]) and test.pval[1] == 1
+        s = test.summary()
+        assert "zero_variance" in s.columns and bool(s["zero_variance"].values[1])
+
+
+def test_rank_three_groups_uses_first_two(de):
+    rng = np.random.default_rng(6)
+    x = rng.poisson(2.0, size=(300, 8)).astype(np.float64)
+    grouping = np.array(["b", "a", "c"])[rng.integers(0, 3, 300)]
+    grouping[0], grouping[1] = "b", "a"
+    names = ["g%d" % i for i in range(8)]
+    res = de.test.rank_test(data=x, grouping=grouping, gene_names=names)
+    ref = ost.two_group_test(x, grouping, "rank")
+    np.testing.assert_allclose(res.pval, ref["pval"], rtol=1e-12, equal_nan=True)
+
+
+def test_host_entry_point_matches_device_path(de, golden_dir):
+    """dx_wald_grouped_host (host CSC buffers in, rows out) == the device-pointer path."""
+    import ctypes as C
+    from diffxpy_b200 import _lib
+    gd = np.load(os.path.join(golden_dir, "nbglm_batch.npz"))
+    y = gd["x"].astype(np.float64)
+    xd = gd["design_loc"]
+    est = _fit(de, y, xd, gd["design_scale"])
+    from diffxpy_b200.estimator import group_rows
+    n, g = y.shape
+    p = xd.shape[1]
+    uniq, inv = group_rows(np.concatenate([xd, np.ones((n, 1))], axis=1))
+    k = uniq.shape[0]
+    csc = scipy.sparse.csc_matrix(y.astype(np.float32))
+    indptr = np.ascontiguousarray(csc.indptr, dtype=np.int64)
+    rows = np.ascontiguousarray(csc.indices, dtype=np.int32)
+    vals = np.ascontiguousarray(csc.data, dtype=np.float32)
+    grp = inv.astype(np.uint8)
+    xu = np.ascontiguousarray(uniq[:, :p])
+    xs = np.ascontiguousarray(uniq[:, p:p + 1])
+    nk = np.bincount(inv, minlength=k).astype(np.float64)
+    pinv = np.ascontiguousarray(np.linalg.pinv(xu))
+    opts = _lib.DxFitOpts(max_steps=1000, update_b_freq=5, train_loc=1, train_scale=1, init_a=_lib.DX_INIT_CLOSED_FORM,
+                          init_b=_lib.DX_INIT_STANDARD, newton_max_iter=100, reserved=0, lltol=1e-10, newton_xtol=1e-8)
+    a = np.zeros((p, g)); b = np.zeros((1, g)); fi = np.zeros((g, p, p)); ll = np.zeros(g); jac = np.zeros(g)
+    ni = np.zeros(g, dtype=np.int32); fl = np.zeros(g, dtype=np.int32); pv = np.zeros(g); lp = np.zeros(g); sdv = np.zeros(g)
+    P = lambda arr: arr.ctypes.data_as(C.c_void_p)
+    _lib.call("dx_wald_grouped_host", n, g, P(indptr), P(rows), P(vals), P(grp), k, p, 1, P(xu), P(xs), None, P(nk),
+              P(pinv), None, k, C.byref(opts), 1, P(a), P(b), P(fi), P(ll), P(jac), P(ni), P(fl), P(pv), P(lp), P(sdv))
+    np.testing.assert_array_equal(a, est.a_var)
+    np.testing.assert_array_equal(ni, est.niter)
+    np.testing.assert_array_equal(fl, est.error_codes)
+    np.testing.assert_array_equal(fi, est.fisher_inv)

@@ -1,0 +1,98 @@
+"""CPU: host-side mirror of the reference interface -- design / constraint builders, argument checks, sharding."""
+import numpy as np
+import pandas as pd
+import pytest
+
+import diffxpy_b200.api as de
+from diffxpy_b200 import dist as dxdist
+from diffxpy_b200.data import design
+from diffxpy_b200.estimator import InputDataGLM, group_rows
+from diffxpy_b200.testing import utils as tutils
+
+
+def _sd(n=24):
+    return pd.DataFrame({
+        "condition": np.array(["0", "1"] * (n // 2)),
+        "batch": np.repeat(np.array(["a", "b", "c", "d"]), n // 4),
+        "numeric1": np.linspace(0, 1, n),
+    })
+
+
+def test_design_matrix_names_and_slices():
+    dm = design.design_matrix(_sd(), "~ 1 + condition + batch")
+    assert dm.design_info.column_names == ["Intercept", "condition[T.1]", "batch[T.b]", "batch[T.c]", "batch[T.d]"]
+    assert dm.design_info.slice("condition") == slice(1, 2)
+    assert dm.design_info.slice("batch") == slice(2, 5)
+    assert np.linalg.matrix_rank(np.asarray(dm)) == 5
+    dm0 = design.design_matrix(_sd(), "~ 0 + batch")
+    assert dm0.design_info.column_names == ["batch[a]", "batch[b]", "batch[c]", "batch[d]"]
+    np.testing.assert_array_equal(np.asarray(dm0).sum(axis=1), 1)
+
+
+def test_numeric_covariates_get_one_coefficient_each():
+    # unit_test/test_numeric_covar.py:31-41
+    sd = _sd()
+    sd["numeric2"] = sd["numeric1"] ** 2
+    names = tutils.preview_coef_names(sd, "~ 1 + condition + numeric1 + numeric2", as_numeric=["numeric1", "numeric2"])
+    assert len(names) == 4 and names[-2:] == ["numeric1", "numeric2"]
+
+
+def test_constraints_from_dict_and_string():
+    # unit_test/test_constrained.py: batches nested in conditions, sum-to-zero per condition
+    sd = pd.DataFrame({"condition": np.repeat(["c0", "c1"], 8), "batch": np.repeat(["b0", "b1", "b2", "b3"], 4)})
+    dmat, names, cmat, terms = design.constraint_system_from_star(sample_description=sd, formula="~ 1 + condition + batch",
+                                                                 constraints={"batch": "condition"})
+    assert names == ["Intercept", "condition[T.c1]", "batch[b0]", "batch[b1]", "batch[b2]", "batch[b3]"]
+    assert cmat.shape == (6, 4)
+    assert np.linalg.matrix_rank(np.asarray(dmat)) < 6 and np.linalg.matrix_rank(np.asarray(dmat) @ cmat) == 4
+    # first coefficient of every constraint is the dependent one: b0 = -b1, b2 = -b3
+    np.testing.assert_array_equal(cmat[2], [0, 0, -1, 0])
+    np.testing.assert_array_equal(cmat[4], [0, 0, 0, -1])
+    cm2 = design.constraint_matrix_from_string(dmat, names, ["batch[b0]+batch[b1]=0", "batch[b2]+batch[b3]=0"])
+    np.testing.assert_array_equal(cm2, cmat)
+
+
+def test_rank_deficient_design_raises_value_error():
+    # unit_test/test_single_fullrank.py:40-52
+    sd = pd.DataFrame({"condition": np.repeat(["c0", "c1"], 8), "batch": np.repeat(["b0", "b1", "b2", "b3"], 4)})
+    dm = design.design_matrix(sd, "~ 1 + condition + batch")
+    with pytest.raises(ValueError):
+        InputDataGLM(np.zeros((16, 3)), dm, np.ones((16, 1)))
+    d2, names, cmat, _ = design.constraint_system_from_star(sample_description=sd, formula="~ 1 + condition + batch",
+                                                            constraints={"batch": "condition"})
+    InputDataGLM(np.zeros((16, 3)), d2, np.ones((16, 1)), constraints_loc=cmat)   # must not raise
+
+
+def test_wald_argument_errors_match_reference():
+    x = np.zeros((24, 3))
+    sd = _sd()
+    with pytest.raises(ValueError):
+        de.test.wald(x, formula_loc=None, sample_description=sd, gene_names=list("abc"))
+    with pytest.raises(ValueError):
+        de.test.wald(x, formula_loc="~1+condition", sample_description=sd, gene_names=list("abc"))   # nothing to test
+    with pytest.raises(ValueError):
+        de.test.wald(x, formula_loc="~1+condition", coef_to_test="nope", sample_description=sd, gene_names=list("abc"))
+    with pytest.raises(ValueError):
+        de.test.wald(x, formula_loc="~1+condition", factor_loc_totest="condition", sample_description=sd,
+                     gene_names=list("abc"), backend="tf1")
+    with pytest.raises(ValueError):
+        de.test.wald(x, formula_loc="~1+condition", factor_loc_totest="condition", sample_description=sd)  # gene names
+
+
+def test_group_rows_and_split_x():
+    m = np.array([[1, 0.0], [1, 1], [1, -0.0], [1, 1]])
+    u, inv = group_rows(m)
+    assert u.shape[0] == 2 and inv[0] == inv[2] and inv[1] == inv[3]
+    x = np.arange(12).reshape(6, 2)
+    x0, x1 = tutils.split_x(x, np.array(["b", "a", "b", "a", "a", "b"]))
+    np.testing.assert_array_equal(x0, x[[0, 2, 5]])      # first appearance order
+
+
+def test_gene_ranges_cover_and_balance():
+    r = dxdist.gene_ranges(10, 3)
+    assert r[0][0] == 0 and r[-1][1] == 10 and all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))
+    w = np.array([100, 1, 1, 1, 1, 1, 1, 100, 1, 1])
+    r = dxdist.gene_ranges(10, 2, w)
+    loads = [w[a:b].sum() for a, b in r]
+    assert r[0][0] == 0 and r[-1][1] == 10 and abs(loads[0] - loads[1]) <= 100
+    assert dxdist.gene_ranges(5, 1) == [(0, 5)]
