@@ -171,27 +171,25 @@ __device__ __forceinline__ double dx_lbeta(double a, double b) {
     if (a > 1e6) return lgamma(b) - (dx_lgamma_ratio(a, b) + b * log(a));
     return lgamma(a) + lgamma(b) - lgamma(a + b);
 }
-__device__ __forceinline__ double dx_betainc(double a, double b, double x) {
+// I_x(a, b) with both x and y = 1 - x supplied (no cancellation in either tail)
+__device__ __forceinline__ double dx_betainc_xy(double a, double b, double x, double y) {
     if (!(x > 0.0)) return 0.0;
-    if (x >= 1.0) return 1.0;
-    const double lbt = a * log(x) + b * log1p(-x) - dx_lbeta(a, b);
+    if (!(y > 0.0)) return 1.0;
+    const double lx = (x < 0.5) ? log(x) : log1p(-y);
+    const double ly = (y < 0.5) ? log(y) : log1p(-x);
+    const double lbt = a * lx + b * ly - dx_lbeta(a, b);
     if (x < (a + 1.0) / (a + b + 2.0)) return exp(lbt) * dx_betacf(a, b, x) / a;
-    return 1.0 - exp(lbt) * dx_betacf(b, a, 1.0 - x) / b;
+    return 1.0 - exp(lbt) * dx_betacf(b, a, y) / b;
 }
-// 2 * scipy.stats.t.sf(t, df) for t >= 0  (stats.py:177)
+// 2 * scipy.stats.t.sf(t, df) for t >= 0  (stats.py:177) = I_{df/(df+t^2)}(df/2, 1/2)
 __device__ __forceinline__ double dx_two_sided_t(double t, double df) {
     if (isnan(t) || isnan(df)) return NAN;
     if (isinf(t)) return 0.0;
     if (df > 1e15) { return erfc(fabs(t) * 0.70710678118654752440); }
     const double t2 = t * t;
-    double x = df / (df + t2);
-    if (t2 > df * 1e300) x = 0.0;
-    // I_x(df/2, 1/2); for small t (x -> 1) evaluate through the complement for accuracy
-    if (t2 < df) {
-        const double y = t2 / (df + t2);
-        return 1.0 - dx_betainc(0.5, 0.5 * df, y);
-    }
-    return dx_betainc(0.5 * df, 0.5, x);
+    if (t2 > df * 1e300) return 0.0;
+    const double x = df / (df + t2), y = t2 / (df + t2);
+    return dx_betainc_xy(0.5 * df, 0.5, x, y);
 }
 
 // ---------------------------------------------------------------------------------------------
