@@ -16,7 +16,8 @@
 #define DX_ETA_SCALE_FROZEN 34.5
 #define DX_CHOL_PIVOT_RTOL 8.8817841970012523e-16 /* 2^-50 */
 #define DX_NEWTON_MAX_STEP 5.0
-#define DX_NEWTON_MAX_HALVINGS 30
+#define DX_NEWTON_MAX_HALVINGS 8
+#define DX_NEWTON_GAIN_RTOL 1e-14
 
 __device__ __forceinline__ double dx_clip(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
 
@@ -53,7 +54,7 @@ __device__ __forceinline__ long long dx_warp_scan_ll(long long v, int lane) {
 // ---------------------------------------------------------------------------------------------
 // digamma / trigamma for x > 0 (recurrence up to x >= 10, then the asymptotic series)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double dx_digamma(double x) {
+static __device__ __noinline__ double dx_digamma(double x) {
     double res = 0.0;
     while (x < 10.0) { res -= 1.0 / x; x += 1.0; }
     const double f = 1.0 / (x * x);
@@ -61,7 +62,7 @@ __device__ __forceinline__ double dx_digamma(double x) {
                      f * (691.0 / 32760.0 + f * (-1.0 / 12.0)))))));
     return res + log(x) - 0.5 / x + t;
 }
-__device__ __forceinline__ double dx_trigamma(double x) {
+static __device__ __noinline__ double dx_trigamma(double x) {
     double res = 0.0;
     while (x < 10.0) { res += 1.0 / (x * x); x += 1.0; }
     const double f = 1.0 / (x * x);
@@ -70,7 +71,7 @@ __device__ __forceinline__ double dx_trigamma(double x) {
     return res + 1.0 / x + 0.5 * f + t * f / x;
 }
 // G(r, y) = lgamma(r + y) - lgamma(r) - y log r, stable for large r (second-order Stirling beyond 1e7)
-__device__ __forceinline__ double dx_lgamma_ratio(double r, double y) {
+static __device__ __noinline__ double dx_lgamma_ratio(double r, double y) {
     if (r >= 1e7) return y * (y - 1.0) / (2.0 * r) - y * (y - 1.0) * (2.0 * y - 1.0) / (12.0 * r * r);
     return lgamma(r + y) - lgamma(r) - y * log(r);
 }
@@ -196,20 +197,25 @@ __device__ __forceinline__ double dx_two_sided_t(double t, double df) {
 // small SPD linear algebra in shared memory, one warp per matrix (n <= 32 in practice)
 // ---------------------------------------------------------------------------------------------
 // guarded Cholesky of the n x n SPD matrix M (row-major, smem) into Lm (lower); warp cooperative.
-__device__ __forceinline__ bool chol_warp(const double* M, double* Lm, int n, int lane) {
+static __device__ __noinline__ bool chol_warp(const double* M, double* Lm, int n, int lane) {
+#pragma unroll 1
     for (int e = lane; e < n * n; e += 32) Lm[e] = M[e];
     __syncwarp();
     bool ok = true;
+#pragma unroll 1
     for (int j = 0; j < n; ++j) {
         const double v = Lm[j * n + j];
         const double mjj = M[j * n + j];
         if (!(isfinite(v) && v > DX_CHOL_PIVOT_RTOL * mjj && mjj > 0.0)) { ok = false; break; }
         const double d = sqrt(v);
         __syncwarp();
+#pragma unroll 1
         for (int i = j + lane; i < n; i += 32) Lm[i * n + j] = (i == j) ? d : Lm[i * n + j] / d;
         __syncwarp();
+#pragma unroll 1
         for (int i = j + 1 + lane; i < n; i += 32) {
             const double lij = Lm[i * n + j];
+#pragma unroll 1
             for (int cc = j + 1; cc <= i; ++cc) Lm[i * n + cc] -= lij * Lm[cc * n + j];
         }
         __syncwarp();
@@ -218,14 +224,18 @@ __device__ __forceinline__ bool chol_warp(const double* M, double* Lm, int n, in
 }
 
 // solve L L^T x = rhs serially (one lane); x may alias rhs
-__device__ __forceinline__ void chol_solve_serial(const double* Lm, int n, const double* rhs, double* x) {
+static __device__ __noinline__ void chol_solve_serial(const double* Lm, int n, const double* rhs, double* x) {
+#pragma unroll 1
     for (int i = 0; i < n; ++i) {
         double s = rhs[i];
+#pragma unroll 1
         for (int k = 0; k < i; ++k) s -= Lm[i * n + k] * x[k];
         x[i] = s / Lm[i * n + i];
     }
+#pragma unroll 1
     for (int i = n - 1; i >= 0; --i) {
         double s = x[i];
+#pragma unroll 1
         for (int k = i + 1; k < n; ++k) s -= Lm[k * n + i] * x[k];
         x[i] = s / Lm[i * n + i];
     }

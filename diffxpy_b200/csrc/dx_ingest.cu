@@ -6,7 +6,7 @@
 // /root/reference/diffxpy/testing/tests.py:242-245 and the x.mean / x.power(2).mean passes of
 // /root/reference/diffxpy/testing/det.py:1567-1584, 1693-1709.
 //
-// One CTA per gene (grid-stride).  Hot bins (y <= YP, K*YP <= 128) are counted in thread-private 16-bit
+// One CTA per gene (grid-stride).  Hot bins (y <= YP, K*YP <= 128) are counted in thread-private 8-bit
 // shared-memory counters laid out [bin][thread] (bank == thread, no conflicts, no atomics); the rare
 // bins YP < y <= 64 go through shared atomics; everything else (non-integer, negative, > 64) is an
 // "overflow" entry that is copied out in a deterministic order by a second, L2-resident pass.
@@ -38,56 +38,77 @@ dx_ingest_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const int3
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw);
     uint32_t* s_scan = s_hist + K * DX_HIST_BINS;
-    uint16_t* s_priv = reinterpret_cast<uint16_t*>(s_scan + T + 4);
+    uint8_t* s_priv = reinterpret_cast<uint8_t*>(s_scan + T + 4);     // [K*YP][T] thread-private 8-bit counters
     const int tid = threadIdx.x;
     const int n_priv = K * YP;
     const int lane = tid & 31, warp = tid >> 5;
 
+    {   // private counters are zeroed once; every flush leaves them zero again
+        uint4* p4 = reinterpret_cast<uint4*>(s_priv);
+        const int n16 = (n_priv * T) / 16;
+        for (int i = tid; i < n16; i += T) p4[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
     for (int64_t g = blockIdx.x; g < n_genes; g += gridDim.x) {
         const int64_t start = indptr[g], end = indptr[g + 1];
         for (int i = tid; i < K * DX_HIST_BINS; i += T) s_hist[i] = 0u;
-        {   // zero private counters, 16 B per store
-            uint4* p4 = reinterpret_cast<uint4*>(s_priv);
-            const int n16 = (n_priv * T * 2) / 16;
-            for (int i = tid; i < n16; i += T) p4[i] = make_uint4(0u, 0u, 0u, 0u);
-        }
         __syncthreads();
         unsigned n_ovf = 0;
-        // a thread sees at most 65535 entries between two flushes of its 16-bit counters
-        const int64_t chunk = (int64_t)65535 * T;
+        // a thread sees at most 255 entries between two flushes of its 8-bit counters
+        const int64_t chunk = (int64_t)255 * T;
         for (int64_t c0 = start; c0 < end; c0 += chunk) {
             const int64_t c1 = (c0 + chunk < end) ? c0 + chunk : end;
-            int64_t i = c0 + tid;
-            for (; i + (int64_t)(U - 1) * T < c1; i += (int64_t)U * T) {
-                float v[U]; int r[U]; int k[U];
+            // software pipeline: the next batch of U value/row loads is in flight while the current batch does
+            // its group gathers and counter updates.  Full batches use immediate-offset loads without bounds
+            // checks; only the last batch of a chunk is predicated.
+            float va[U], vb[U];
+            int ra[U], rb[U];
+            const int n_here = (int)(c1 - c0);
+            const int n_batches = (n_here + U * T - 1) / (U * T);
+            const float* vp = vals + c0 + tid;
+            const int32_t* rp = rows + c0 + tid;
+            uint8_t* priv_t = s_priv + tid;
+            auto load = [&](int b, float (&v)[U], int (&r)[U]) {
+                const float* vq = vp + b * (U * T);
+                const int32_t* rq = rp + b * (U * T);
+                if ((b + 1) * (U * T) <= n_here) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) { v[u] = __ldg(vals + i + (int64_t)u * T); r[u] = __ldg(rows + i + (int64_t)u * T); }
+                    for (int u = 0; u < U; ++u) { v[u] = __ldg(vq + u * T); r[u] = __ldg(rq + u * T); }
+                } else if (b < n_batches) {
+                    const int left = n_here - b * (U * T) - tid;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const bool ok = u * T < left;
+                        v[u] = ok ? __ldg(vq + u * T) : 0.0f;
+                        r[u] = ok ? __ldg(rq + u * T) : 0;
+                    }
+                }
+            };
+            auto consume = [&](const float (&v)[U], const int (&r)[U]) {
+                int k[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) k[u] = __ldg(cell_group + r[u]);
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    int y;
-                    if (dx_classify(v[u], k[u], K, y)) {
-                        if (y <= YP) s_priv[(k[u] * YP + (y - 1)) * T + tid] += 1;
-                        else atomicAdd(&s_hist[k[u] * DX_HIST_BINS + (y - 1)], 1u);
+                    const int y = __float2int_rz(v[u]);
+                    const bool isbin = ((unsigned)(y - 1) < (unsigned)DX_HIST_BINS) && (__int2float_rn(y) == v[u]) && (k[u] < K);
+                    if (isbin && y <= YP) {
+                        priv_t[(k[u] * YP + (y - 1)) * T] += 1;
+                    } else if (isbin) {
+                        atomicAdd(&s_hist[k[u] * DX_HIST_BINS + (y - 1)], 1u);
                     } else if (v[u] != 0.0f && k[u] < K) {
                         ++n_ovf;
                     }
                 }
-            }
-            for (; i < c1; i += T) {
-                const float v = __ldg(vals + i);
-                const int k = __ldg(cell_group + __ldg(rows + i));
-                int y;
-                if (dx_classify(v, k, K, y)) {
-                    if (y <= YP) s_priv[(k * YP + (y - 1)) * T + tid] += 1;
-                    else atomicAdd(&s_hist[k * DX_HIST_BINS + (y - 1)], 1u);
-                } else if (v != 0.0f && k < K) {
-                    ++n_ovf;
-                }
+            };
+            load(0, va, ra);
+            for (int b = 0; b < n_batches; b += 2) {
+                load(b + 1, vb, rb);
+                consume(va, ra);
+                load(b + 2, va, ra);
+                if (b + 1 < n_batches) consume(vb, rb);
             }
             __syncthreads();
-            // flush: each warp reduces bins warp, warp+4, ...; lane l sums counters l, l+32, ...
+            // flush: warp w reduces bins w, w+4, ...; lane l sums counters l, l+32, l+64, l+96
             for (int b = warp; b < n_priv; b += T / 32) {
                 unsigned s = 0;
 #pragma unroll
@@ -180,7 +201,7 @@ cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32
                              float* ovf_val, uint8_t* ovf_group, int sm_count, cudaStream_t stream) {
     if (n_genes <= 0) return cudaSuccess;
     const int YP = dx_ingest_private_bins(K);
-    const size_t smem = (size_t)K * DX_HIST_BINS * 4 + (T + 4) * 4 + (size_t)K * YP * T * 2 + 16;
+    const size_t smem = (size_t)K * DX_HIST_BINS * 4 + (T + 4) * 4 + (size_t)K * YP * T + 16;
     cudaError_t e = cudaFuncSetAttribute(dx_ingest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;

@@ -51,7 +51,8 @@ ETA_SCALE_FROZEN = 34.5     # exp(34.5) ~ 1e15: beyond this the NB is numericall
 NEWTON_MAX_ITER = 100
 NEWTON_XTOL = 1e-8
 NEWTON_MAX_STEP = 5.0
-NEWTON_MAX_HALVINGS = 30
+NEWTON_MAX_HALVINGS = 8
+NEWTON_GAIN_RTOL = 1e-14
 CHOL_PIVOT_RTOL = 2.0 ** -50
 
 
@@ -445,6 +446,11 @@ def _b_step_newton(model, a, b, idx, flags):
             smax = np.max(np.abs(s))
             if smax > NEWTON_MAX_STEP:
                 s = s * (NEWTON_MAX_STEP / smax)
+                smax = NEWTON_MAX_STEP
+            pred = float(np.dot(gvec, s))
+            # converged: the step is below xtol or its predicted gain is below the resolution of the likelihood
+            if smax <= NEWTON_XTOL or not (pred > NEWTON_GAIN_RTOL * abs(f)):
+                break
             tstep = 1.0
             accepted = False
             for _h in range(NEWTON_MAX_HALVINGS):
@@ -456,11 +462,8 @@ def _b_step_newton(model, a, b, idx, flags):
                 tstep *= 0.5
             if not accepted:
                 break
-            db = np.max(np.abs(b_try - bj))
             bj = b_try
             f = f_try
-            if db <= NEWTON_XTOL:
-                break
             if np.max(np.clip(model.xh_scale @ bj, ETA_MIN, ETA_MAX)) >= ETA_SCALE_FROZEN:
                 break
         out[:, t] = bj[:, 0]
