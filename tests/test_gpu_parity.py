@@ -478,3 +478,61 @@ def test_host_entry_point_matches_device_path(de, golden_dir):
     np.testing.assert_array_equal(ni, est.niter)
     np.testing.assert_array_equal(fl, est.error_codes)
     np.testing.assert_array_equal(fi, est.fisher_inv)
+
+
+# ---------------------------------------------------------------------------------------------------
+# K_fit (per cell): designs that do not collapse into groups
+# ---------------------------------------------------------------------------------------------------
+def test_percell_size_factors(de):
+    """unit_test/test_single_sf_null.py: per-cell size factors U(0.5, 1.5) -> the per-cell streaming kernel."""
+    rng = np.random.default_rng(17)
+    n, g = 1500, 20
+    cond = rng.integers(0, 2, n)
+    batch = rng.integers(0, 3, n)
+    xd = np.concatenate([np.ones((n, 1)), cond[:, None], (batch[:, None] == np.arange(1, 3)[None])], axis=1).astype(float)
+    sf = rng.uniform(0.5, 1.5, n)
+    mu = np.exp(rng.uniform(np.log(0.3), np.log(30), g))[None] * np.exp(0.4 * cond)[:, None] * sf[:, None]
+    y = rng.poisson(rng.gamma(2.0, mu / 2.0)).astype(np.float64)
+    y[:, 0] = 0
+    y[3, 0] = 2
+    for data in (y, scipy.sparse.csr_matrix(y)):
+        est = _fit(de, data, xd, np.ones((n, 1)), size_factors=sf)
+        assert est._plan["kind"] == "percell"
+        ref = onb.fit_nb(y, xd, np.ones((n, 1)), size_factors=sf, method_b="newton")
+        degenerate = np.arange(g) == 0        # a single non-zero count: separation, Fisher information ~ 1e-126
+        _check_fit(est, ref, flags_exact=True, skip=degenerate)
+        np.testing.assert_allclose(est.b_var[:, 1:], ref["b_var"][:, 1:], rtol=1e-5, atol=2e-6)
+
+
+def test_percell_numeric_covariate_and_multi_scale(de):
+    """unit_test/test_numeric_covar.py: numeric covariates; scale model with a numeric covariate too."""
+    rng = np.random.default_rng(23)
+    n, g = 1200, 12
+    cond = rng.integers(0, 2, n)
+    t = rng.uniform(0, 1, n)
+    xd = np.stack([np.ones(n), cond, t, t * t], axis=1).astype(float)
+    zd = np.stack([np.ones(n), t], axis=1).astype(float)
+    mu = np.exp(rng.uniform(np.log(1), np.log(40), g))[None] * np.exp(0.5 * cond + 0.8 * t)[:, None]
+    r = np.exp(0.3 + 0.5 * t)[:, None]
+    y = rng.poisson(rng.gamma(r, mu / r)).astype(np.float64)
+    est = _fit(de, y, xd, zd)
+    assert est._plan["kind"] == "percell" and est.a_var.shape[0] == 4
+    ref = onb.fit_nb(y, xd, zd, method_b="newton")
+    _check_fit(est, ref, flags_exact=True)
+    np.testing.assert_allclose(est.b_var, ref["b_var"], rtol=1e-5, atol=2e-6)
+
+
+def test_wald_with_size_factors_null_calibration(de):
+    # unit_test/test_single_sf_null.py:12-67
+    rng = np.random.default_rng(1)
+    n, g = 2000, 200
+    cond = rng.integers(0, 2, n)
+    sf = rng.uniform(0.5, 1.5, n)
+    mu = np.exp(rng.uniform(np.log(5), np.log(200), g))[None] * sf[:, None]
+    r = rng.uniform(0.7, 4, g)[None]
+    y = rng.poisson(rng.gamma(r, mu / r)).astype(np.float64)
+    sd = pd.DataFrame({"condition": cond.astype(str)})
+    res = de.test.wald(data=y, formula_loc="~ 1 + condition", factor_loc_totest="condition", sample_description=sd,
+                       size_factors=sf, gene_names=["g%d" % i for i in range(g)])
+    ks = scipy.stats.kstest(res.pval, "uniform").pvalue
+    assert ks > 0.05, "null p-values are not uniform: KS p = %g" % ks
