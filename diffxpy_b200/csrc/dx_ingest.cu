@@ -6,23 +6,50 @@
 // /root/reference/diffxpy/testing/tests.py:242-245 and the x.mean / x.power(2).mean passes of
 // /root/reference/diffxpy/testing/det.py:1567-1584, 1693-1709.
 //
-// One CTA per gene (grid-stride).  Hot bins (y <= YP, K*YP <= 128) are counted in thread-private 8-bit
-// shared-memory counters laid out [bin][thread] (bank == thread, no conflicts, no atomics); the rare
-// bins YP < y <= 64 go through shared atomics; everything else (non-integer, negative, > 64) is an
-// "overflow" entry that is copied out in a deterministic order by a second, L2-resident pass.
+// One CTA (4 warps) per gene, grid-stride over genes.  Hot bins (y <= YP, K*YP <= 128, YP a power of two) are
+// counted in THREAD-PRIVATE 8-bit counters packed four to a 32-bit shared-memory word; the words of one
+// thread live in bank == lane (layout [warp][word][lane]), so the fire-and-forget shared atomic that bumps a
+// counter is conflict-free and carries no read-modify-write dependency.  A warp folds its own counters into
+// the CTA histogram with a skewed (conflict-free) column walk; no block barrier is needed for that.  The rare
+// bins YP < y <= 64 go through shared atomics on the CTA histogram; everything else (non-integer, negative,
+// > 64) is an "overflow" entry that is copied out in a deterministic order by a second, L2-resident pass.
 #include "dx_common.cuh"
 #include "dx_internal.h"
 
 namespace {
 
 constexpr int T = DX_INGEST_THREADS;   // 128
-constexpr int U = 8;                   // independent loads in flight per thread and array
+#ifndef DX_INGEST_U
+#define DX_INGEST_U 8
+#endif
+#ifndef DX_INGEST_MINB
+#define DX_INGEST_MINB 6
+#endif
+constexpr int U = DX_INGEST_U;         // independent loads in flight per thread and array
+constexpr int NWARP = T / 32;
 
-struct IngestSmem {
-    uint32_t* hist;     // [K][64]
-    uint16_t* priv;     // [K*YP][T]
-    uint32_t* scan;     // [T]
-};
+// streaming loads: read-only path, do not allocate in L1 (the cell -> group table should stay there instead)
+#ifndef DX_INGEST_NOALLOC
+#define DX_INGEST_NOALLOC 1
+#endif
+__device__ __forceinline__ float dx_ld_stream(const float* p) {
+#if DX_INGEST_NOALLOC
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ int dx_ld_stream(const int32_t* p) {
+#if DX_INGEST_NOALLOC
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
 
 __device__ __forceinline__ bool dx_classify(float v, int k, int K, int& y) {
     // true -> direct bin y (1..64); false -> overflow candidate (or ignorable when v == 0 / skipped cell)
@@ -30,27 +57,31 @@ __device__ __forceinline__ bool dx_classify(float v, int k, int K, int& y) {
     return (k < K) && (v >= 1.0f) && (v <= 64.0f) && ((float)y == v);
 }
 
-__global__ void __launch_bounds__(T)
+__global__ void __launch_bounds__(T, DX_INGEST_MINB)
 dx_ingest_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const int32_t* __restrict__ rows,
-                 const float* __restrict__ vals, const uint8_t* __restrict__ cell_group, int K, int YP,
+                 const float* __restrict__ vals, const uint8_t* __restrict__ cell_group, int K, int ysh, int NW, int NWA,
                  uint32_t* __restrict__ hist_out, int32_t* __restrict__ ovf_count,
                  float* __restrict__ ovf_val, uint8_t* __restrict__ ovf_group) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw);
-    uint32_t* s_scan = s_hist + K * DX_HIST_BINS;
-    uint8_t* s_priv = reinterpret_cast<uint8_t*>(s_scan + T + 4);     // [K*YP][T] thread-private 8-bit counters
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw);         // [K][64]
+    uint32_t* s_scan = s_hist + K * DX_HIST_BINS;                     // [T + 4]
+    uint32_t* s_priv = s_scan + T + 4;                                // [NWARP][NWA][32] packed 8-bit counters
     const int tid = threadIdx.x;
-    const int n_priv = K * YP;
     const int lane = tid & 31, warp = tid >> 5;
+    const unsigned YP = (ysh >= 0) ? (1u << ysh) : 0u;
+    const unsigned ysh_u = (ysh >= 0) ? (unsigned)ysh : 0u;
+    const unsigned n_priv = (unsigned)K * YP;
+    uint32_t* priv_warp = s_priv + warp * NWA * 32;
+    uint32_t* priv_t = priv_warp + lane;
+    const unsigned row_mask = (unsigned)(NWA - 1) << 5;   // word-row offset (in words) of counter j: (j >> 2) * 32 == (8j) & row_mask
 
-    {   // private counters are zeroed once; every flush leaves them zero again
-        uint4* p4 = reinterpret_cast<uint4*>(s_priv);
-        const int n16 = (n_priv * T) / 16;
-        for (int i = tid; i < n16; i += T) p4[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
+    for (int i = tid; i < NWARP * NWA * 32; i += T) s_priv[i] = 0u;    // every flush leaves the counters zero again
     for (int64_t g = blockIdx.x; g < n_genes; g += gridDim.x) {
         const int64_t start = indptr[g], end = indptr[g + 1];
-        for (int i = tid; i < K * DX_HIST_BINS; i += T) s_hist[i] = 0u;
+        {
+            uint4* h4 = reinterpret_cast<uint4*>(s_hist);
+            for (int i = tid; i < K * (DX_HIST_BINS / 4); i += T) h4[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
         __syncthreads();
         unsigned n_ovf = 0;
         // a thread sees at most 255 entries between two flushes of its 8-bit counters
@@ -59,44 +90,56 @@ dx_ingest_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const int3
             const int64_t c1 = (c0 + chunk < end) ? c0 + chunk : end;
             // software pipeline: the next batch of U value/row loads is in flight while the current batch does
             // its group gathers and counter updates.  Full batches use immediate-offset loads without bounds
-            // checks; only the last batch of a chunk is predicated.
+            // checks; only the last batch of a chunk is predicated (padding entries are zeros -> ignored).
             float va[U], vb[U];
             int ra[U], rb[U];
             const int n_here = (int)(c1 - c0);
             const int n_batches = (n_here + U * T - 1) / (U * T);
             const float* vp = vals + c0 + tid;
             const int32_t* rp = rows + c0 + tid;
-            uint8_t* priv_t = s_priv + tid;
             auto load = [&](int b, float (&v)[U], int (&r)[U]) {
                 const float* vq = vp + b * (U * T);
                 const int32_t* rq = rp + b * (U * T);
                 if ((b + 1) * (U * T) <= n_here) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u) { v[u] = __ldg(vq + u * T); r[u] = __ldg(rq + u * T); }
+                    for (int u = 0; u < U; ++u) { v[u] = dx_ld_stream(vq + u * T); r[u] = dx_ld_stream(rq + u * T); }
                 } else if (b < n_batches) {
                     const int left = n_here - b * (U * T) - tid;
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         const bool ok = u * T < left;
-                        v[u] = ok ? __ldg(vq + u * T) : 0.0f;
-                        r[u] = ok ? __ldg(rq + u * T) : 0;
+                        v[u] = ok ? dx_ld_stream(vq + u * T) : 0.0f;
+                        r[u] = ok ? dx_ld_stream(rq + u * T) : 0;
                     }
                 }
             };
             auto consume = [&](const float (&v)[U], const int (&r)[U]) {
-                int k[U];
+                unsigned k[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) k[u] = __ldg(cell_group + r[u]);
+                for (int u = 0; u < U; ++u) k[u] = __ldg(cell_group + (unsigned)r[u]);
+                bool slow = false;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int y = __float2int_rz(v[u]);
-                    const bool isbin = ((unsigned)(y - 1) < (unsigned)DX_HIST_BINS) && (__int2float_rn(y) == v[u]) && (k[u] < K);
-                    if (isbin && y <= YP) {
-                        priv_t[(k[u] * YP + (y - 1)) * T] += 1;
-                    } else if (isbin) {
-                        atomicAdd(&s_hist[k[u] * DX_HIST_BINS + (y - 1)], 1u);
-                    } else if (v[u] != 0.0f && k[u] < K) {
-                        ++n_ovf;
+                    const unsigned ym1 = (unsigned)(y - 1);
+                    const bool fast = (__int2float_rn(y) == v[u]) && (ym1 < YP) && (k[u] < (unsigned)K);
+                    const unsigned j8 = ((k[u] << ysh_u) + ym1) << 3;            // 8 * counter index
+                    // branch-free: a non-private entry adds 0 to an in-range word
+                    const unsigned inc = fast ? (1u << (j8 & 24u)) : 0u;
+                    atomicAdd(priv_t + (j8 & row_mask), inc);
+                    slow = slow || !fast;
+                }
+                if (slow) {     // rare: counts above the private range, non-counts, padding
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int y = __float2int_rz(v[u]);
+                        const unsigned ym1 = (unsigned)(y - 1);
+                        const bool isbin = (ym1 < (unsigned)DX_HIST_BINS) && (__int2float_rn(y) == v[u]) && (k[u] < (unsigned)K);
+                        if (isbin) {
+                            if (ym1 >= YP) atomicAdd(&s_hist[k[u] * DX_HIST_BINS + ym1], 1u);
+                        } else if (v[u] != 0.0f && k[u] < (unsigned)K) {
+                            ++n_ovf;
+                        }
                     }
                 }
             };
@@ -107,24 +150,35 @@ dx_ingest_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const int3
                 load(b + 2, va, ra);
                 if (b + 1 < n_batches) consume(vb, rb);
             }
-            __syncthreads();
-            // flush: warp w reduces bins w, w+4, ...; lane l sums counters l, l+32, l+64, l+96
-            for (int b = warp; b < n_priv; b += T / 32) {
-                unsigned s = 0;
+            __syncwarp();
+            // flush of the warp's own counters: lane l owns word-row l (bins 4l .. 4l+3) and walks the 32 columns
+            // with a skew so that the 32 lanes always hit 32 different banks
+            if (lane < NW) {
+                uint32_t* row = priv_warp + lane * 32;
+                unsigned lo = 0, hi = 0;
+#pragma unroll 8
+                for (int c = 0; c < 32; ++c) {
+                    const int col = (c + lane) & 31;
+                    const unsigned x = row[col];
+                    row[col] = 0u;
+                    lo += x & 0x00ff00ffu;
+                    hi += (x >> 8) & 0x00ff00ffu;
+                }
+                const unsigned cnt[4] = {lo & 0xffffu, hi & 0xffffu, lo >> 16, hi >> 16};
 #pragma unroll
-                for (int t = lane; t < T; t += 32) { s += s_priv[b * T + t]; s_priv[b * T + t] = 0; }
-                s = dx_warp_sum_u32(s);
-                if (lane == 0 && s) {
-                    const int k = b / YP, y1 = b - k * YP;
-                    s_hist[k * DX_HIST_BINS + y1] += s;      // bins <= YP are only touched here: no race
+                for (int b = 0; b < 4; ++b) {
+                    const unsigned idx = 4u * lane + b;
+                    if (cnt[b] && idx < n_priv)
+                        atomicAdd(&s_hist[(idx >> ysh_u) * DX_HIST_BINS + (idx & (YP - 1u))], cnt[b]);
                 }
             }
-            __syncthreads();
+            __syncwarp();
         }
+        const int any_ovf = __syncthreads_or(n_ovf != 0u);
         // write tail counts c_k(j) = #{cells of group k with j < y <= 64}, j = 0..63 (suffix sums of the bins):
         // the NB likelihood needs sum_j c(j) f(r + j), the rank test recovers the bins as c(j-1) - c(j).
         uint32_t* out = hist_out + g * (int64_t)K * DX_HIST_BINS;
-        for (int k = warp; k < K; k += T / 32) {
+        for (int k = warp; k < K; k += NWARP) {
             const unsigned lo = s_hist[k * DX_HIST_BINS + lane], hi = s_hist[k * DX_HIST_BINS + 32 + lane];
             unsigned plo = lo, phi = hi;   // inclusive prefix sums
 #pragma unroll
@@ -135,6 +189,11 @@ dx_ingest_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const int3
             const unsigned tot_lo = __shfl_sync(DX_FULL_MASK, plo, 31), tot_hi = __shfl_sync(DX_FULL_MASK, phi, 31);
             out[k * DX_HIST_BINS + 32 + lane] = tot_hi - phi + hi;
             out[k * DX_HIST_BINS + lane] = tot_hi + (tot_lo - plo + lo);
+        }
+        if (!any_ovf) {
+            if (tid == 0) ovf_count[g] = 0;
+            __syncthreads();
+            continue;
         }
         // deterministic overflow compaction: exclusive scan of per-thread counts, then a second pass
         s_scan[tid] = n_ovf;
@@ -152,7 +211,8 @@ dx_ingest_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const int3
             if (lane == 0) { s_scan[T] = run; ovf_count[g] = (int32_t)run; }
         }
         __syncthreads();
-        if (s_scan[T] != 0u) {
+        {
+            // thread t re-visits exactly the entries it counted: chunk by chunk, batch by batch, stride T
             int64_t pos = start + s_scan[tid];
             for (int64_t i = start + tid; i < end; i += T) {
                 const float v = __ldg(vals + i);
@@ -191,9 +251,10 @@ dx_gene_moments_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, cons
 }  // namespace
 
 int dx_ingest_private_bins(int K) {
-    int yp = K > 0 ? 128 / K : 0;
-    if (yp > DX_HIST_BINS) yp = DX_HIST_BINS;
-    return yp;   // 0 when K > 128: everything through shared atomics
+    // largest power of two YP <= 64 with K * YP <= 128; 0 when K > 128 (everything through shared atomics)
+    int yp = 0;
+    for (int c = 1; c <= DX_HIST_BINS && K * c <= 128; c <<= 1) yp = c;
+    return yp;
 }
 
 cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,
@@ -201,7 +262,12 @@ cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32
                              float* ovf_val, uint8_t* ovf_group, int sm_count, cudaStream_t stream) {
     if (n_genes <= 0) return cudaSuccess;
     const int YP = dx_ingest_private_bins(K);
-    const size_t smem = (size_t)K * DX_HIST_BINS * 4 + (T + 4) * 4 + (size_t)K * YP * T + 16;
+    int ysh = -1;
+    for (int c = YP; c > 0; c >>= 1) ++ysh;
+    const int NW = (K * YP + 3) / 4;        // packed counter words per thread (<= 32)
+    int NWA = 1;                            // rows allocated: next power of two (index masking keeps every update in range)
+    while (NWA < NW) NWA <<= 1;
+    const size_t smem = (size_t)K * DX_HIST_BINS * 4 + (T + 4) * 4 + (size_t)NWARP * NWA * 32 * 4 + 16;
     cudaError_t e = cudaFuncSetAttribute(dx_ingest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
@@ -210,7 +276,7 @@ cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)sm_count * per_sm;
     if (grid > n_genes) grid = n_genes;
-    dx_ingest_kernel<<<(unsigned)grid, T, smem, stream>>>(n_genes, indptr, rows, vals, cell_group, K, YP,
+    dx_ingest_kernel<<<(unsigned)grid, T, smem, stream>>>(n_genes, indptr, rows, vals, cell_group, K, ysh, NW, NWA,
                                                            hist, ovf_count, ovf_val, ovf_group);
     return cudaGetLastError();
 }

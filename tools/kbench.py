@@ -1,0 +1,129 @@
+#!/usr/bin/env python
+"""
+Kernel tuning bench: times K_ingest / K_fit of several builds of libdxb200 (tools/build_variant.sh) on the
+bench.py workload (one shard generated once) and checks that every variant produces the same outputs as the
+first one.  Development tool only; the numbers that count come from bench.py.
+
+    python tools/kbench.py [--genes 20000] [--reps 10] [--what ingest,fit] name1 name2 ...   (name "product" = libdxb200.so)
+"""
+import argparse
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from diffxpy_b200 import _lib  # noqa: E402
+from diffxpy_b200.device import ptr, stream_ptr  # noqa: E402
+from diffxpy_b200.estimator import group_rows  # noqa: E402
+
+
+def load_variant(name):
+    path = _lib.LIB_PATH if name == "product" else os.path.join(ROOT, "diffxpy_b200", "variants", "libdxb200_%s.so" % name)
+    lib = C.CDLL(path)
+    for fn, argtypes in _lib.SIGNATURES.items():
+        f = getattr(lib, fn)
+        f.argtypes = argtypes
+        f.restype = C.c_int
+    lib.dx_last_error.restype = C.c_char_p
+    return lib
+
+
+def call(lib, name, *args):
+    rc = getattr(lib, name)(*args)
+    if rc:
+        raise RuntimeError("%s: %s" % (name, lib.dx_last_error().decode()))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--genes", type=int, default=20000)
+    ap.add_argument("--cells", type=int, default=100000)
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--what", default="ingest,fit")
+    ap.add_argument("names", nargs="+")
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    shard, cond, batch = bench.make_shard(torch, dev, seed=1000, n_genes=a.genes, n_cells=a.cells)
+    nnz = shard.nnz
+    g = a.genes
+    xd = bench.design_for(cond, batch)
+    p, ps = xd.shape[1], 1
+    uniq, inv = group_rows(np.concatenate([xd, np.ones((a.cells, 1))], axis=1))
+    k = uniq.shape[0]
+    xu_loc = np.ascontiguousarray(uniq[:, :p])
+    xu_scale = np.ascontiguousarray(uniq[:, p:p + 1])
+    n_k = np.bincount(inv, minlength=k).astype(np.float64)
+    pinv = np.ascontiguousarray(np.linalg.pinv(xu_loc))
+    cell_group = torch.from_numpy(inv.astype(np.uint8)).to(dev)
+    d_xl, d_xs = torch.from_numpy(xu_loc).to(dev), torch.from_numpy(xu_scale).to(dev)
+    d_nk, d_pinv = torch.from_numpy(n_k).to(dev), torch.from_numpy(pinv).to(dev)
+    opts = _lib.DxFitOpts(max_steps=1000, update_b_freq=5, train_loc=1, train_scale=1,
+                          init_a=_lib.DX_INIT_CLOSED_FORM, init_b=_lib.DX_INIT_STANDARD, newton_max_iter=100,
+                          reserved=0, lltol=1e-10, newton_xtol=1e-8)
+    f64 = dict(dtype=torch.float64, device=dev)
+    ref = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    print("nnz %d  genes %d  groups %d  p %d" % (nnz, g, k, p))
+    for name in a.names:
+        lib = load_variant(name)
+        tail = torch.zeros((g, k, _lib.DX_HIST_BINS), dtype=torch.int32, device=dev)
+        ovf_count = torch.zeros(g, dtype=torch.int32, device=dev)
+        ovf_val = torch.zeros(nnz, dtype=torch.float32, device=dev)
+        ovf_group = torch.zeros(nnz, dtype=torch.uint8, device=dev)
+        a_var, b_var = torch.zeros((p, g), **f64), torch.zeros((ps, g), **f64)
+        fim_inv, ll, jac = torch.zeros((g, p, p), **f64), torch.zeros(g, **f64), torch.zeros(g, **f64)
+        niter, flags = torch.zeros(g, dtype=torch.int32, device=dev), torch.zeros(g, dtype=torch.int32, device=dev)
+
+        def ingest():
+            call(lib, "dx_group_suffstats", g, ptr(shard.indptr), ptr(shard.rows), ptr(shard.vals), ptr(cell_group), k,
+                 ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), stream_ptr())
+
+        def fit():
+            call(lib, "dx_nb_fit_grouped", g, k, p, ps, ptr(d_xl), ptr(d_xs), None, ptr(d_nk), ptr(d_pinv), None, k,
+                 ptr(tail), ptr(ovf_count), ptr(shard.indptr), ptr(ovf_val), ptr(ovf_group), opts, ptr(a_var),
+                 ptr(b_var), ptr(fim_inv), ptr(ll), ptr(jac), ptr(niter), ptr(flags), stream_ptr())
+
+        out = [name]
+        for what, fn in (("ingest", ingest), ("fit", fit)):
+            if what not in a.what.split(",") and not (what == "ingest"):
+                continue
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(a.reps):
+                e0, e1 = ev(), ev()
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ts = np.array(ts)
+            extra = ""
+            if what == "ingest":
+                extra = " %.0f GB/s" % ((8 * nnz + 4 * g * k * 64) / (np.median(ts) * 1e-3) / 1e9)
+            out.append("%s median %.4f ms min %.4f%s" % (what, np.median(ts), ts.min(), extra))
+        res = {"tail": tail, "ovf_count": ovf_count, "a": a_var, "b": b_var, "fim": fim_inv, "ll": ll, "niter": niter, "flags": flags}
+        if not ref:
+            ref = {kk: v.clone() for kk, v in res.items()}
+            out.append("mean niter %.3f conv %.4f" % (niter.double().mean().item(), (flags & 1).double().mean().item()))
+        else:
+            ok_int = all(torch.equal(ref[kk], res[kk]) for kk in ("tail", "ovf_count"))
+            out.append("suffstats_equal=%s" % ok_int)
+            if "fit" in a.what.split(","):
+                da = (ref["a"] - res["a"]).abs().max().item()
+                dll = ((ref["ll"] - res["ll"]).abs() / ref["ll"].abs().clamp(min=1)).max().item()
+                dfim = ((ref["fim"] - res["fim"]).abs() / ref["fim"].abs().clamp(min=1e-300)).nan_to_num(0).max().item()
+                out.append("niter_equal=%s flags_equal=%s max|da|=%.2e rel dll=%.2e rel dfim=%.2e" % (
+                    torch.equal(ref["niter"], res["niter"]), torch.equal(ref["flags"], res["flags"]), da, dll, dfim))
+        print(" | ".join(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()
