@@ -1,513 +1,668 @@
 // dx_fit_grouped.cu -- K_fit (grouped design): the whole batchglm training schedule for one gene runs
-// inside ONE WARP, from initialisation to finalize, on the per-(gene, group) sufficient statistics that
-// K_ingest produced.  No pass over the count matrix, no host loop, no global synchronisation: genes are
-// independent, so the reference's lock-step loop over all genes
+// inside ONE SUB-WARP (8, 16 or 32 lanes, picked from the number of design groups / coefficients), from
+// initialisation to finalize, on the per-(gene, group) sufficient statistics that K_ingest produced.
+// No pass over the count matrix, no host loop, no global synchronisation: genes are independent, so the
+// reference's lock-step loop over all genes
 //   (/root/reference/diffxpy/testing/tests.py:222-248 -> batchglm numpy Estimator.initialize /
 //    train_sequence("DEFAULT") / finalize; restated in oracle/nb_glm.py, method_b="newton")
 // is exactly equivalent to one independent loop per gene.
 //
 // For design group k (distinct row of [design_loc | design_scale | log size factor], n_k cells):
-//   eta_k = x_k.a + off_k, mu_k = exp(eta_k), zeta_k = z_k.b, r_k = exp(zeta_k)
-//   ll   = sum_k [ sum_j c_k(j) log1p((j - mu_k)/(r_k + mu_k)) + S_k eta_k - n_k r_k log1p(mu_k / r_k) ]
-//          + sum_ovf [ G(r_k, y) - y log1p(mu_k / r_k) ] - sum_i lgamma(y_i + 1)
-//   X^T W X   = sum_k n_k W_k x_k x_k^T,   W_k = mu_k r_k / (r_k + mu_k)
+//   eta_k = x_k.a + off_k, mu_k = exp(eta_k), zeta_k = z_k.b, r_k = exp(zeta_k), l_k = log1p(mu_k / r_k)
+//   ll   = T(r) + sum_k [ S_k (eta_k - zeta_k - l_k) - n_k r_k l_k ] - sum_i lgamma(y_i + 1)
+//   T(r) = sum_k sum_j c_k(j) log(r_k + j) + sum_ovf [ lgamma(r_k + y) - lgamma(r_k) ]
+//   X^T W X    = sum_k n_k W_k x_k x_k^T,   W_k = mu_k r_k / (r_k + mu_k)
 //   X^T W ybar = sum_k x_k ( S_k r_k/(r_k + mu_k) - n_k W_k )
 // with c_k(j) the tail counts #{i in k: y_i > j} (integer counts <= 64) and S_k = sum_{i in k} y_i.
+//
+// Work layout: lane <-> design group for everything per group (exp / log1p / reciprocal are evaluated once
+// per (a, b) state and cached in shared memory, in a current and a trial copy that swap on acceptance);
+// lane <-> matrix row for the p x p LDL^T factorisation and the triangular solves; lane <-> entry of the
+// lower triangle for X^T W X, which is a product-table x weight contraction (the products x_ki x_kj do not
+// depend on the gene and are staged once per CTA).  Coefficient vectors live in registers (lane i holds
+// coefficient i).
 #include "dx_common.cuh"
 #include "dx_internal.h"
 
 namespace {
 
-constexpr int WARPS_PER_CTA = 1;     // one gene per CTA: the block scheduler balances the uneven per-gene cost
+extern __shared__ __align__(16) double smem_d[];
 
-struct Ctx {
-    int K, p, ps, lane, ymax, novf;
-    bool shared_r;                         // every group has the same scale design row (constant dispersion)
-    unsigned long long ovf_groups_lo[4];   // bitmask of groups that own overflow entries (K <= 255)
-    const double* __restrict__ xl;   // [K][p]
-    const double* __restrict__ xs;   // [K][ps]
-    const double* __restrict__ off;  // [K] or null
-    const double* __restrict__ nk;   // [K]
-    const uint32_t* __restrict__ tail;  // [K][64]
+constexpr int PTAB_MAX_DOUBLES = 3072;     // product table budget per CTA (24 KB)
+
+template <int SW> __device__ __forceinline__ double sw_sum(double v, unsigned m) {
+#pragma unroll
+    for (int o = SW / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
+    return v;
+}
+template <int SW> __device__ __forceinline__ double sw_max(double v, unsigned m) {
+#pragma unroll
+    for (int o = SW / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(m, v, o));
+    return v;
+}
+template <int SW> __device__ __forceinline__ int sw_max_i(int v, unsigned m) {
+#pragma unroll
+    for (int o = SW / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(m, v, o));
+    return v;
+}
+template <int SW> __device__ __forceinline__ double sw_bcast(double v, int src, unsigned m) {
+    return __shfl_sync(m, v, src, SW);
+}
+template <int SW> __device__ __forceinline__ bool sw_all(bool v, unsigned m) {
+    return (__ballot_sync(m, v) & m) == m;
+}
+
+// All arrays of a slot are addressed as offsets (in doubles) into smem_d, so every access is a shared-memory
+// instruction and "swap current and trial state" is an integer swap.
+struct Slot {
+    unsigned mask;
+    int sl;                                  // lane inside the sub-warp
+    int K, p, ps, ymax, novf, nent;
+    bool shared_r, has_ptab;
+    // CTA-wide tables
+    int t_xl, t_xs, t_off, t_nk, t_ptab;     // [K][p], [K][ps], [K], [K], [K][nent]
+    const unsigned char *ei, *ej;            // entry -> (row, column) of the lower triangle (shared memory)
+    // per-slot state: a-dependent, b-dependent, (a, b)-dependent; current and trial copies
+    int eta, mu, eta_t, mu_t;
+    int zeta, rr, zeta_t, rr_t;
+    int l1p, irm, l1p_t, irm_t;
+    int S, w1, w2, Cj, A, vec, Hb, Hw, Ainv;
+    double T_r, lgam_const, n_total;
+    unsigned long long ovf_groups[4];        // bitmask of groups that own overflow entries (K <= 255)
+    const uint32_t* __restrict__ tail;       // [K][64]
     const float* __restrict__ oval;
     const uint8_t* __restrict__ ogrp;
-    double *mu, *eta, *rr, *zeta, *S, *w1, *w2; // [K]; w1, w2 are scratch
-    double *A, *L, *rhs, *a, *at;              // p*p, p*p, p, p, p
-    double *b, *bt, *gb, *sb, *Hb, *Lb;        // ps, ps, ps, ps, ps*ps, ps*ps
-    double *Cj;                                // [64] tail counts summed over groups (shared_r only)
-    double lgam_const, n_total;
-    double T_r;                                // part of the likelihood that depends on r only (cached)
 };
 
-__device__ __forceinline__ bool ctx_group_has_ovf(const Ctx& c, int k) {
-    return (c.ovf_groups_lo[k >> 6] >> (k & 63)) & 1ull;
+__device__ __forceinline__ bool slot_group_has_ovf(const Slot& s, int k) {
+    return (s.ovf_groups[k >> 6] >> (k & 63)) & 1ull;
 }
 
 // T(r) = sum_k sum_j c_k(j) log(r_k + j) + sum_ovf [lgamma(r_k + y) - lgamma(r_k)]
-__device__ __noinline__ double compute_T(Ctx& c) {
+template <int SW> __device__ __noinline__ double compute_T(const Slot& s, int o_rr) {
+    const double* rr = smem_d + o_rr;
     double part = 0.0;
-    if (c.shared_r) {
-        const double r = c.rr[0];
+    if (s.shared_r) {
+        const double r = rr[0];
+        const double* Cj = smem_d + s.Cj;
 #pragma unroll 1
-        for (int j = c.lane; j < c.ymax; j += 32) {
-            const double cnt = c.Cj[j];
+        for (int j = s.sl; j < s.ymax; j += SW) {
+            const double cnt = Cj[j];
             if (cnt != 0.0) part += cnt * log(r + (double)j);
         }
     } else {
 #pragma unroll 1
-        for (int k = 0; k < c.K; ++k) {
-            const double r = c.rr[k];
+        for (int k = 0; k < s.K; ++k) {
+            const double r = rr[k];
 #pragma unroll 1
-            for (int j = c.lane; j < c.ymax; j += 32) {
-                const unsigned cnt = c.tail[k * DX_HIST_BINS + j];
+            for (int j = s.sl; j < s.ymax; j += SW) {
+                const unsigned cnt = __ldg(s.tail + k * DX_HIST_BINS + j);
                 if (cnt) part += (double)cnt * log(r + (double)j);
             }
         }
     }
 #pragma unroll 1
-    for (int t = c.lane; t < c.novf; t += 32) {
-        const double y = (double)c.oval[t];
-        const double r = c.rr[c.ogrp[t]];
+    for (int t = s.sl; t < s.novf; t += SW) {
+        const double y = (double)__ldg(s.oval + t);
+        const double r = rr[__ldg(s.ogrp + t)];
         part += dx_lgamma_ratio(r, y) + y * log(r);
     }
-    return dx_warp_sum(part);
+    return sw_sum<SW>(part, s.mask);
 }
 
-// r_k = exp(clip(z_k . b)) and the cached T(r); returns max_k zeta_k
-__device__ __noinline__ double set_b(Ctx& c, const double* bvec) {
+// zeta_k = clip(z_k . b), r_k = exp(zeta_k) into the given buffers, T(r) into T_out; returns max_k zeta_k.
+// breg: lane i holds b_i.
+template <int SW> __device__ __noinline__ double set_b(const Slot& s, double breg, int o_zeta, int o_rr, double& T_out) {
+    double* vec = smem_d + s.vec;
+    if (s.sl < s.ps) vec[s.sl] = breg;
+    __syncwarp(s.mask);
+    const double* xs = smem_d + s.t_xs;
     double zmax = -INFINITY;
 #pragma unroll 1
-    for (int k = c.lane; k < c.K; k += 32) {
+    for (int k = s.sl; k < s.K; k += SW) {
         double z = 0.0;
 #pragma unroll 1
-        for (int i = 0; i < c.ps; ++i) z += c.xs[k * c.ps + i] * bvec[i];
+        for (int i = 0; i < s.ps; ++i) z += xs[k * s.ps + i] * vec[i];
         z = dx_clip(z, DX_ETA_MIN, DX_ETA_MAX);
-        c.zeta[k] = z;
-        c.rr[k] = exp(z);
+        smem_d[o_zeta + k] = z;
+        smem_d[o_rr + k] = exp(z);
         zmax = fmax(zmax, z);
     }
-    __syncwarp();
-    c.T_r = compute_T(c);
-    return dx_warp_max(zmax);
+    __syncwarp(s.mask);
+    T_out = compute_T<SW>(s, o_rr);
+    return sw_max<SW>(zmax, s.mask);
 }
 
-// mu_k = exp(clip(x_k . a + off_k))
-__device__ __noinline__ void compute_mu(Ctx& c, const double* avec) {
+// eta_k = clip(x_k . a + off_k), mu_k = exp(eta_k); areg: lane i holds a_i
+template <int SW> __device__ __noinline__ void set_a(const Slot& s, double areg, int o_eta, int o_mu) {
+    double* vec = smem_d + s.vec;
+    if (s.sl < s.p) vec[s.sl] = areg;
+    __syncwarp(s.mask);
+    const double* xl = smem_d + s.t_xl;
+    const int p = s.p;
 #pragma unroll 1
-    for (int k = c.lane; k < c.K; k += 32) {
-        double e = c.off ? c.off[k] : 0.0;
-#pragma unroll 1
-        for (int i = 0; i < c.p; ++i) e += c.xl[k * c.p + i] * avec[i];
+    for (int k = s.sl; k < s.K; k += SW) {
+        double e = smem_d[s.t_off + k];
+#pragma unroll 3
+        for (int i = 0; i < p; ++i) e += xl[k * p + i] * vec[i];
         e = dx_clip(e, DX_ETA_MIN, DX_ETA_MAX);
-        c.eta[k] = e;
-        c.mu[k] = exp(e);
+        smem_d[o_eta + k] = e;
+        smem_d[o_mu + k] = exp(e);
     }
-    __syncwarp();
+    __syncwarp(s.mask);
 }
 
-// log-likelihood from the current mu / eta / rr / T_r:
-//   ll = T(r) - sum lgamma(y+1) + sum_k [ S_k (eta_k - log(r_k + mu_k)) - n_k r_k log1p(mu_k / r_k) ]
-__device__ __noinline__ double ll_state(Ctx& c) {
+// l_k = log1p(mu_k / r_k), irm_k = 1 / (r_k + mu_k)
+template <int SW> __device__ __noinline__ void refresh(const Slot& s, int o_mu, int o_rr, int o_l1p, int o_irm) {
+#pragma unroll 1
+    for (int k = s.sl; k < s.K; k += SW) {
+        const double m = smem_d[o_mu + k], r = smem_d[o_rr + k];
+        smem_d[o_irm + k] = 1.0 / (r + m);
+        smem_d[o_l1p + k] = log1p(m / r);
+    }
+    __syncwarp(s.mask);
+}
+
+template <int SW> __device__ __forceinline__ double ll_state(const Slot& s, int o_eta, int o_zeta, int o_rr, int o_l1p, double T) {
     double part = 0.0;
 #pragma unroll 1
-    for (int k = c.lane; k < c.K; k += 32) {
-        const double m = c.mu[k], r = c.rr[k];
-        part += c.S[k] * (c.eta[k] - log(r + m)) - c.nk[k] * r * log1p(m / r);
+    for (int k = s.sl; k < s.K; k += SW) {
+        const double l = smem_d[o_l1p + k];
+        part += smem_d[s.S + k] * (smem_d[o_eta + k] - smem_d[o_zeta + k] - l) - smem_d[s.t_nk + k] * smem_d[o_rr + k] * l;
     }
-    return dx_warp_sum(part) + (c.T_r - c.lgam_const);
+    return sw_sum<SW>(part, s.mask) + (T - s.lgam_const);
 }
 
-__device__ double ll_at(Ctx& c, const double* avec) { compute_mu(c, avec); return ll_state(c); }
-
-// A = X^T W X (full symmetric p x p in c.A), rhs = X^T W ybar; needs current mu, rr
-__device__ __noinline__ void loc_terms(Ctx& c) {
+// A = X^T W X (lower triangle, column-major in s.A) from the current state; returns (X^T W ybar)_i in lane i
+template <int SW> __device__ __noinline__ double loc_terms(const Slot& s) {
+    const int K = s.K, p = s.p, nent = s.nent;
+    double* w1 = smem_d + s.w1;
+    double* w2 = smem_d + s.w2;
 #pragma unroll 1
-    for (int k = c.lane; k < c.K; k += 32) {
-        const double m = c.mu[k], r = c.rr[k];
-        const double q = r / (r + m);
-        const double nw = c.nk[k] * m * q;
-        c.w1[k] = nw;
-        c.w2[k] = c.S[k] * q - nw;
+    for (int k = s.sl; k < K; k += SW) {
+        const double q = smem_d[s.rr + k] * smem_d[s.irm + k];
+        const double nw = smem_d[s.t_nk + k] * smem_d[s.mu + k] * q;
+        w1[k] = nw;
+        w2[k] = smem_d[s.S + k] * q - nw;
     }
-    __syncwarp();
-    const int p = c.p, nent = p * (p + 1) / 2;
+    __syncwarp(s.mask);
+    const double* xl = smem_d + s.t_xl;
+    double* A = smem_d + s.A;
 #pragma unroll 1
-    for (int e = c.lane; e < nent; e += 32) {
-        int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-#pragma unroll 1
-        while ((i + 1) * (i + 2) / 2 <= e) ++i;
-#pragma unroll 1
-        while (i * (i + 1) / 2 > e) --i;
-        const int j = e - i * (i + 1) / 2;
+    for (int e = s.sl; e < nent; e += SW) {
+        const int i = s.ei[e], j = s.ej[e];
         double acc = 0.0;
-#pragma unroll 1
-        for (int k = 0; k < c.K; ++k) acc += c.w1[k] * c.xl[k * p + i] * c.xl[k * p + j];
-        c.A[i * p + j] = acc;
-        c.A[j * p + i] = acc;
+        if (s.has_ptab) {
+            const double* P = smem_d + s.t_ptab + e;
+#pragma unroll 4
+            for (int k = 0; k < K; ++k) acc += w1[k] * P[k * nent];
+        } else {
+#pragma unroll 4
+            for (int k = 0; k < K; ++k) acc += w1[k] * (xl[k * p + i] * xl[k * p + j]);
+        }
+        A[j * p + i] = acc;
     }
-#pragma unroll 1
-    for (int i = c.lane; i < p; i += 32) {
-        double acc = 0.0;
-#pragma unroll 1
-        for (int k = 0; k < c.K; ++k) acc += c.w2[k] * c.xl[k * p + i];
-        c.rhs[i] = acc;
+    double rhs = 0.0;
+    if (s.sl < p) {
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) rhs += w2[k] * xl[k * p + s.sl];
     }
-    __syncwarp();
+    __syncwarp(s.mask);
+    return rhs;
 }
 
-// gradient (c.gb) and NEGATIVE Hessian (c.Hb) of ll wrt b at the current mu / rr / zeta
-__device__ __noinline__ void scale_terms(Ctx& c) {
-    const int ps = c.ps;
-    if (c.shared_r) {
+// In-place LDL^T of the n x n SPD matrix whose lower triangle is stored column-major in A (lane <-> row).
+// On exit A[j*n + i] (i > j) holds L_ij (unit lower), the diagonal holds d_j and lane j returns 1/d_j in dinv.
+// Pivot guard of oracle/nb_glm.py:chol_guarded: d_j must be finite and exceed 2^-50 of the input diagonal.
+template <int SW> __device__ __noinline__ bool ldl_factor(double* A, int n, int sl, unsigned mask, double& dinv) {
+    const double m_ii = (sl < n) ? A[sl * n + sl] : 1.0;
+    dinv = 0.0;
+    bool ok = true;
+#pragma unroll 1
+    for (int j = 0; j < n; ++j) {
+        const double d = A[j * n + j];
+        const double mjj = sw_bcast<SW>(m_ii, j, mask);
+        if (!(isfinite(d) && d > DX_CHOL_PIVOT_RTOL * mjj && mjj > 0.0)) { ok = false; break; }
+        const double inv = 1.0 / d;
+        if (sl == j) dinv = inv;
+        const bool act = sl > j && sl < n;
+        double lij = 0.0;
+        if (act) {
+            lij = A[j * n + sl] * inv;
+#pragma unroll 1
+            for (int c = j + 1; c <= sl; ++c) A[c * n + sl] -= lij * A[j * n + c];
+        }
+        __syncwarp(mask);
+        if (act) A[j * n + sl] = lij;     // column j is not read again before the solves
+    }
+    __syncwarp(mask);
+    return ok;
+}
+
+// solve (L D L^T) x = rhs; lane i holds rhs_i / returns x_i
+template <int SW> __device__ __forceinline__ double ldl_solve(const double* A, int n, int sl, unsigned mask, double dinv, double x) {
+#pragma unroll 1
+    for (int j = 0; j < n - 1; ++j) {
+        const double xj = sw_bcast<SW>(x, j, mask);
+        if (sl > j && sl < n) x -= A[j * n + sl] * xj;
+    }
+    x *= dinv;
+#pragma unroll 1
+    for (int j = n - 1; j > 0; --j) {
+        const double xj = sw_bcast<SW>(x, j, mask);
+        if (sl < j) x -= A[sl * n + j] * xj;
+    }
+    return x;
+}
+
+// gradient (returned: lane i holds g_i) and NEGATIVE Hessian (s.Hb, full symmetric ps x ps) of ll wrt b at the
+// current state
+template <int SW> __device__ __noinline__ double scale_terms(const Slot& s) {
+    const int ps = s.ps, K = s.K;
+    const double* xs = smem_d + s.t_xs;
+    double* Hb = smem_d + s.Hb;
+    if (s.shared_r) {
         // constant dispersion: sum the digamma / trigamma differences over all groups at once (lanes over j)
-        const double r = c.rr[0];
+        const double r = smem_d[s.rr];
+        const double* Cj = smem_d + s.Cj;
         double D = 0.0, E = 0.0;
 #pragma unroll 1
-        for (int j = c.lane; j < c.ymax; j += 32) {
-            const double cnt = c.Cj[j];
+        for (int j = s.sl; j < s.ymax; j += SW) {
+            const double cnt = Cj[j];
             if (cnt != 0.0) {
                 const double inv = 1.0 / (r + (double)j);
                 D += cnt * inv;
                 E -= cnt * inv * inv;
             }
         }
-        if (c.novf > 0) {
+        if (s.novf > 0) {
             const double psi_r = dx_digamma(r), psi1_r = dx_trigamma(r);
 #pragma unroll 1
-            for (int t = c.lane; t < c.novf; t += 32) {
-                const double y = (double)c.oval[t];
+            for (int t = s.sl; t < s.novf; t += SW) {
+                const double y = (double)__ldg(s.oval + t);
                 D += dx_digamma(r + y) - psi_r;
                 E += dx_trigamma(r + y) - psi1_r;
             }
         }
         double G = 0.0, H = 0.0;
 #pragma unroll 1
-        for (int k = c.lane; k < c.K; k += 32) {
-            const double m = c.mu[k], n = c.nk[k], S = c.S[k];
-            const double rm = r + m;
-            G += -n * log1p(m / r) + (n * m - S) / rm;
-            H += (n * m * m + r * S) / (rm * rm);
+        for (int k = s.sl; k < K; k += SW) {
+            const double m = smem_d[s.mu + k], n = smem_d[s.t_nk + k], S = smem_d[s.S + k];
+            const double irm = smem_d[s.irm + k];
+            G += -n * smem_d[s.l1p + k] + (n * m - S) * irm;
+            H += (n * m * m + r * S) * (irm * irm);
         }
-        G = r * (dx_warp_sum(G + D));
-        H = G + r * r * dx_warp_sum(E) + r * dx_warp_sum(H);
-        if (c.lane == 0) {
-#pragma unroll 1
-            for (int i = 0; i < ps; ++i) {
-                c.gb[i] = c.xs[i] * G;
-#pragma unroll 1
-                for (int j = 0; j < ps; ++j) c.Hb[i * ps + j] = -c.xs[i] * c.xs[j] * H;
-            }
+        G = r * sw_sum<SW>(G + D, s.mask);
+        H = G + r * r * sw_sum<SW>(E, s.mask) + r * sw_sum<SW>(H, s.mask);
+        for (int e = s.sl; e < ps * ps; e += SW) {
+            const int i = e / ps, j = e - i * ps;
+            Hb[e] = -xs[i] * xs[j] * H;
         }
-        __syncwarp();
-        return;
+        __syncwarp(s.mask);
+        return (s.sl < ps) ? xs[s.sl] * G : 0.0;
     }
     // general scale model: lane <-> group, serial over j (results stay with the lane)
+    double* w1 = smem_d + s.w1;
+    double* w2 = smem_d + s.w2;
 #pragma unroll 1
-    for (int k = c.lane; k < c.K; k += 32) {
-        const double r = c.rr[k];
+    for (int k = s.sl; k < K; k += SW) {
+        const double r = smem_d[s.rr + k];
         double D = 0.0, E = 0.0;
 #pragma unroll 1
-        for (int j = 0; j < c.ymax; ++j) {
-            const unsigned cnt = c.tail[k * DX_HIST_BINS + j];
+        for (int j = 0; j < s.ymax; ++j) {
+            const unsigned cnt = __ldg(s.tail + k * DX_HIST_BINS + j);
             if (cnt) {
                 const double inv = 1.0 / (r + (double)j);
                 D += (double)cnt * inv;
                 E -= (double)cnt * inv * inv;
             }
         }
-        c.w1[k] = D;
-        c.w2[k] = E;
+        w1[k] = D;
+        w2[k] = E;
     }
-    __syncwarp();
-    if (c.novf > 0) {
+    __syncwarp(s.mask);
+    if (s.novf > 0) {
 #pragma unroll 1
-        for (int k = 0; k < c.K; ++k) {
-            if (!ctx_group_has_ovf(c, k)) continue;
-            const double r = c.rr[k];
+        for (int k = 0; k < K; ++k) {
+            if (!slot_group_has_ovf(s, k)) continue;
+            const double r = smem_d[s.rr + k];
             const double psi_r = dx_digamma(r), psi1_r = dx_trigamma(r);
             double D = 0.0, E = 0.0;
 #pragma unroll 1
-            for (int t = c.lane; t < c.novf; t += 32) {
-                if (c.ogrp[t] == k) {
-                    const double y = (double)c.oval[t];
+            for (int t = s.sl; t < s.novf; t += SW) {
+                if (__ldg(s.ogrp + t) == k) {
+                    const double y = (double)__ldg(s.oval + t);
                     D += dx_digamma(r + y) - psi_r;
                     E += dx_trigamma(r + y) - psi1_r;
                 }
             }
-            D = dx_warp_sum(D);
-            E = dx_warp_sum(E);
-            if (c.lane == 0) { c.w1[k] += D; c.w2[k] += E; }
+            D = sw_sum<SW>(D, s.mask);
+            E = sw_sum<SW>(E, s.mask);
+            if (s.sl == 0) { w1[k] += D; w2[k] += E; }
         }
-        __syncwarp();
+        __syncwarp(s.mask);
     }
 #pragma unroll 1
-    for (int k = c.lane; k < c.K; k += 32) {
-        const double r = c.rr[k], m = c.mu[k], n = c.nk[k], S = c.S[k];
-        const double rm = r + m;
-        const double g = r * (c.w1[k] - n * log1p(m / r) + (n * m - S) / rm);
-        const double h = g + r * r * c.w2[k] + r * (n * m * m + r * S) / (rm * rm);
-        c.w1[k] = g;
-        c.w2[k] = h;
+    for (int k = s.sl; k < K; k += SW) {
+        const double r = smem_d[s.rr + k], m = smem_d[s.mu + k], n = smem_d[s.t_nk + k], S = smem_d[s.S + k];
+        const double irm = smem_d[s.irm + k];
+        const double g = r * (w1[k] - n * smem_d[s.l1p + k] + (n * m - S) * irm);
+        const double h = g + r * r * w2[k] + r * (n * m * m + r * S) * (irm * irm);
+        w1[k] = g;
+        w2[k] = h;
     }
-    __syncwarp();
+    __syncwarp(s.mask);
 #pragma unroll 1
-    for (int e = c.lane; e < ps * ps; e += 32) {
+    for (int e = s.sl; e < ps * ps; e += SW) {
         const int i = e / ps, j = e - i * ps;
         double acc = 0.0;
 #pragma unroll 1
-        for (int k = 0; k < c.K; ++k) acc += c.w2[k] * c.xs[k * ps + i] * c.xs[k * ps + j];
-        c.Hb[e] = -acc;
+        for (int k = 0; k < K; ++k) acc += w2[k] * xs[k * ps + i] * xs[k * ps + j];
+        Hb[e] = -acc;
     }
+    double g = 0.0;
+    if (s.sl < ps) {
 #pragma unroll 1
-    for (int i = c.lane; i < ps; i += 32) {
-        double acc = 0.0;
-#pragma unroll 1
-        for (int k = 0; k < c.K; ++k) acc += c.w1[k] * c.xs[k * ps + i];
-        c.gb[i] = acc;
+        for (int k = 0; k < K; ++k) g += w1[k] * xs[k * ps + s.sl];
     }
-    __syncwarp();
+    __syncwarp(s.mask);
+    return g;
 }
 
-// Newton direction s (c.sb) from c.gb and c.Hb (= -Hessian): solve (Hb + lam I) s = gb, lam grows until the
-// guarded Cholesky succeeds (oracle/nb_glm.py:_newton_direction); returns false on non-finite input
-__device__ __noinline__ bool newton_direction(Ctx& c) {
-    const int ps = c.ps;
+// Newton direction (lane i returns s_i) from the gradient (lane registers) and s.Hb (= -Hessian): solve
+// (Hb + lam I) s = g, lam grows until the guarded factorisation succeeds (oracle/nb_glm.py:_newton_direction);
+// returns false on non-finite input
+template <int SW> __device__ __noinline__ bool newton_direction(const Slot& s, double g, double& sb) {
+    const int ps = s.ps;
+    const double* Hb = smem_d + s.Hb;
     if (ps == 1) {
-        const double h = c.Hb[0], g = c.gb[0];
-        if (!(isfinite(h) && isfinite(g))) return false;
-        if (c.lane == 0) c.sb[0] = (h > 0.0) ? g / h : (double)((g > 0.0) - (g < 0.0));
-        __syncwarp();
+        const double h = Hb[0];
+        const double g0 = sw_bcast<SW>(g, 0, s.mask);
+        sb = 0.0;
+        if (!(isfinite(h) && isfinite(g0))) return false;
+        sb = (h > 0.0) ? g0 / h : (double)((g0 > 0.0) - (g0 < 0.0));
         return true;
     }
-    bool fin = true;
+    bool fin = (s.sl < ps) ? isfinite(g) : true;
 #pragma unroll 1
-    for (int e = c.lane; e < ps * ps; e += 32) fin = fin && isfinite(c.Hb[e]);
-#pragma unroll 1
-    for (int i = c.lane; i < ps; i += 32) fin = fin && isfinite(c.gb[i]);
-    if (!__all_sync(DX_FULL_MASK, fin)) return false;
-    const double diag = (c.lane < ps) ? c.Hb[c.lane * ps + c.lane] : 0.0;   // ps <= 32: one diagonal entry per lane
-    const double base = fmax(dx_warp_max(fabs(diag)), 1e-300);
+    for (int e = s.sl; e < ps * ps; e += SW) fin = fin && isfinite(Hb[e]);
+    sb = 0.0;
+    if (!sw_all<SW>(fin, s.mask)) return false;
+    const double diag = (s.sl < ps) ? Hb[s.sl * ps + s.sl] : 0.0;
+    const double base = fmax(sw_max<SW>(fabs(diag), s.mask), 1e-300);
+    double* Hw = smem_d + s.Hw;
     double lam = 0.0;
 #pragma unroll 1
     for (int it = 0; it < 12; ++it) {
-        if (c.lane < ps) c.Hb[c.lane * ps + c.lane] = diag + lam;
-        __syncwarp();
-        const bool ok = chol_warp(c.Hb, c.Lb, ps, c.lane);
-        __syncwarp();
+#pragma unroll 1
+        for (int e = s.sl; e < ps * ps; e += SW) Hw[e] = Hb[e];
+        __syncwarp(s.mask);
+        if (s.sl < ps) Hw[s.sl * ps + s.sl] = diag + lam;
+        __syncwarp(s.mask);
+        double dinv;
+        const bool ok = ldl_factor<SW>(Hw, ps, s.sl, s.mask, dinv);
         if (ok) {
-            if (c.lane == 0) chol_solve_serial(c.Lb, ps, c.gb, c.sb);
-            __syncwarp();
+            sb = ldl_solve<SW>(Hw, ps, s.sl, s.mask, dinv, (s.sl < ps) ? g : 0.0);
             return true;
         }
         lam = (lam == 0.0) ? base * 1e-6 : lam * 10.0;
     }
-#pragma unroll 1
-    for (int i = c.lane; i < ps; i += 32) { const double g = c.gb[i]; c.sb[i] = (double)((g > 0.0) - (g < 0.0)); }
-    __syncwarp();
+    sb = (s.sl < ps) ? (double)((g > 0.0) - (g < 0.0)) : 0.0;
     return true;
 }
 
-// safeguarded Newton in b with a fixed (oracle/nb_glm.py:_b_step_newton); c.b is updated in place; returns ll at
-// the final b.  Requires c.mu / c.eta to hold mu(a) and f_cur = ll(a, c.b).
-__device__ __noinline__ double scale_newton(Ctx& c, double f_cur, int max_iter, double xtol) {
-    double zmax = set_b(c, c.b);
+__device__ __forceinline__ void swap_i(int& a, int& b) { const int t = a; a = b; b = t; }
+
+// safeguarded Newton in b with a fixed (oracle/nb_glm.py:_b_step_newton).  breg (lane i holds b_i) and the current
+// b / (a, b) state are updated in place; returns ll at the final b.  f_cur = ll at entry.
+template <int SW> __device__ __noinline__ double scale_newton(Slot& s, double& breg, double& zmax, double f_cur, int max_iter, double xtol) {
     if (zmax >= DX_ETA_SCALE_FROZEN) return f_cur;
     double f = f_cur;
 #pragma unroll 1
     for (int it = 0; it < max_iter; ++it) {
-        // (rr, zeta, T_r correspond to c.b here)
-        scale_terms(c);
-        if (!newton_direction(c)) break;
-        double smax = 0.0;
-#pragma unroll 1
-        for (int i = c.lane; i < c.ps; i += 32) smax = fmax(smax, fabs(c.sb[i]));
-        smax = dx_warp_max(smax);
+        const double g = scale_terms<SW>(s);
+        double sb;
+        if (!newton_direction<SW>(s, g, sb)) break;
+        const double smax = sw_max<SW>((s.sl < s.ps) ? fabs(sb) : 0.0, s.mask);
         const double sc = (smax > DX_NEWTON_MAX_STEP) ? DX_NEWTON_MAX_STEP / smax : 1.0;
-        double pred = 0.0;
-#pragma unroll 1
-        for (int i = c.lane; i < c.ps; i += 32) pred += c.gb[i] * (sc * c.sb[i]);
-        pred = dx_warp_sum(pred);
+        const double pred = sw_sum<SW>((s.sl < s.ps) ? g * (sc * sb) : 0.0, s.mask);
         // converged: the step is below xtol or its predicted gain is below the resolution of the likelihood
         if (sc * smax <= xtol || !(pred > DX_NEWTON_GAIN_RTOL * fabs(f))) break;
-        double t = 1.0, f_try = f;
+        double t = 1.0, f_try = f, bt = breg, T_t = 0.0, zmax_t = zmax;
         bool accepted = false;
 #pragma unroll 1
         for (int h = 0; h < DX_NEWTON_MAX_HALVINGS; ++h) {
-#pragma unroll 1
-            for (int i = c.lane; i < c.ps; i += 32)
-                c.bt[i] = dx_clip(c.b[i] + t * (sc * c.sb[i]), DX_ETA_MIN, DX_ETA_MAX);
-            __syncwarp();
-            zmax = set_b(c, c.bt);
-            f_try = ll_state(c);
+            bt = dx_clip(breg + t * (sc * sb), DX_ETA_MIN, DX_ETA_MAX);
+            zmax_t = set_b<SW>(s, bt, s.zeta_t, s.rr_t, T_t);
+            refresh<SW>(s, s.mu, s.rr_t, s.l1p_t, s.irm_t);
+            f_try = ll_state<SW>(s, s.eta, s.zeta_t, s.rr_t, s.l1p_t, T_t);
             if (isfinite(f_try) && f_try >= f) { accepted = true; break; }
             t *= 0.5;
         }
         if (!accepted) break;
-#pragma unroll 1
-        for (int i = c.lane; i < c.ps; i += 32) c.b[i] = c.bt[i];
-        __syncwarp();
+        breg = bt;
+        swap_i(s.zeta, s.zeta_t); swap_i(s.rr, s.rr_t); swap_i(s.l1p, s.l1p_t); swap_i(s.irm, s.irm_t);
+        s.T_r = T_t;
+        zmax = zmax_t;
         f = f_try;
         if (zmax >= DX_ETA_SCALE_FROZEN) break;
     }
-    set_b(c, c.b);
     return f;
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 16)
-dx_fit_grouped_kernel(int64_t n_genes, int K, int p, int ps,
-                      const double* __restrict__ xu_loc, const double* __restrict__ xu_scale,
-                      const double* __restrict__ offset, const double* __restrict__ n_k,
-                      const double* __restrict__ pinv_loc, const int32_t* __restrict__ loc_group, int KL,
-                      const uint32_t* __restrict__ tail_all, const int32_t* __restrict__ ovf_count,
-                      const int64_t* __restrict__ indptr, const float* __restrict__ ovf_val,
-                      const uint8_t* __restrict__ ovf_group, dx_fit_opts opts,
-                      double* __restrict__ a_var, double* __restrict__ b_var, double* __restrict__ fim_inv,
-                      double* __restrict__ ll_out, double* __restrict__ jac_out,
-                      int32_t* __restrict__ niter_out, int32_t* __restrict__ flags_out, int per_warp_doubles) {
-    extern __shared__ __align__(16) double smem_d[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t g = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
-    if (g >= n_genes) return;
-    double* base = smem_d + (size_t)warp * per_warp_doubles;
-    Ctx c;
-    c.K = K; c.p = p; c.ps = ps; c.lane = lane;
-    c.xl = xu_loc; c.xs = xu_scale; c.off = offset; c.nk = n_k;
-    c.tail = tail_all + g * (int64_t)K * DX_HIST_BINS;
-    c.novf = ovf_count[g];
-    c.oval = ovf_val + indptr[g];
-    c.ogrp = ovf_group + indptr[g];
-    c.mu = base; c.eta = c.mu + K; c.rr = c.eta + K; c.zeta = c.rr + K; c.S = c.zeta + K; c.w1 = c.S + K; c.w2 = c.w1 + K;
-    c.A = c.w2 + K; c.L = c.A + p * p; c.rhs = c.L + p * p; c.a = c.rhs + p; c.at = c.a + p;
-    c.b = c.at + p; c.bt = c.b + ps; c.gb = c.bt + ps; c.sb = c.gb + ps; c.Hb = c.sb + ps; c.Lb = c.Hb + ps * ps;
-    c.Cj = c.Lb + ps * ps;
+struct FitArgs {
+    int64_t n_genes;
+    int K, p, ps, KL;
+    const double *xu_loc, *xu_scale, *offset, *n_k, *pinv_loc;
+    const int32_t* loc_group;
+    const uint32_t* tail_all;
+    const int32_t* ovf_count;
+    const int64_t* indptr;
+    const float* ovf_val;
+    const uint8_t* ovf_group;
+    dx_fit_opts opts;
+    double *a_var, *b_var, *fim_inv, *ll_out, *jac_out;
+    int32_t *niter_out, *flags_out;
+    int slot_doubles, table_doubles, nent, has_ptab, ainv_extra;
+};
+
+template <int SW>
+__global__ void __launch_bounds__(256)
+dx_fit_grouped_kernel(const FitArgs P) {
+    constexpr int SLOTS_PER_WARP = 32 / SW;
+    const int K = P.K, p = P.p, ps = P.ps, nent = P.nent;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int slots_per_cta = (blockDim.x >> 5) * SLOTS_PER_WARP;
+
+    // ---- CTA tables: design rows, offsets, group sizes, product table, entry decode --------------------------
+    const int t_xl = 0, t_xs = t_xl + K * p, t_off = t_xs + K * ps, t_nk = t_off + K, t_ptab = t_nk + K;
+    const int t_dec = t_ptab + (P.has_ptab ? K * nent : 0);          // entry decode bytes live here
+    unsigned char* dec_i = reinterpret_cast<unsigned char*>(smem_d + t_dec);
+    unsigned char* dec_j = dec_i + ((nent + 7) & ~7);
+    for (int i = tid; i < K * p; i += blockDim.x) smem_d[t_xl + i] = P.xu_loc[i];
+    for (int i = tid; i < K * ps; i += blockDim.x) smem_d[t_xs + i] = P.xu_scale[i];
+    for (int i = tid; i < K; i += blockDim.x) {
+        smem_d[t_off + i] = P.offset ? P.offset[i] : 0.0;
+        smem_d[t_nk + i] = P.n_k[i];
+    }
+    for (int e = tid; e < nent; e += blockDim.x) {
+        int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+        while ((i + 1) * (i + 2) / 2 <= e) ++i;
+        while (i * (i + 1) / 2 > e) --i;
+        dec_i[e] = (unsigned char)i;
+        dec_j[e] = (unsigned char)(e - i * (i + 1) / 2);
+    }
+    __syncthreads();
+    if (P.has_ptab) {
+        for (int t = tid; t < K * nent; t += blockDim.x) {
+            const int k = t / nent, e = t - k * nent;
+            smem_d[t_ptab + t] = smem_d[t_xl + k * p + dec_i[e]] * smem_d[t_xl + k * p + dec_j[e]];
+        }
+    }
+    __syncthreads();
+
+    const int slot = warp * SLOTS_PER_WARP + lane / SW;
+    const int64_t g = (int64_t)blockIdx.x * slots_per_cta + slot;
+    if (g >= P.n_genes) return;
+
+    Slot s;
+    s.sl = lane % SW;
+    s.mask = (SW == 32) ? 0xffffffffu : (((1u << SW) - 1u) << ((lane / SW) * SW));
+    s.K = K; s.p = p; s.ps = ps; s.nent = nent;
+    s.has_ptab = P.has_ptab != 0;
+    s.t_xl = t_xl; s.t_xs = t_xs; s.t_off = t_off; s.t_nk = t_nk; s.t_ptab = t_ptab;
+    s.ei = dec_i; s.ej = dec_j;
+    {
+        int o = P.table_doubles + slot * P.slot_doubles;
+        s.eta = o; o += K; s.mu = o; o += K; s.eta_t = o; o += K; s.mu_t = o; o += K;
+        s.zeta = o; o += K; s.rr = o; o += K; s.zeta_t = o; o += K; s.rr_t = o; o += K;
+        s.l1p = o; o += K; s.irm = o; o += K; s.l1p_t = o; o += K; s.irm_t = o; o += K;
+        s.S = o; o += K;
+        s.w1 = o; s.Ainv = o; o += K; s.w2 = o; o += K; s.Cj = o; o += DX_HIST_BINS + P.ainv_extra;   // Ainv aliases w1 | w2 | Cj
+        s.A = o; o += p * p;
+        s.vec = o; o += (p > ps ? p : ps);
+        s.Hb = o; o += ps * ps; s.Hw = o; o += ps * ps;
+    }
+    const int sl = s.sl;
+    const unsigned mask = s.mask;
+    s.tail = P.tail_all + g * (int64_t)K * DX_HIST_BINS;
+    s.novf = P.ovf_count[g];
+    s.oval = P.ovf_val + P.indptr[g];
+    s.ogrp = P.ovf_group + P.indptr[g];
     {   // constant dispersion model <=> every group carries the same scale design row
         bool same = true;
 #pragma unroll 1
-        for (int k = lane; k < K; k += 32)
+        for (int k = sl; k < K; k += SW)
 #pragma unroll 1
-            for (int i = 0; i < ps; ++i) same = same && (xu_scale[k * ps + i] == xu_scale[i]);
-        c.shared_r = __all_sync(DX_FULL_MASK, same);
+            for (int i = 0; i < ps; ++i) same = same && (smem_d[t_xs + k * ps + i] == smem_d[t_xs + i]);
+        s.shared_r = sw_all<SW>(same, mask);
     }
-    c.T_r = 0.0;
+    s.T_r = 0.0;
 
     // ---- sufficient statistics of the gene ---------------------------------------------------------
+    double* Sk = smem_d + s.S;
+    double* w1 = smem_d + s.w1;
+    double* w2 = smem_d + s.w2;
     int ymax = 0;
     double lgc = 0.0;
-    double cj0 = 0.0, cj1 = 0.0;
-#pragma unroll 1
-    for (int k = 0; k < K; ++k) {
-        // lanes over j (two bins each): S_k = sum_j c_k(j), sum y^2 = sum_j c(j)(2j+1), sum lgamma(y+1) = sum_j c(j) log(j+1)
-        const unsigned c0 = c.tail[k * DX_HIST_BINS + lane], c1 = c.tail[k * DX_HIST_BINS + 32 + lane];
-        double s = (double)c0 + (double)c1;
-        double q = (double)c0 * (2.0 * lane + 1.0) + (double)c1 * (2.0 * (lane + 32) + 1.0);
-        cj0 += (double)c0;
-        cj1 += (double)c1;
-        if (c0) ymax = max(ymax, lane + 1);
-        if (c1) ymax = max(ymax, lane + 33);
-        s = dx_warp_sum(s);
-        q = dx_warp_sum(q);
-        if (lane == 0) { c.S[k] = s; c.w2[k] = q; }
-    }
-    c.Cj[lane] = cj0;
-    c.Cj[lane + 32] = cj1;
-    if (cj0 != 0.0) lgc += cj0 * log((double)lane + 1.0);
-    if (cj1 != 0.0) lgc += cj1 * log((double)lane + 33.0);
+    {
+        constexpr int R = DX_HIST_BINS / SW;
+        double cj[R];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ymax = max(ymax, __shfl_xor_sync(DX_FULL_MASK, ymax, o));
-    c.ymax = ymax;
-    c.ovf_groups_lo[0] = c.ovf_groups_lo[1] = c.ovf_groups_lo[2] = c.ovf_groups_lo[3] = 0ull;
-    __syncwarp();
-    if (c.novf > 0) {
+        for (int r = 0; r < R; ++r) cj[r] = 0.0;
 #pragma unroll 1
         for (int k = 0; k < K; ++k) {
-            double s = 0.0, q = 0.0;
+            // lanes over j: S_k = sum_j c_k(j), sum y^2 = sum_j c(j)(2j+1), sum lgamma(y+1) = sum_j c(j) log(j+1)
+            double sk = 0.0, qk = 0.0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int j = sl + r * SW;
+                const unsigned c = __ldg(s.tail + k * DX_HIST_BINS + j);
+                const double cd = (double)c;
+                sk += cd;
+                qk += cd * (2.0 * j + 1.0);
+                cj[r] += cd;
+                if (c) ymax = max(ymax, j + 1);
+            }
+            sk = sw_sum<SW>(sk, mask);
+            qk = sw_sum<SW>(qk, mask);
+            if (sl == 0) { Sk[k] = sk; w2[k] = qk; }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int j = sl + r * SW;
+            smem_d[s.Cj + j] = cj[r];
+            if (cj[r] != 0.0) lgc += cj[r] * log((double)j + 1.0);
+        }
+    }
+    s.ymax = sw_max_i<SW>(ymax, mask);
+    s.ovf_groups[0] = s.ovf_groups[1] = s.ovf_groups[2] = s.ovf_groups[3] = 0ull;
+    __syncwarp(mask);
+    if (s.novf > 0) {
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) {
+            double sk = 0.0, qk = 0.0;
             bool any = false;
 #pragma unroll 1
-            for (int t = lane; t < c.novf; t += 32) {
-                if (c.ogrp[t] == k) {
-                    const double y = (double)c.oval[t];
-                    s += y; q += y * y; lgc += lgamma(y + 1.0); any = true;
+            for (int t = sl; t < s.novf; t += SW) {
+                if (__ldg(s.ogrp + t) == k) {
+                    const double y = (double)__ldg(s.oval + t);
+                    sk += y; qk += y * y; lgc += lgamma(y + 1.0); any = true;
                 }
             }
-            s = dx_warp_sum(s); q = dx_warp_sum(q);
-            if (__any_sync(DX_FULL_MASK, any)) {
-                c.ovf_groups_lo[k >> 6] |= (1ull << (k & 63));
-                if (lane == 0) { c.S[k] += s; c.w2[k] += q; }
+            sk = sw_sum<SW>(sk, mask); qk = sw_sum<SW>(qk, mask);
+            if (__ballot_sync(mask, any) & mask) {
+                s.ovf_groups[k >> 6] |= (1ull << (k & 63));
+                if (sl == 0) { Sk[k] += sk; w2[k] += qk; }
             }
         }
-        __syncwarp();
+        __syncwarp(mask);
     }
-    c.lgam_const = dx_warp_sum(lgc);
+    s.lgam_const = sw_sum<SW>(lgc, mask);
     double n_total = 0.0, sum_all = 0.0, m_sf = 0.0, e2_sf = 0.0;
 #pragma unroll 1
     for (int k = 0; k < K; ++k) {
-        const double isf = offset ? exp(-offset[k]) : 1.0;
-        n_total += n_k[k];
-        sum_all += c.S[k];
-        m_sf += c.S[k] * isf;
-        e2_sf += c.w2[k] * isf * isf;
+        const double isf = P.offset ? exp(-smem_d[t_off + k]) : 1.0;
+        n_total += smem_d[t_nk + k];
+        sum_all += Sk[k];
+        m_sf += Sk[k] * isf;
+        e2_sf += w2[k] * isf * isf;
     }
-    c.n_total = n_total;
+    s.n_total = n_total;
     int flags = 0;
-    if (sum_all == 0.0 && c.novf == 0) flags |= DX_FLAG_ALL_ZERO;
+    if (sum_all == 0.0 && s.novf == 0) flags |= DX_FLAG_ALL_ZERO;
+    __syncwarp(mask);
 
-    // ---- initialize (batchglm init_par) -----------------------------------------------------------
+    // ---- initialize (batchglm init_par); lane i holds a_i / b_i ------------------------------------
+    const dx_fit_opts& opts = P.opts;
+    double areg = 0.0, breg = 0.0;
     if (opts.init_a == DX_INIT_STANDARD) {
-#pragma unroll 1
-        for (int i = lane; i < p; i += 32) c.a[i] = (i == 0) ? dx_clip(log(sum_all / n_total), DX_ETA_MIN, DX_ETA_MAX) : 0.0;
+        areg = (sl == 0) ? dx_clip(log(sum_all / n_total), DX_ETA_MIN, DX_ETA_MAX) : 0.0;
     } else if (opts.init_a == DX_INIT_CLOSED_FORM) {
         // batchglm closedform_glm_mean: log of the mean of x / size_factor over every distinct LOCATION design
         // row, pushed through the pseudo-inverse of those rows (np.linalg.lstsq in the reference)
+        const int KL = P.KL;
 #pragma unroll 1
-        for (int l = lane; l < KL; l += 32) {
+        for (int l = sl; l < KL; l += SW) {
             double num = 0.0, den = 0.0;
 #pragma unroll 1
             for (int k = 0; k < K; ++k) {
-                if ((loc_group ? loc_group[k] : k) == l) {
-                    num += c.S[k] * (offset ? exp(-offset[k]) : 1.0);
-                    den += n_k[k];
+                if ((P.loc_group ? P.loc_group[k] : k) == l) {
+                    num += Sk[k] * (P.offset ? exp(-smem_d[t_off + k]) : 1.0);
+                    den += smem_d[t_nk + k];
                 }
             }
-            c.w1[l] = log(num / den + DX_TINY);
+            w1[l] = log(num / den + DX_TINY);
         }
-        __syncwarp();
-#pragma unroll 1
-        for (int i = lane; i < p; i += 32) {
+        __syncwarp(mask);
+        if (sl < p) {
             double acc = 0.0;
 #pragma unroll 1
-            for (int l = 0; l < KL; ++l) acc += pinv_loc[i * KL + l] * c.w1[l];
-            c.a[i] = dx_clip(acc, DX_ETA_MIN, DX_ETA_MAX);
+            for (int l = 0; l < KL; ++l) acc += P.pinv_loc[sl * KL + l] * w1[l];
+            areg = dx_clip(acc, DX_ETA_MIN, DX_ETA_MAX);
         }
-        __syncwarp();
-    } else if (opts.init_a == DX_INIT_ALL_ZERO) {
-#pragma unroll 1
-        for (int i = lane; i < p; i += 32) c.a[i] = 0.0;
-    } else {
-#pragma unroll 1
-        for (int i = lane; i < p; i += 32) c.a[i] = dx_clip(a_var[(int64_t)i * n_genes + g], DX_ETA_MIN, DX_ETA_MAX);
+        __syncwarp(mask);
+    } else if (opts.init_a == DX_INIT_GIVEN) {
+        if (sl < p) areg = dx_clip(P.a_var[(int64_t)sl * P.n_genes + g], DX_ETA_MIN, DX_ETA_MAX);
     }
     if (opts.init_b == DX_INIT_STANDARD) {
         const double m = m_sf / n_total;
         const double v = e2_sf / n_total - m * m;
         const double denom = fmax(v - m, 2.2227587494850775e-162);
-#pragma unroll 1
-        for (int i = lane; i < ps; i += 32) c.b[i] = (i == 0) ? dx_clip(log(m * m / denom + DX_TINY), DX_ETA_MIN, DX_ETA_MAX) : 0.0;
-    } else if (opts.init_b == DX_INIT_ALL_ZERO) {
-#pragma unroll 1
-        for (int i = lane; i < ps; i += 32) c.b[i] = 0.0;
-    } else {
-#pragma unroll 1
-        for (int i = lane; i < ps; i += 32) c.b[i] = dx_clip(b_var[(int64_t)i * n_genes + g], DX_ETA_MIN, DX_ETA_MAX);
+        breg = (sl == 0) ? dx_clip(log(m * m / denom + DX_TINY), DX_ETA_MIN, DX_ETA_MAX) : 0.0;
+    } else if (opts.init_b == DX_INIT_GIVEN) {
+        if (sl < ps) breg = dx_clip(P.b_var[(int64_t)sl * P.n_genes + g], DX_ETA_MIN, DX_ETA_MAX);
     }
-    __syncwarp();
 
     // ---- train (batchglm numpy EstimatorGlm.train, per-gene form) -----------------------------------
     const bool train_loc = opts.train_loc != 0, train_scale = opts.train_scale != 0;
     const int freq = train_scale ? (train_loc ? opts.update_b_freq : 1) : 0x7fffffff;
     int epochs_until_b = freq;
     bool loc_conv = false, fully = false;
-    set_b(c, c.b);
-    double nll = -ll_at(c, c.a);
+    double zmax = set_b<SW>(s, breg, s.zeta, s.rr, s.T_r);
+    set_a<SW>(s, areg, s.eta, s.mu);
+    refresh<SW>(s, s.mu, s.rr, s.l1p, s.irm);
+    double nll = -ll_state<SW>(s, s.eta, s.zeta, s.rr, s.l1p, s.T_r);
     int step = 0;
 #pragma unroll 1
     while (!fully && step < opts.max_steps) {
@@ -515,49 +670,42 @@ dx_fit_grouped_kernel(int64_t n_genes, int K, int p, int ps,
         bool b_updated = false;
         if (epochs_until_b == 0) {
             if (train_scale) {
-                const double bold = (lane < ps) ? c.b[lane] : 0.0;    // ps <= 32: one coefficient per lane
-                compute_mu(c, c.a);
-                const double f = scale_newton(c, -nll, opts.newton_max_iter, opts.newton_xtol);
+                const double bold = breg;
+                const double f = scale_newton<SW>(s, breg, zmax, -nll, opts.newton_max_iter, opts.newton_xtol);
                 const double nll_prop = -f;
                 if (!isfinite(nll_prop)) flags |= DX_FLAG_NONFINITE;
                 if (isfinite(nll_prop) && !(nll_prop > nll)) {
                     nll_new = nll_prop;
                 } else {
-                    if (lane < ps) c.b[lane] = bold;
-                    __syncwarp();
-                    set_b(c, c.b);
+                    breg = bold;
+                    zmax = set_b<SW>(s, breg, s.zeta, s.rr, s.T_r);
+                    refresh<SW>(s, s.mu, s.rr, s.l1p, s.irm);
                 }
             }
             epochs_until_b = freq;
             b_updated = true;
         } else {
             if (train_loc && !loc_conv) {
-                compute_mu(c, c.a);
-                loc_terms(c);
-                const bool ok = chol_warp(c.A, c.L, p, lane);
-                bool fin = true;
-#pragma unroll 1
-                for (int i = lane; i < p; i += 32) fin = fin && isfinite(c.rhs[i]);
-                fin = __all_sync(DX_FULL_MASK, fin);
+                const double rhs = loc_terms<SW>(s);
+                double dinv;
+                const bool ok = ldl_factor<SW>(smem_d + s.A, p, sl, mask, dinv);
+                const bool fin = sw_all<SW>((sl < p) ? isfinite(rhs) : true, mask);
+                double atry = areg;
                 if (ok && fin) {
-                    if (lane == 0) chol_solve_serial(c.L, p, c.rhs, c.rhs);
-                    __syncwarp();
-#pragma unroll 1
-                    for (int i = lane; i < p; i += 32) c.at[i] = dx_clip(c.a[i] + c.rhs[i], DX_ETA_MIN, DX_ETA_MAX);
+                    const double delta = ldl_solve<SW>(smem_d + s.A, p, sl, mask, dinv, (sl < p) ? rhs : 0.0);
+                    atry = dx_clip(areg + delta, DX_ETA_MIN, DX_ETA_MAX);
                 } else {
                     flags |= DX_FLAG_SINGULAR_FIM;
-#pragma unroll 1
-                    for (int i = lane; i < p; i += 32) c.at[i] = c.a[i];
                 }
-                __syncwarp();
-                const double nll_prop = -ll_at(c, c.at);
+                set_a<SW>(s, atry, s.eta_t, s.mu_t);
+                refresh<SW>(s, s.mu_t, s.rr, s.l1p_t, s.irm_t);
+                const double nll_prop = -ll_state<SW>(s, s.eta_t, s.zeta, s.rr, s.l1p_t, s.T_r);
                 if (!isfinite(nll_prop)) flags |= DX_FLAG_NONFINITE;
                 if (isfinite(nll_prop) && !(nll_prop > nll)) {
-#pragma unroll 1
-                    for (int i = lane; i < p; i += 32) c.a[i] = c.at[i];
+                    areg = atry;
+                    swap_i(s.eta, s.eta_t); swap_i(s.mu, s.mu_t); swap_i(s.l1p, s.l1p_t); swap_i(s.irm, s.irm_t);
                     nll_new = nll_prop;
                 }
-                __syncwarp();
             }
             epochs_until_b -= 1;
         }
@@ -575,60 +723,66 @@ dx_fit_grouped_kernel(int64_t n_genes, int K, int p, int ps,
     if (fully) flags |= DX_FLAG_CONVERGED;
 
     // ---- finalize (batchglm Estimator.finalize) -----------------------------------------------------
-    const double zmax = set_b(c, c.b);
     if (zmax >= DX_ETA_SCALE_FROZEN) flags |= DX_FLAG_SCALE_FROZEN;
-    compute_mu(c, c.a);
-    loc_terms(c);
-    double jac = 0.0;
+    const double rhs_f = loc_terms<SW>(s);
+    const double gb_f = scale_terms<SW>(s);                 // (may use w1 / w2: X^T W X is already in s.A)
+    double jac = ((sl < p) ? fabs(rhs_f) : 0.0) + ((sl < ps) ? fabs(gb_f) : 0.0);
+    jac = sw_sum<SW>(jac, mask) / n_total;
+    double dinv_f;
+    const bool okf = ldl_factor<SW>(smem_d + s.A, p, sl, mask, dinv_f);
+    double* Ainv = smem_d + s.Ainv;                         // aliases w1 | w2 | Cj: none of them is needed any more
+    if (okf) {
 #pragma unroll 1
-    for (int i = lane; i < p; i += 32) jac += fabs(c.rhs[i]);
-    const bool okf = chol_warp(c.A, c.L, p, lane);
-    __syncwarp();
-    // inverse: lane col solves L L^T x = e_col serially into its own column of c.A (A is no longer needed)
-#pragma unroll 1
-    for (int col = lane; col < p; col += 32) {
-        double* x = c.A + col * p;     // column stored as a row; the inverse is symmetric
-        if (okf) {
-#pragma unroll 1
-            for (int i = 0; i < p; ++i) {
-                double s = (i == col) ? 1.0 : 0.0;
-#pragma unroll 1
-                for (int k = 0; k < i; ++k) s -= c.L[i * p + k] * x[k];
-                x[i] = s / c.L[i * p + i];
-            }
-#pragma unroll 1
-            for (int i = p - 1; i >= 0; --i) {
-                double s = x[i];
-#pragma unroll 1
-                for (int k = i + 1; k < p; ++k) s -= c.L[k * p + i] * x[k];
-                x[i] = s / c.L[i * p + i];
-            }
-        } else {
-#pragma unroll 1
-            for (int i = 0; i < p; ++i) x[i] = NAN;
+        for (int c = 0; c < p; ++c) {
+            const double x = ldl_solve<SW>(smem_d + s.A, p, sl, mask, dinv_f, (sl == c) ? 1.0 : 0.0);
+            if (sl < p) Ainv[c * p + sl] = x;
         }
     }
-    __syncwarp();
-    double* fo = fim_inv + g * (int64_t)p * p;
+    __syncwarp(mask);
+    double* fo = P.fim_inv + g * (int64_t)p * p;
 #pragma unroll 1
-    for (int e = lane; e < p * p; e += 32) {
+    for (int e = sl; e < p * p; e += SW) {
         const int i = e / p, j = e - i * p;
-        fo[e] = okf ? 0.5 * (c.A[i * p + j] + c.A[j * p + i]) : NAN;
+        fo[e] = okf ? 0.5 * (Ainv[i * p + j] + Ainv[j * p + i]) : NAN;
     }
-    scale_terms(c);
-#pragma unroll 1
-    for (int i = lane; i < ps; i += 32) jac += fabs(c.gb[i]);
-    jac = dx_warp_sum(jac) / n_total;
-#pragma unroll 1
-    for (int i = lane; i < p; i += 32) a_var[(int64_t)i * n_genes + g] = c.a[i];
-#pragma unroll 1
-    for (int i = lane; i < ps; i += 32) b_var[(int64_t)i * n_genes + g] = c.b[i];
-    if (lane == 0) {
-        ll_out[g] = -nll;
-        jac_out[g] = jac;
-        niter_out[g] = step;
-        flags_out[g] = flags;
+    if (sl < p) P.a_var[(int64_t)sl * P.n_genes + g] = areg;
+    if (sl < ps) P.b_var[(int64_t)sl * P.n_genes + g] = breg;
+    if (sl == 0) {
+        P.ll_out[g] = -nll;
+        P.jac_out[g] = jac;
+        P.niter_out[g] = step;
+        P.flags_out[g] = flags;
     }
+}
+
+template <int SW>
+cudaError_t launch_sw(FitArgs& A, int sm_count, cudaStream_t stream) {
+    const int slots_per_warp = 32 / SW;
+    const size_t table_bytes = (size_t)A.table_doubles * 8, slot_bytes = (size_t)A.slot_doubles * 8;
+    // warps per CTA: maximise the number of resident gene slots per SM under the shared-memory budget
+    const size_t budget = 220 * 1024;
+    int best_w = 1;
+    long best_res = -1;
+    const int cand[] = {1, 2, 3, 4, 6, 8};
+    for (int w : cand) {
+        const size_t need = table_bytes + (size_t)w * slots_per_warp * slot_bytes;
+        if (need > budget) continue;
+        long ctas = (long)(budget / need);
+        if (ctas > 32) ctas = 32;
+        long warps = ctas * w;
+        if (warps > 40) warps = 40;          // beyond ~40 warps the register file is the limit anyway
+        const long res = warps * 1000 - w;   // ties -> fewer warps per CTA (finer-grained scheduling)
+        if (res > best_res) { best_res = res; best_w = w; }
+    }
+    if (best_res < 0) return cudaErrorInvalidConfiguration;
+    const int slots_per_cta = best_w * slots_per_warp;
+    const size_t smem = table_bytes + (size_t)slots_per_cta * slot_bytes;
+    cudaError_t e = cudaFuncSetAttribute(dx_fit_grouped_kernel<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)((A.n_genes + slots_per_cta - 1) / slots_per_cta);
+    (void)sm_count;
+    dx_fit_grouped_kernel<SW><<<grid, best_w * 32, smem, stream>>>(A);
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -641,13 +795,20 @@ cudaError_t dx_launch_fit_grouped(int64_t n_genes, int K, int p, int ps,
                                   double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
                                   int32_t* niter, int32_t* flags, cudaStream_t stream) {
     if (n_genes <= 0) return cudaSuccess;
-    const int per_warp = 7 * K + 2 * p * p + 3 * p + 4 * ps + 2 * ps * ps + DX_HIST_BINS + 2;
-    const size_t smem = (size_t)per_warp * WARPS_PER_CTA * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(dx_fit_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    const unsigned grid = (unsigned)((n_genes + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
-    dx_fit_grouped_kernel<<<grid, WARPS_PER_CTA * 32, smem, stream>>>(
-        n_genes, K, p, ps, xu_loc, xu_scale, offset, n_k, pinv_loc, loc_group, n_loc_groups, tail, ovf_count, indptr, ovf_val, ovf_group,
-        *opts, a_var, b_var, fim_inv, ll, jac, niter, flags, per_warp);
-    return cudaGetLastError();
+    FitArgs A;
+    A.n_genes = n_genes; A.K = K; A.p = p; A.ps = ps; A.KL = n_loc_groups;
+    A.xu_loc = xu_loc; A.xu_scale = xu_scale; A.offset = offset; A.n_k = n_k; A.pinv_loc = pinv_loc; A.loc_group = loc_group;
+    A.tail_all = tail; A.ovf_count = ovf_count; A.indptr = indptr; A.ovf_val = ovf_val; A.ovf_group = ovf_group;
+    A.opts = *opts;
+    A.a_var = a_var; A.b_var = b_var; A.fim_inv = fim_inv; A.ll_out = ll; A.jac_out = jac; A.niter_out = niter; A.flags_out = flags;
+    A.nent = p * (p + 1) / 2;
+    A.has_ptab = (A.nent * K <= PTAB_MAX_DOUBLES) ? 1 : 0;
+    A.table_doubles = K * p + K * ps + 2 * K + (A.has_ptab ? K * A.nent : 0) + 2 * ((A.nent + 7) / 8) + 2;
+    A.ainv_extra = (p * p > 2 * K + DX_HIST_BINS) ? p * p - (2 * K + DX_HIST_BINS) : 0;
+    A.slot_doubles = 13 * K + 2 * K + DX_HIST_BINS + A.ainv_extra + p * p + (p > ps ? p : ps) + 2 * ps * ps;
+    A.slot_doubles = (A.slot_doubles + 1) & ~1;
+    A.table_doubles = (A.table_doubles + 1) & ~1;
+    if (K <= 8 && p <= 8 && ps <= 8) return launch_sw<8>(A, 0, stream);
+    if (K <= 16 && p <= 16 && ps <= 16) return launch_sw<16>(A, 0, stream);
+    return launch_sw<32>(A, 0, stream);
 }
