@@ -13,6 +13,8 @@
 // the CTA histogram with a skewed (conflict-free) column walk; no block barrier is needed for that.  The rare
 // bins YP < y <= 64 go through shared atomics on the CTA histogram; everything else (non-integer, negative,
 // > 64) is an "overflow" entry that is copied out in a deterministic order by a second, L2-resident pass.
+#include <atomic>
+#include <cstdlib>
 #include "dx_common.cuh"
 #include "dx_internal.h"
 
@@ -51,6 +53,11 @@ __device__ __forceinline__ int dx_ld_stream(const int32_t* p) {
 #endif
 }
 
+// fire-and-forget shared-memory add on a 32-bit shared-space address
+__device__ __forceinline__ void dx_red_shared(uint32_t addr, unsigned inc) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(inc) : "memory");
+}
+
 __device__ __forceinline__ bool dx_classify(float v, int k, int K, int& y) {
     // true -> direct bin y (1..64); false -> overflow candidate (or ignorable when v == 0 / skipped cell)
     y = (int)v;
@@ -74,6 +81,8 @@ dx_ingest_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const int3
     uint32_t* priv_warp = s_priv + warp * NWA * 32;
     uint32_t* priv_t = priv_warp + lane;
     const unsigned row_mask = (unsigned)(NWA - 1) << 5;   // word-row offset (in words) of counter j: (j >> 2) * 32 == (8j) & row_mask
+    const unsigned ysh3 = ysh_u + 3u;
+    const uint32_t priv_addr = (uint32_t)__cvta_generic_to_shared(priv_t);
 
     for (int i = tid; i < NWARP * NWA * 32; i += T) s_priv[i] = 0u;    // every flush leaves the counters zero again
     for (int64_t g = blockIdx.x; g < n_genes; g += gridDim.x) {
@@ -123,10 +132,10 @@ dx_ingest_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const int3
                     const int y = __float2int_rz(v[u]);
                     const unsigned ym1 = (unsigned)(y - 1);
                     const bool fast = (__int2float_rn(y) == v[u]) && (ym1 < YP) && (k[u] < (unsigned)K);
-                    const unsigned j8 = ((k[u] << ysh_u) + ym1) << 3;            // 8 * counter index
+                    const unsigned j8 = (k[u] << ysh3) + (ym1 << 3);             // 8 * counter index
                     // branch-free: a non-private entry adds 0 to an in-range word
                     const unsigned inc = fast ? (1u << (j8 & 24u)) : 0u;
-                    atomicAdd(priv_t + (j8 & row_mask), inc);
+                    dx_red_shared(priv_addr + ((j8 & row_mask) << 2), inc);
                     slow = slow || !fast;
                 }
                 if (slow) {     // rare: counts above the private range, non-counts, padding
@@ -229,6 +238,304 @@ dx_ingest_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const int3
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// K_ingest, TMA variant (K <= 32, 16-byte aligned shard): one WARP per gene (dynamic gene queue), persistent
+// CTAs.  Each warp owns a ring of NS stages in shared memory that lane 0 keeps full with cp.async.bulk
+// (TMA bulk copies completing on an mbarrier), across gene boundaries, so ~NS*2 KB per warp are always in
+// flight from HBM without holding registers; the streamed data never enters L1, which is left to the
+// cell -> group table.  The group gathers of tile t+1 are issued before tile t is counted (software pipeline),
+// so their L1/L2 latency hides behind a full tile of work.  Counters / histogram / flush as in the CTA kernel,
+// but private to the warp: no block barrier anywhere.
+// ---------------------------------------------------------------------------------------------------------
+#ifndef DX_TMA_NS
+#define DX_TMA_NS 2
+#endif
+#ifndef DX_TMA_TILE
+#define DX_TMA_TILE 256
+#endif
+constexpr int TW = 16;            // max warps per CTA
+constexpr int NS = DX_TMA_NS;     // ring stages per warp
+constexpr int TILE = DX_TMA_TILE; // elements per stage
+constexpr int TU = TILE / 32;     // elements per lane and tile
+constexpr int NG = 8;             // gene descriptors in flight per warp (>= NS + 2)
+
+__device__ __forceinline__ uint32_t dx_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dx_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void dx_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void dx_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void dx_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void dx_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+struct GeneDesc {          // written once per gene by the issue side, read once by the consume side
+    long long start, end;  // the gene's [start, end) in the shard
+    int gene, pad;
+};
+struct TileInfo {          // registers, per fetched tile
+    int slot, last;        // gene descriptor slot; 1 when this is the last tile of the gene
+};
+
+__global__ void __launch_bounds__(TW * 32, 1)
+dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const int32_t* __restrict__ rows,
+                     const float* __restrict__ vals, const uint8_t* __restrict__ cell_group, int K, int ysh, int NW, int NWA,
+                     uint32_t* __restrict__ hist_out, int32_t* __restrict__ ovf_count,
+                     float* __restrict__ ovf_val, uint8_t* __restrict__ ovf_group, unsigned int* __restrict__ queue,
+                     int warp_bytes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* base = smem_raw + (size_t)warp * warp_bytes;
+    float* ring_v = reinterpret_cast<float*>(base);                               // [NS][TILE]
+    int32_t* ring_r = reinterpret_cast<int32_t*>(base + NS * TILE * 4);           // [NS][TILE]
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(base + 2 * NS * TILE * 4);     // [K][64]
+    uint32_t* s_priv = s_hist + K * DX_HIST_BINS;                                 // [NWA][32]
+    GeneDesc* s_gene = reinterpret_cast<GeneDesc*>(s_priv + NWA * 32);            // [NG]
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_gene + NG);   // [NS]
+    const unsigned YP = (ysh >= 0) ? (1u << ysh) : 0u;
+    const unsigned ysh_u = (ysh >= 0) ? (unsigned)ysh : 0u;
+    const unsigned n_priv = (unsigned)K * YP;
+    const unsigned row_mask = (unsigned)(NWA - 1) << 5;
+    const unsigned ysh3 = ysh_u + 3u;
+    const uint32_t priv_addr = dx_smem_u32(s_priv + lane);
+    const uint32_t bar0 = dx_smem_u32(s_bar);
+    const uint32_t ringv0 = dx_smem_u32(ring_v), ringr0 = dx_smem_u32(ring_r);
+
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < NS; ++st) dx_mbar_init(bar0 + 8u * st, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    for (int i = lane; i < NWA * 32; i += 32) s_priv[i] = 0u;
+    for (int i = lane; i < K * DX_HIST_BINS; i += 32) s_hist[i] = 0u;
+    __syncwarp();
+
+    // ---- issue side (warp-uniform state; lane 0 performs the side effects) ----------------------------------
+    unsigned issued = 0, consumed = 0, g_head = 0, g_tail = 0;
+    bool done_issue = false;
+    int i_tiles = 0;                  // tiles of the current issue gene not yet issued
+    const float* i_pv = vals;         // next tile of the issue gene
+    const int32_t* i_pr = rows;
+    int i_left = 0;                   // elements (padded to 4) of the issue gene not yet issued
+    auto issue_one = [&]() {
+        if (i_tiles == 0) {
+            unsigned gq = 0;
+            if (lane == 0) gq = atomicAdd(queue, 1u);
+            gq = __shfl_sync(DX_FULL_MASK, gq, 0);
+            if ((int64_t)gq >= n_genes) { done_issue = true; return; }
+            const long long st_ = __ldg(indptr + gq), en_ = __ldg(indptr + gq + 1);
+            if (lane == 0) {
+                GeneDesc d;
+                d.start = st_; d.end = en_; d.gene = (int)gq; d.pad = 0;
+                s_gene[g_head % NG] = d;
+            }
+            ++g_head;
+            const long long a0 = st_ & ~3ll;
+            i_left = (int)(((en_ + 3ll) & ~3ll) - a0);
+            i_tiles = (i_left + TILE - 1) / TILE;
+            if (i_tiles < 1) i_tiles = 1;
+            i_pv = vals + a0;
+            i_pr = rows + a0;
+        }
+        const unsigned st = issued % NS;
+        const int n = i_left > TILE ? TILE : i_left;
+        if (lane == 0) {
+            const uint32_t bar = bar0 + 8u * st;
+            if (n > 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic reads of the stage
+                dx_mbar_expect_tx(bar, (uint32_t)(8 * n));
+                dx_bulk_g2s(ringv0 + st * (TILE * 4), i_pv, (uint32_t)(4 * n), bar);
+                dx_bulk_g2s(ringr0 + st * (TILE * 4), i_pr, (uint32_t)(4 * n), bar);
+            } else {
+                dx_mbar_arrive(bar);
+            }
+        }
+        i_pv += TILE; i_pr += TILE;
+        i_left -= n;
+        --i_tiles;
+        ++issued;
+    };
+
+    // ---- consume side ---------------------------------------------------------------------------------------
+    float v0[TU], v1[TU];
+    int r0[TU], r1[TU];
+    unsigned k0[TU], k1[TU];
+    TileInfo m0, m1;
+    unsigned n_ovf = 0;
+    int since_flush = 0;
+    int c_tiles = 0;                  // tiles of the current consume gene not yet fetched
+    int c_lo = 0, c_hi = 0;           // valid element range of the next tile, relative to the tile start
+    int c_slot = 0;
+
+    // waits for the next tile, copies it to registers (masked to the gene), frees the stage, refills the ring
+    // and issues the group gathers
+    auto fetch = [&](float (&v)[TU], int (&r)[TU], unsigned (&k)[TU], TileInfo& m) {
+        const unsigned st = consumed % NS;
+        dx_mbar_wait(bar0 + 8u * st, (consumed / NS) & 1u);     // acquire: also orders lane 0's descriptor write
+        if (c_tiles == 0) {
+            c_slot = (int)(g_tail % NG);
+            const GeneDesc d = s_gene[c_slot];
+            ++g_tail;
+            const long long a0 = d.start & ~3ll;
+            c_lo = (int)(d.start - a0);
+            c_hi = (int)(d.end - a0);
+            const int span = (int)(((d.end + 3ll) & ~3ll) - a0);
+            c_tiles = (span + TILE - 1) / TILE;
+            if (c_tiles < 1) c_tiles = 1;
+        }
+        const float* sv = ring_v + st * TILE + lane;
+        const int32_t* sr = ring_r + st * TILE + lane;
+        if (c_lo <= 0 && c_hi >= TILE) {                        // interior tile: no masking
+#pragma unroll
+            for (int u = 0; u < TU; ++u) { v[u] = sv[32 * u]; r[u] = sr[32 * u]; }
+        } else {
+#pragma unroll
+            for (int u = 0; u < TU; ++u) {
+                const int pos = lane + 32 * u;
+                const bool ok = (pos >= c_lo) && (pos < c_hi);
+                v[u] = ok ? sv[32 * u] : 0.0f;
+                r[u] = ok ? sr[32 * u] : 0;
+            }
+        }
+        __syncwarp();
+        ++consumed;
+        --c_tiles;
+        c_lo -= TILE; c_hi -= TILE;
+        m.slot = c_slot;
+        m.last = (c_tiles == 0) ? 1 : 0;
+        if (!done_issue && issued - consumed < NS) issue_one();
+#pragma unroll
+        for (int u = 0; u < TU; ++u) k[u] = __ldg(cell_group + (unsigned)r[u]);
+    };
+
+    auto flush = [&]() {
+        __syncwarp();
+        if (lane < NW) {
+            uint32_t* row = s_priv + lane * 32;
+            unsigned lo = 0, hi = 0;
+#pragma unroll 8
+            for (int c = 0; c < 32; ++c) {
+                const int col = (c + lane) & 31;
+                const unsigned x = row[col];
+                row[col] = 0u;
+                lo += x & 0x00ff00ffu;
+                hi += (x >> 8) & 0x00ff00ffu;
+            }
+            const unsigned cnt[4] = {lo & 0xffffu, hi & 0xffffu, lo >> 16, hi >> 16};
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const unsigned idx = 4u * lane + b;
+                if (cnt[b] && idx < n_priv) s_hist[(idx >> ysh_u) * DX_HIST_BINS + (idx & (YP - 1u))] += cnt[b];
+            }
+        }
+        __syncwarp();
+        since_flush = 0;
+    };
+
+    auto process = [&](const float (&v)[TU], const int (&r)[TU], const unsigned (&k)[TU], const TileInfo& m) {
+        if (since_flush + TU > 255) flush();
+        since_flush += TU;
+        bool slow = false;
+#pragma unroll
+        for (int u = 0; u < TU; ++u) {
+            const int y = __float2int_rz(v[u]);
+            const unsigned ym1 = (unsigned)(y - 1);
+            const bool fast = (__int2float_rn(y) == v[u]) && (ym1 < YP) && (k[u] < (unsigned)K);
+            const unsigned j8 = (k[u] << ysh3) + (ym1 << 3);
+            const unsigned inc = fast ? (1u << (j8 & 24u)) : 0u;
+            dx_red_shared(priv_addr + ((j8 & row_mask) << 2), inc);
+            slow = slow || !fast;
+        }
+        if (slow) {
+#pragma unroll
+            for (int u = 0; u < TU; ++u) {
+                const int y = __float2int_rz(v[u]);
+                const unsigned ym1 = (unsigned)(y - 1);
+                const bool isbin = (ym1 < (unsigned)DX_HIST_BINS) && (__int2float_rn(y) == v[u]) && (k[u] < (unsigned)K);
+                if (isbin) {
+                    if (ym1 >= YP) atomicAdd(&s_hist[k[u] * DX_HIST_BINS + ym1], 1u);
+                } else if (v[u] != 0.0f && k[u] < (unsigned)K) {
+                    ++n_ovf;
+                }
+            }
+        }
+        if (!m.last) return;
+        // ---- the gene is complete: tail counts, overflow entries, reset ----------------------------------------
+        flush();
+        const GeneDesc gd = s_gene[m.slot];      // still valid: at most NS + 1 < NG genes are in flight
+        const int64_t g = gd.gene;
+        uint32_t* out = hist_out + g * (int64_t)K * DX_HIST_BINS;
+#pragma unroll 1
+        for (int kk = 0; kk < K; ++kk) {
+            const unsigned lo = s_hist[kk * DX_HIST_BINS + lane], hi = s_hist[kk * DX_HIST_BINS + 32 + lane];
+            s_hist[kk * DX_HIST_BINS + lane] = 0u;
+            s_hist[kk * DX_HIST_BINS + 32 + lane] = 0u;
+            unsigned plo = lo, phi = hi;   // inclusive prefix sums
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned a = __shfl_up_sync(DX_FULL_MASK, plo, o), b = __shfl_up_sync(DX_FULL_MASK, phi, o);
+                if (lane >= o) { plo += a; phi += b; }
+            }
+            const unsigned tot_lo = __shfl_sync(DX_FULL_MASK, plo, 31), tot_hi = __shfl_sync(DX_FULL_MASK, phi, 31);
+            out[kk * DX_HIST_BINS + 32 + lane] = tot_hi - phi + hi;
+            out[kk * DX_HIST_BINS + lane] = tot_hi + (tot_lo - plo + lo);
+        }
+        const unsigned total = __reduce_add_sync(DX_FULL_MASK, n_ovf);
+        if (lane == 0) ovf_count[g] = (int32_t)total;
+        if (total) {
+            unsigned inc = n_ovf;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(DX_FULL_MASK, inc, o); if (lane >= o) inc += t; }
+            // lane l re-visits exactly the entries it counted: i = a0 + l (mod 32), in ascending order
+            int64_t pos = gd.start + (inc - n_ovf);
+            for (int64_t i = (gd.start & ~3ll) + lane; i < gd.end; i += 32) {
+                if (i < gd.start) continue;
+                const float vv = __ldg(vals + i);
+                const int kk = __ldg(cell_group + __ldg(rows + i));
+                int y;
+                if (!dx_classify(vv, kk, K, y) && vv != 0.0f && kk < K) {
+                    ovf_val[pos] = vv;
+                    ovf_group[pos] = (uint8_t)kk;
+                    ++pos;
+                }
+            }
+        }
+        n_ovf = 0;
+        __syncwarp();
+    };
+
+    while (!done_issue && issued < (unsigned)NS) issue_one();
+    if (issued == 0) return;
+    fetch(v0, r0, k0, m0);
+    for (;;) {      // ping-pong between the two register sets: tile t+1 is fetched (and its gathers issued) before t is counted
+        bool more = consumed < issued;
+        if (more) fetch(v1, r1, k1, m1);
+        process(v0, r0, k0, m0);
+        if (!more) break;
+        more = consumed < issued;
+        if (more) fetch(v0, r0, k0, m0);
+        process(v1, r1, k1, m1);
+        if (!more) break;
+    }
+}
+
 // per-gene sum(x), sum(x^2) of the raw shard (optionally of x / size factor): init of the per-cell path
 __global__ void __launch_bounds__(256)
 dx_gene_moments_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const int32_t* __restrict__ rows,
@@ -257,6 +564,19 @@ int dx_ingest_private_bins(int K) {
     return yp;
 }
 
+// dynamic gene queues: a ring of zero-initialised counters so that concurrent launches (different streams)
+// never share one
+__device__ unsigned int g_dx_queue_slots[256];
+
+cudaError_t dx_queue_acquire(cudaStream_t stream, unsigned int** out) {
+    static std::atomic<unsigned> seq{0};
+    void* base = nullptr;
+    cudaError_t e = cudaGetSymbolAddress(&base, g_dx_queue_slots);
+    if (e != cudaSuccess) return e;
+    *out = static_cast<unsigned int*>(base) + (seq.fetch_add(1u) & 255u);
+    return cudaMemsetAsync(*out, 0, sizeof(unsigned int), stream);
+}
+
 cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,
                              const uint8_t* cell_group, int K, uint32_t* hist, int32_t* ovf_count,
                              float* ovf_val, uint8_t* ovf_group, int sm_count, cudaStream_t stream) {
@@ -267,8 +587,34 @@ cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32
     const int NW = (K * YP + 3) / 4;        // packed counter words per thread (<= 32)
     int NWA = 1;                            // rows allocated: next power of two (index masking keeps every update in range)
     while (NWA < NW) NWA <<= 1;
+    cudaError_t e;
+    // ---- TMA variant: warp per gene, per-warp bulk-copy ring (needs 16-byte aligned arrays, modest K) ----------
+    static const char* impl_env = getenv("DXB200_INGEST_IMPL");          // tuning hooks (development only)
+    static const char* warps_env = getenv("DXB200_INGEST_WARPS");
+    const bool aligned = ((reinterpret_cast<uintptr_t>(vals) | reinterpret_cast<uintptr_t>(rows)) & 15u) == 0;
+    int warp_bytes = 2 * NS * TILE * 4 + K * DX_HIST_BINS * 4 + NWA * 32 * 4 + NG * (int)sizeof(GeneDesc) + NS * 8;
+    warp_bytes = (warp_bytes + 15) & ~15;
+    int warps = (220 * 1024) / warp_bytes;
+    if (warps > TW) warps = TW;
+    if (warps_env && atoi(warps_env) > 0 && atoi(warps_env) < warps) warps = atoi(warps_env);
+    const bool want_tma = !(impl_env && impl_env[0] == 'c');
+    if (want_tma && aligned && warps >= 6 && n_genes < 2147483647LL) {
+        unsigned int* queue = nullptr;
+        e = dx_queue_acquire(stream, &queue);
+        if (e != cudaSuccess) return e;
+        const size_t smem = (size_t)warps * warp_bytes;
+        e = cudaFuncSetAttribute(dx_ingest_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int64_t grid = sm_count;
+        const int64_t need = (n_genes + warps - 1) / warps;
+        if (grid > need) grid = need;
+        dx_ingest_tma_kernel<<<(unsigned)grid, warps * 32, smem, stream>>>(n_genes, indptr, rows, vals, cell_group, K, ysh, NW,
+                                                                          NWA, hist, ovf_count, ovf_val, ovf_group, queue, warp_bytes);
+        return cudaGetLastError();
+    }
+    // ---- CTA-per-gene variant (any K, any alignment) -------------------------------------------------------------
     const size_t smem = (size_t)K * DX_HIST_BINS * 4 + (T + 4) * 4 + (size_t)NWARP * NWA * 32 * 4 + 16;
-    cudaError_t e = cudaFuncSetAttribute(dx_ingest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(dx_ingest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dx_ingest_kernel, T, smem);

@@ -7,6 +7,8 @@
 #define DX_INGEST_THREADS 128
 
 int dx_ingest_private_bins(int K);
+// zero-initialised work-queue counter for one launch (ring of 256 slots, safe across concurrent streams)
+cudaError_t dx_queue_acquire(cudaStream_t stream, unsigned int** out);
 cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,
                              const uint8_t* cell_group, int K, uint32_t* hist, int32_t* ovf_count,
                              float* ovf_val, uint8_t* ovf_group, int sm_count, cudaStream_t stream);
