@@ -145,6 +145,12 @@ int dx_t_test_moments(int64_t n, const double* mu0, const double* mu1, const dou
     return DX_OK;
 }
 
+int dx_bh_qvalues(int64_t n, const double* pval, double* qval, double* work, void* stream) {
+    DX_CHECK(n >= 0 && pval && qval && work, "dx_bh_qvalues: bad arguments");
+    DX_CUDA(dx_launch_bh(n, pval, qval, work, (cudaStream_t)stream), "dx_bh_qvalues");
+    return DX_OK;
+}
+
 int dx_two_group_tests(int64_t n_genes, double n0, double n1,
                        const uint32_t* hist, const int32_t* ovf_count, const int64_t* indptr,
                        const float* ovf_val, const uint8_t* ovf_group,

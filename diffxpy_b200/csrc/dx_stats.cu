@@ -261,6 +261,115 @@ dx_two_group_kernel(int64_t G, double n0, double n1, const uint32_t* __restrict_
 
 inline unsigned grid1d(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Benjamini-Hochberg q-values (correction.py:5-24 -> statsmodels multipletests(method="fdr_bh") arithmetic:
+// p sorted ascending, q_k = p_k / (k / n), running minimum from the right, clip at 1) WITHOUT a sort:
+//   c_i = #{j : p_j <= p_i}  (the largest rank inside a tie block),  t_i = p_i / (c_i / n),
+//   q_i = min(1, min_{j : p_j >= p_i} t_j)      -- identical values, two O(G^2 / SMs) all-pairs passes over
+// shared-memory tiles (G = 2e4: ~4e8 compares per pass).  NaN p-values are excluded from n and stay NaN.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int BH_T = 128, BH_R = 4, BH_TILE = 1024, BH_JS = 8;   // threads, p-values per thread, j-tile, j-slices (grid.y)
+constexpr int BH_ST = 1024;                                       // threads of the single scan CTA
+
+// order-preserving integer image of a p-value (p >= 0 or NaN): non-negative doubles sort like their bit patterns;
+// NaN becomes the largest key, so it never satisfies "<= valid"
+__device__ __forceinline__ long long dx_p_key(double p) {
+    return (p == p) ? __double_as_longlong(p + 0.0) : 0x7fffffffffffffffLL;
+}
+
+// pass 1 (all pairs, register-tiled): cnt_i += #{j in slice : p_j <= p_i}; slice 0 also clears the sorted table
+__global__ void __launch_bounds__(BH_T)
+dx_bh_rank_kernel(int64_t G, const double* __restrict__ p, int* __restrict__ cnt, double* __restrict__ tsorted) {
+    __shared__ long long sk[BH_TILE];
+    const int tid = threadIdx.x;
+    const int64_t i0 = (int64_t)blockIdx.x * (BH_T * BH_R) + tid;
+    long long ki[BH_R];
+    int c[BH_R];
+#pragma unroll
+    for (int r = 0; r < BH_R; ++r) {
+        const int64_t i = i0 + r * BH_T;
+        ki[r] = (i < G) ? dx_p_key(p[i]) : -1;
+        c[r] = 0;
+        if (blockIdx.y == 0 && i < G) tsorted[i] = INFINITY;
+    }
+    const int64_t per = ((G + BH_JS - 1) / BH_JS + BH_TILE - 1) / BH_TILE * BH_TILE;
+    const int64_t j_lo = (int64_t)blockIdx.y * per, j_hi = (j_lo + per < G) ? j_lo + per : G;
+    for (int64_t t0 = j_lo; t0 < j_hi; t0 += BH_TILE) {
+#pragma unroll
+        for (int u = 0; u < BH_TILE / BH_T; ++u) {
+            const int64_t j = t0 + tid + u * BH_T;
+            sk[tid + u * BH_T] = (j < j_hi) ? dx_p_key(p[j]) : 0x7fffffffffffffffLL;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int j = 0; j < BH_TILE; ++j) {
+            const long long kj = sk[j];
+#pragma unroll
+            for (int r = 0; r < BH_R; ++r) c[r] += (kj <= ki[r]) ? 1 : 0;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < BH_R; ++r) {
+        const int64_t i = i0 + r * BH_T;
+        if (i < G && c[r]) atomicAdd(cnt + i, c[r]);
+    }
+}
+
+// n = #{non-NaN}; t_i = p_i / (cnt_i / n) goes to slot cnt_i - 1 of the table sorted by p (a tie block shares its
+// last slot and one value; the other slots of the block stay +inf)
+__global__ void __launch_bounds__(256)
+dx_bh_scatter_kernel(int64_t G, const double* __restrict__ p, const int* __restrict__ cnt, double* __restrict__ tsorted) {
+    __shared__ int s_cnt[8];
+    const int tid = threadIdx.x;
+    int nv = 0;
+    for (int64_t j = tid; j < G; j += 256) { const double v = p[j]; nv += (v == v) ? 1 : 0; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nv += __shfl_xor_sync(DX_FULL_MASK, nv, o);
+    if ((tid & 31) == 0) s_cnt[tid >> 5] = nv;
+    __syncthreads();
+    int n = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) n += s_cnt[w];
+    const int64_t i = (int64_t)blockIdx.x * 256 + tid;
+    if (i < G) {
+        const double pi = p[i];
+        if (pi == pi) tsorted[cnt[i] - 1] = pi / ((double)cnt[i] / (double)n);      // statsmodels: p_sorted / (rank / n)
+    }
+}
+
+// running minimum from the right over the sorted table (one CTA), then q_i = min(1, table[cnt_i - 1])
+__global__ void __launch_bounds__(BH_ST)
+dx_bh_scan_kernel(int64_t G, const double* __restrict__ p, const int* __restrict__ cnt, double* __restrict__ tsorted,
+                  double* __restrict__ q) {
+    __shared__ double s_min[BH_ST];
+    const int tid = threadIdx.x;
+    const int64_t L = (G + BH_ST - 1) / BH_ST;
+    const int64_t lo = (int64_t)tid * L, hi = (lo + L < G) ? lo + L : G;
+    double m = INFINITY;
+    for (int64_t j = lo; j < hi; ++j) m = fmin(m, tsorted[j]);
+    s_min[tid] = m;
+    __syncthreads();
+    // suffix minimum over the chunk minima: s_min[t] = min over chunks >= t (Hillis-Steele)
+    for (int o = 1; o < BH_ST; o <<= 1) {
+        const double other = (tid + o < BH_ST) ? s_min[tid + o] : INFINITY;
+        __syncthreads();
+        s_min[tid] = fmin(s_min[tid], other);
+        __syncthreads();
+    }
+    double run = (tid + 1 < BH_ST) ? s_min[tid + 1] : INFINITY;
+    for (int64_t j = hi - 1; j >= lo; --j) {
+        run = fmin(run, tsorted[j]);
+        tsorted[j] = run;
+    }
+    __syncthreads();
+    for (int64_t i = tid; i < G; i += BH_ST) {
+        const double pi = p[i];
+        q[i] = (pi == pi) ? fmin(tsorted[cnt[i] - 1], 1.0) : NAN;
+    }
+}
+
 }  // namespace
 
 cudaError_t dx_launch_wald(int64_t n, const double* theta, const double* sd, double* pval, double* logp, cudaStream_t s) {
@@ -305,5 +414,18 @@ cudaError_t dx_launch_two_group(int64_t G, double n0, double n1, const uint32_t*
     if (G <= 0) return cudaSuccess;
     dx_two_group_kernel<<<(unsigned)G, TG_T, 0, s>>>(G, n0, n1, tail, ovf_count, indptr, ovf_val, ovf_group, do_rank,
                                                      out, u1x2, tie, flags);
+    return cudaGetLastError();
+}
+
+cudaError_t dx_launch_bh(int64_t n, const double* pval, double* qval, double* work, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    // work: n doubles (table sorted by p) followed by n ints (cnt)
+    int* cnt = reinterpret_cast<int*>(work + n);
+    cudaError_t e = cudaMemsetAsync(cnt, 0, (size_t)n * sizeof(int), s);
+    if (e != cudaSuccess) return e;
+    const dim3 grid((unsigned)((n + BH_T * BH_R - 1) / (BH_T * BH_R)), BH_JS);
+    dx_bh_rank_kernel<<<grid, BH_T, 0, s>>>(n, pval, cnt, work);
+    dx_bh_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, pval, cnt, work);
+    dx_bh_scan_kernel<<<1, BH_ST, 0, s>>>(n, pval, cnt, work, qval);
     return cudaGetLastError();
 }

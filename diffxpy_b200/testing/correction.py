@@ -6,25 +6,31 @@ statsmodels.stats.multitest.multipletests(method="fdr_bh") on the non-NaN p-valu
 import numpy as np
 import torch
 
-from ..device import cuda_device
+from .. import _lib
+from ..device import cuda_device, ptr, stream_ptr
+
+BH_KERNEL_MAX = 65536     # above this the all-pairs kernel loses to a device sort
 
 
 def bh_device(p):
     """Benjamini-Hochberg on a float64 CUDA vector; NaNs are excluded from n and stay NaN."""
-    q = torch.full_like(p, float("nan"))
-    ok = ~torch.isnan(p)
-    pv = p[ok]
-    n = pv.shape[0]
-    if n == 0:
+    if p.shape[0] <= BH_KERNEL_MAX:
+        p = p.contiguous()
+        q = torch.empty_like(p)
+        work = torch.empty((p.shape[0] * 3 + 1) // 2, dtype=torch.float64, device=p.device)   # n doubles + n int32
+        _lib.call("dx_bh_qvalues", p.shape[0], ptr(p), ptr(q), ptr(work), stream_ptr())
         return q
-    ps, order = torch.sort(pv, stable=True)
-    ecdf = torch.arange(1, n + 1, dtype=torch.float64, device=p.device) / float(n)
-    qs = ps / ecdf
+    # sort path, no host synchronisation: NaNs sort last and are masked out of the running minimum
+    g = p.shape[0]
+    ps, order = torch.sort(p, stable=True)
+    bad = torch.isnan(ps)
+    n = (g - bad.sum()).to(torch.float64)                       # 0-d tensor: true division like numpy's
+    ecdf = torch.arange(1, g + 1, dtype=torch.float64, device=p.device) / n
+    qs = torch.where(bad, torch.full_like(ps, float("inf")), ps / ecdf)
     qs = torch.flip(torch.cummin(torch.flip(qs, [0]), 0).values, [0])
-    qs = torch.clamp(qs, max=1.0)
-    out = torch.empty_like(qs)
-    out[order] = qs
-    q[ok] = out
+    qs = torch.where(bad, torch.full_like(ps, float("nan")), torch.clamp(qs, max=1.0))
+    q = torch.empty_like(qs)
+    q[order] = qs
     return q
 
 

@@ -139,6 +139,11 @@ int dx_two_coef_z(int64_t n, const double* t0, const double* t1, const double* s
 int dx_t_test_moments(int64_t n, const double* mu0, const double* mu1, const double* var0, const double* var1,
                       double n0, double n1, double* pval, void* stream);
 
+/* Benjamini-Hochberg q-values of the non-NaN p-values (correction.py:5-24 -> statsmodels fdr_bh arithmetic,
+ * bit-identical values; all-pairs formulation without a sort, meant for n up to ~1e5).
+ * work: 12 * n bytes (n doubles + n int32), 8-byte aligned. */
+int dx_bh_qvalues(int64_t n, const double* pval, double* qval, double* work, void* stream);
+
 /* ---- K_twogroup: det.py:1545-1620 (Welch t) and det.py:1672-1743 (Mann-Whitney U) from the
  * 2-group sufficient statistics of dx_group_suffstats (group 0 = first sample, group 1 = second).
  * out[G][DX_TG_NCOL] doubles; u1x2 / tie are the exact integers 2*U1 and sum(t^3 - t). */

@@ -83,6 +83,20 @@ def test_bh_on_device(de, gold):
     p = gold["bh_p"].copy()
     p[[3, 50]] = np.nan
     np.testing.assert_allclose(correction.correct(p), ost.bh_correct(p), rtol=1e-14, atol=0, equal_nan=True)
+    # heavy ties (rank-test p-values repeat), exact zeros / ones, NaNs: the sort-free kernel and the sort path agree bit for bit
+    rng = np.random.default_rng(5)
+    p = np.round(rng.uniform(size=5000), 2)
+    p[::97] = np.nan
+    p[1::101] = 0.0
+    want = ost.bh_correct(p)
+    np.testing.assert_array_equal(correction.correct(p), want)
+    old = correction.BH_KERNEL_MAX
+    try:
+        correction.BH_KERNEL_MAX = 0          # force the torch.sort path
+        np.testing.assert_array_equal(correction.correct(p), want)
+    finally:
+        correction.BH_KERNEL_MAX = old
+    assert np.all(np.isnan(correction.correct(np.full(7, np.nan))))
 
 
 # ---------------------------------------------------------------------------------------------------
