@@ -1,8 +1,12 @@
 // dx_api.cu -- the extern "C" surface of libdxb200.so (include/dxb200.h): argument checks, error
 // strings, launch plumbing.  No torch types, no allocation except inside the *_host entry point.
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <vector>
 #include "dx_common.cuh"
 #include "dx_internal.h"
 
@@ -77,7 +81,7 @@ int dx_nb_fit_grouped(int64_t n_genes, int32_t n_groups, int32_t p_loc, int32_t 
     DX_CHECK(opts->init_b != DX_INIT_CLOSED_FORM, "dx_nb_fit_grouped: closed-form init_b must be resolved by the host");
     DX_CUDA(dx_launch_fit_grouped(n_genes, n_groups, p_loc, p_scale, xu_loc, xu_scale, offset, n_k, pinv_loc, loc_group,
                                   n_loc_groups, hist, ovf_count, indptr, ovf_val, ovf_group, opts, a_var, b_var, fim_inv, ll, jac, niter,
-                                  flags, (cudaStream_t)stream), "dx_nb_fit_grouped");
+                                  flags, 0, (cudaStream_t)stream), "dx_nb_fit_grouped");
     return DX_OK;
 }
 
@@ -110,7 +114,7 @@ int dx_wald_from_fit(int64_t n_genes, int32_t p_loc, int32_t coef, const double*
                      double* theta, double* sd, double* pval, double* log_pval, void* stream) {
     DX_CHECK(n_genes >= 0 && a_var && fim_inv && pval, "dx_wald_from_fit: bad arguments");
     DX_CHECK(coef >= 0 && coef < p_loc, "dx_wald_from_fit: coefficient index out of range");
-    DX_CUDA(dx_launch_wald_from_fit(n_genes, p_loc, coef, a_var, fim_inv, theta, sd, pval, log_pval, (cudaStream_t)stream),
+    DX_CUDA(dx_launch_wald_from_fit(n_genes, p_loc, coef, a_var, fim_inv, theta, sd, pval, log_pval, 0, (cudaStream_t)stream),
             "dx_wald_from_fit");
     return DX_OK;
 }
@@ -164,12 +168,51 @@ int dx_two_group_tests(int64_t n_genes, double n0, double n1,
 }
 
 // ---- host-buffer entry point ------------------------------------------------------------------------
+// The host shard is cut into chunks of genes with about equal non-zero counts; chunk c+1 crosses PCIe on the copy
+// stream while chunk c is ingested, fitted and tested on the compute stream, so the call costs about one
+// host-to-device transfer of the matrix.  Device workspace is cached per process (grown on demand).
 namespace {
-struct DevBuf {
-    void* p = nullptr;
-    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
-    ~DevBuf() { if (p) cudaFree(p); }
+struct HostPipe {
+    std::mutex mu;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    std::vector<cudaEvent_t> ev;
+    struct Buf { void* p = nullptr; size_t cap = 0; };
+    Buf bufs[32];
+    int device = -1;
+    cudaError_t ensure(int slot, size_t bytes, void** out) {
+        Buf& b = bufs[slot];
+        if (b.cap < bytes) {
+            if (b.p) cudaFree(b.p);
+            b.p = nullptr; b.cap = 0;
+            const size_t want = bytes + bytes / 8 + 256;
+            cudaError_t e = cudaMalloc(&b.p, want);
+            if (e != cudaSuccess) return e;
+            b.cap = want;
+        }
+        *out = b.p;
+        return cudaSuccess;
+    }
+    cudaError_t init(int n_events) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev != device) {           // workspace belongs to one device: drop it when the caller switched devices
+            for (Buf& b : bufs) { b.p = nullptr; b.cap = 0; }
+            s_copy = s_comp = nullptr; ev.clear();
+            device = dev;
+        }
+        if (!s_copy) { e = cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking); if (e != cudaSuccess) return e; }
+        if (!s_comp) { e = cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking); if (e != cudaSuccess) return e; }
+        while ((int)ev.size() < n_events) {
+            cudaEvent_t x;
+            e = cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+            ev.push_back(x);
+        }
+        return cudaSuccess;
+    }
 };
+HostPipe g_pipe;
 }  // namespace
 
 int dx_wald_grouped_host(int64_t n_cells, int64_t n_genes, const int64_t* indptr, const int32_t* rows,
@@ -182,67 +225,105 @@ int dx_wald_grouped_host(int64_t n_cells, int64_t n_genes, const int64_t* indptr
                          int32_t* niter, int32_t* flags, double* pval, double* log_pval, double* sd) {
     DX_CHECK(n_cells >= 1 && n_genes >= 0 && indptr && cell_group, "dx_wald_grouped_host: bad arguments");
     DX_CHECK(n_groups >= 1 && n_groups <= DX_MAX_GROUPS, "dx_wald_grouped_host: n_groups must be in 1..255");
+    DX_CHECK(p_loc >= 1 && p_loc <= DX_MAX_COEF && p_scale >= 1 && p_scale <= DX_MAX_COEF,
+             "dx_wald_grouped_host: coefficient counts must be in 1..32");
     DX_CHECK(coef >= 0 && coef < p_loc, "dx_wald_grouped_host: coefficient index out of range");
     DX_CHECK(!bad_opts(opts), "dx_wald_grouped_host: bad options");
+    DX_CHECK(xu_loc && xu_scale && n_k && a_var && b_var, "dx_wald_grouped_host: null pointer");
+    DX_CHECK(opts->init_a != DX_INIT_CLOSED_FORM || (pinv_loc && n_loc_groups >= 1 && n_loc_groups <= n_groups),
+             "dx_wald_grouped_host: closed-form init needs pinv_loc and 1 <= n_loc_groups <= n_groups");
+    if (n_genes == 0) return DX_OK;
     const int64_t nnz = indptr[n_genes];
     const int64_t G = n_genes;
-    DevBuf d_indptr, d_rows, d_vals, d_grp, d_hist, d_oc, d_ov, d_og, d_xl, d_xs, d_off, d_nk, d_pinv, d_lg;
-    DevBuf d_a, d_b, d_fi, d_ll, d_jac, d_ni, d_fl, d_p, d_lp, d_sd;
-    cudaStream_t s;
-    DX_CUDA(cudaStreamCreate(&s), "stream");
+    const int K = n_groups, p = p_loc, ps = p_scale;
+    std::lock_guard<std::mutex> lock(g_pipe.mu);
+    // chunk boundaries: about equal non-zero counts, at least 256 genes, at most 32 chunks
+    int n_chunks = (int)((nnz >> 24) + 1);                       // ~16M non-zeros (128 MB) per chunk
+    if (n_chunks > 32) n_chunks = 32;
+    if (const char* env = getenv("DXB200_HOST_CHUNKS")) { const int v = atoi(env); if (v >= 1 && v <= 30) n_chunks = v; }
+    else if ((int64_t)n_chunks * 256 > G) n_chunks = (int)((G + 255) / 256);
+    if ((int64_t)n_chunks > G) n_chunks = (int)G;
+    if (n_chunks < 1) n_chunks = 1;
+    std::vector<int64_t> cut(n_chunks + 1);
+    cut[0] = 0; cut[n_chunks] = G;
+    for (int c = 1; c < n_chunks; ++c) {
+        const int64_t target = nnz / n_chunks * c;
+        const int64_t* it = std::lower_bound(indptr + cut[c - 1], indptr + G, target);
+        int64_t g0 = it - indptr;
+        if (g0 < cut[c - 1]) g0 = cut[c - 1];
+        cut[c] = g0;
+    }
+    DX_CUDA(g_pipe.init(n_chunks + 2), "dx_wald_grouped_host: streams");
+    cudaStream_t sc = g_pipe.s_copy, sx = g_pipe.s_comp;
     int rc = DX_OK;
+    void *d_indptr, *d_rows, *d_vals, *d_grp, *d_hist, *d_oc, *d_ov, *d_og, *d_xl, *d_xs, *d_off, *d_nk, *d_pinv, *d_lg;
+    void *d_a, *d_b, *d_fi, *d_ll, *d_jac, *d_ni, *d_fl, *d_p, *d_lp, *d_sd;
 #define HX(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail_cuda(e__, "dx_wald_grouped_host"); goto done; } } while (0)
     {
-        HX(d_indptr.alloc((G + 1) * 8)); HX(d_rows.alloc(nnz * 4)); HX(d_vals.alloc(nnz * 4)); HX(d_grp.alloc(n_cells));
-        HX(d_hist.alloc((size_t)G * n_groups * DX_HIST_BINS * 4)); HX(d_oc.alloc(G * 4)); HX(d_ov.alloc(nnz * 4)); HX(d_og.alloc(nnz));
-        HX(d_xl.alloc((size_t)n_groups * p_loc * 8)); HX(d_xs.alloc((size_t)n_groups * p_scale * 8));
-        HX(d_off.alloc((size_t)n_groups * 8)); HX(d_nk.alloc((size_t)n_groups * 8)); HX(d_pinv.alloc((size_t)n_groups * p_loc * 8));
-        HX(d_a.alloc((size_t)G * p_loc * 8)); HX(d_b.alloc((size_t)G * p_scale * 8)); HX(d_fi.alloc((size_t)G * p_loc * p_loc * 8));
-        HX(d_ll.alloc(G * 8)); HX(d_jac.alloc(G * 8)); HX(d_ni.alloc(G * 4)); HX(d_fl.alloc(G * 4));
-        HX(d_p.alloc(G * 8)); HX(d_lp.alloc(G * 8)); HX(d_sd.alloc(G * 8));
-        HX(cudaMemcpyAsync(d_indptr.p, indptr, (G + 1) * 8, cudaMemcpyHostToDevice, s));
-        HX(cudaMemcpyAsync(d_rows.p, rows, nnz * 4, cudaMemcpyHostToDevice, s));
-        HX(cudaMemcpyAsync(d_vals.p, vals, nnz * 4, cudaMemcpyHostToDevice, s));
-        HX(cudaMemcpyAsync(d_grp.p, cell_group, n_cells, cudaMemcpyHostToDevice, s));
-        HX(cudaMemcpyAsync(d_xl.p, xu_loc, (size_t)n_groups * p_loc * 8, cudaMemcpyHostToDevice, s));
-        HX(cudaMemcpyAsync(d_xs.p, xu_scale, (size_t)n_groups * p_scale * 8, cudaMemcpyHostToDevice, s));
-        if (offset) HX(cudaMemcpyAsync(d_off.p, offset, (size_t)n_groups * 8, cudaMemcpyHostToDevice, s));
-        HX(cudaMemcpyAsync(d_nk.p, n_k, (size_t)n_groups * 8, cudaMemcpyHostToDevice, s));
-        HX(d_lg.alloc((size_t)n_groups * 4));
-        if (pinv_loc) HX(cudaMemcpyAsync(d_pinv.p, pinv_loc, (size_t)(n_loc_groups > 0 ? n_loc_groups : n_groups) * p_loc * 8, cudaMemcpyHostToDevice, s));
-        if (loc_group) HX(cudaMemcpyAsync(d_lg.p, loc_group, (size_t)n_groups * 4, cudaMemcpyHostToDevice, s));
-        if (opts->init_a == DX_INIT_GIVEN) HX(cudaMemcpyAsync(d_a.p, a_var, (size_t)G * p_loc * 8, cudaMemcpyHostToDevice, s));
-        if (opts->init_b == DX_INIT_GIVEN) HX(cudaMemcpyAsync(d_b.p, b_var, (size_t)G * p_scale * 8, cudaMemcpyHostToDevice, s));
-        rc = dx_group_suffstats(G, (const int64_t*)d_indptr.p, (const int32_t*)d_rows.p, (const float*)d_vals.p,
-                                (const uint8_t*)d_grp.p, n_groups, (uint32_t*)d_hist.p, (int32_t*)d_oc.p,
-                                (float*)d_ov.p, (uint8_t*)d_og.p, s);
-        if (rc) goto done;
-        rc = dx_nb_fit_grouped(G, n_groups, p_loc, p_scale, (const double*)d_xl.p, (const double*)d_xs.p,
-                               offset ? (const double*)d_off.p : nullptr, (const double*)d_nk.p,
-                               pinv_loc ? (const double*)d_pinv.p : nullptr,
-                               loc_group ? (const int32_t*)d_lg.p : nullptr, n_loc_groups, (const uint32_t*)d_hist.p,
-                               (const int32_t*)d_oc.p, (const int64_t*)d_indptr.p, (const float*)d_ov.p,
-                               (const uint8_t*)d_og.p, opts, (double*)d_a.p, (double*)d_b.p, (double*)d_fi.p,
-                               (double*)d_ll.p, (double*)d_jac.p, (int32_t*)d_ni.p, (int32_t*)d_fl.p, s);
-        if (rc) goto done;
-        rc = dx_wald_from_fit(G, p_loc, coef, (const double*)d_a.p, (const double*)d_fi.p, nullptr, (double*)d_sd.p,
-                              (double*)d_p.p, (double*)d_lp.p, s);
-        if (rc) goto done;
-        HX(cudaMemcpyAsync(a_var, d_a.p, (size_t)G * p_loc * 8, cudaMemcpyDeviceToHost, s));
-        HX(cudaMemcpyAsync(b_var, d_b.p, (size_t)G * p_scale * 8, cudaMemcpyDeviceToHost, s));
-        if (fim_inv) HX(cudaMemcpyAsync(fim_inv, d_fi.p, (size_t)G * p_loc * p_loc * 8, cudaMemcpyDeviceToHost, s));
-        if (ll) HX(cudaMemcpyAsync(ll, d_ll.p, G * 8, cudaMemcpyDeviceToHost, s));
-        if (jac) HX(cudaMemcpyAsync(jac, d_jac.p, G * 8, cudaMemcpyDeviceToHost, s));
-        if (niter) HX(cudaMemcpyAsync(niter, d_ni.p, G * 4, cudaMemcpyDeviceToHost, s));
-        if (flags) HX(cudaMemcpyAsync(flags, d_fl.p, G * 4, cudaMemcpyDeviceToHost, s));
-        if (pval) HX(cudaMemcpyAsync(pval, d_p.p, G * 8, cudaMemcpyDeviceToHost, s));
-        if (log_pval) HX(cudaMemcpyAsync(log_pval, d_lp.p, G * 8, cudaMemcpyDeviceToHost, s));
-        if (sd) HX(cudaMemcpyAsync(sd, d_sd.p, G * 8, cudaMemcpyDeviceToHost, s));
-        HX(cudaStreamSynchronize(s));
+        int sl = 0;
+        HX(g_pipe.ensure(sl++, (G + 1) * 8, &d_indptr)); HX(g_pipe.ensure(sl++, nnz * 4 + 16, &d_rows));
+        HX(g_pipe.ensure(sl++, nnz * 4 + 16, &d_vals)); HX(g_pipe.ensure(sl++, n_cells, &d_grp));
+        HX(g_pipe.ensure(sl++, (size_t)G * K * DX_HIST_BINS * 4, &d_hist)); HX(g_pipe.ensure(sl++, G * 4, &d_oc));
+        HX(g_pipe.ensure(sl++, nnz * 4 + 16, &d_ov)); HX(g_pipe.ensure(sl++, nnz + 16, &d_og));
+        HX(g_pipe.ensure(sl++, (size_t)K * p * 8, &d_xl)); HX(g_pipe.ensure(sl++, (size_t)K * ps * 8, &d_xs));
+        HX(g_pipe.ensure(sl++, (size_t)K * 8, &d_off)); HX(g_pipe.ensure(sl++, (size_t)K * 8, &d_nk));
+        HX(g_pipe.ensure(sl++, (size_t)K * p * 8, &d_pinv)); HX(g_pipe.ensure(sl++, (size_t)K * 4, &d_lg));
+        HX(g_pipe.ensure(sl++, (size_t)G * p * 8, &d_a)); HX(g_pipe.ensure(sl++, (size_t)G * ps * 8, &d_b));
+        HX(g_pipe.ensure(sl++, (size_t)G * p * p * 8, &d_fi)); HX(g_pipe.ensure(sl++, G * 8, &d_ll));
+        HX(g_pipe.ensure(sl++, G * 8, &d_jac)); HX(g_pipe.ensure(sl++, G * 4, &d_ni)); HX(g_pipe.ensure(sl++, G * 4, &d_fl));
+        HX(g_pipe.ensure(sl++, G * 8, &d_p)); HX(g_pipe.ensure(sl++, G * 8, &d_lp)); HX(g_pipe.ensure(sl++, G * 8, &d_sd));
+        // small inputs first
+        HX(cudaMemcpyAsync(d_indptr, indptr, (G + 1) * 8, cudaMemcpyHostToDevice, sc));
+        HX(cudaMemcpyAsync(d_grp, cell_group, n_cells, cudaMemcpyHostToDevice, sc));
+        HX(cudaMemcpyAsync(d_xl, xu_loc, (size_t)K * p * 8, cudaMemcpyHostToDevice, sc));
+        HX(cudaMemcpyAsync(d_xs, xu_scale, (size_t)K * ps * 8, cudaMemcpyHostToDevice, sc));
+        if (offset) HX(cudaMemcpyAsync(d_off, offset, (size_t)K * 8, cudaMemcpyHostToDevice, sc));
+        HX(cudaMemcpyAsync(d_nk, n_k, (size_t)K * 8, cudaMemcpyHostToDevice, sc));
+        if (pinv_loc) HX(cudaMemcpyAsync(d_pinv, pinv_loc, (size_t)(n_loc_groups > 0 ? n_loc_groups : K) * p * 8, cudaMemcpyHostToDevice, sc));
+        if (loc_group) HX(cudaMemcpyAsync(d_lg, loc_group, (size_t)K * 4, cudaMemcpyHostToDevice, sc));
+        if (opts->init_a == DX_INIT_GIVEN) HX(cudaMemcpyAsync(d_a, a_var, (size_t)G * p * 8, cudaMemcpyHostToDevice, sc));
+        if (opts->init_b == DX_INIT_GIVEN) HX(cudaMemcpyAsync(d_b, b_var, (size_t)G * ps * 8, cudaMemcpyHostToDevice, sc));
+        for (int c = 0; c < n_chunks; ++c) {
+            const int64_t g0 = cut[c], g1 = cut[c + 1];
+            if (g1 <= g0) continue;
+            const int64_t e0 = indptr[g0], e1 = indptr[g1];
+            if (e1 > e0) {
+                HX(cudaMemcpyAsync((int32_t*)d_rows + e0, rows + e0, (e1 - e0) * 4, cudaMemcpyHostToDevice, sc));
+                HX(cudaMemcpyAsync((float*)d_vals + e0, vals + e0, (e1 - e0) * 4, cudaMemcpyHostToDevice, sc));
+            }
+            HX(cudaEventRecord(g_pipe.ev[c], sc));
+            HX(cudaStreamWaitEvent(sx, g_pipe.ev[c], 0));
+            const int64_t gc = g1 - g0;
+            HX(dx_launch_ingest(gc, (const int64_t*)d_indptr + g0, (const int32_t*)d_rows, (const float*)d_vals,
+                                (const uint8_t*)d_grp, K, (uint32_t*)d_hist + g0 * (int64_t)K * DX_HIST_BINS,
+                                (int32_t*)d_oc + g0, (float*)d_ov, (uint8_t*)d_og, sm_count_cached(), sx));
+            HX(dx_launch_fit_grouped(gc, K, p, ps, (const double*)d_xl, (const double*)d_xs,
+                                     offset ? (const double*)d_off : nullptr, (const double*)d_nk,
+                                     pinv_loc ? (const double*)d_pinv : nullptr, loc_group ? (const int32_t*)d_lg : nullptr,
+                                     n_loc_groups, (const uint32_t*)d_hist + g0 * (int64_t)K * DX_HIST_BINS,
+                                     (const int32_t*)d_oc + g0, (const int64_t*)d_indptr + g0, (const float*)d_ov,
+                                     (const uint8_t*)d_og, opts, (double*)d_a + g0, (double*)d_b + g0,
+                                     (double*)d_fi + g0 * (int64_t)p * p, (double*)d_ll + g0, (double*)d_jac + g0,
+                                     (int32_t*)d_ni + g0, (int32_t*)d_fl + g0, G, sx));
+            HX(dx_launch_wald_from_fit(gc, p, coef, (const double*)d_a + g0, (const double*)d_fi + g0 * (int64_t)p * p, nullptr,
+                                       (double*)d_sd + g0, (double*)d_p + g0, (double*)d_lp + g0, G, sx));
+        }
+        HX(cudaMemcpyAsync(a_var, d_a, (size_t)G * p * 8, cudaMemcpyDeviceToHost, sx));
+        HX(cudaMemcpyAsync(b_var, d_b, (size_t)G * ps * 8, cudaMemcpyDeviceToHost, sx));
+        if (fim_inv) HX(cudaMemcpyAsync(fim_inv, d_fi, (size_t)G * p * p * 8, cudaMemcpyDeviceToHost, sx));
+        if (ll) HX(cudaMemcpyAsync(ll, d_ll, G * 8, cudaMemcpyDeviceToHost, sx));
+        if (jac) HX(cudaMemcpyAsync(jac, d_jac, G * 8, cudaMemcpyDeviceToHost, sx));
+        if (niter) HX(cudaMemcpyAsync(niter, d_ni, G * 4, cudaMemcpyDeviceToHost, sx));
+        if (flags) HX(cudaMemcpyAsync(flags, d_fl, G * 4, cudaMemcpyDeviceToHost, sx));
+        if (pval) HX(cudaMemcpyAsync(pval, d_p, G * 8, cudaMemcpyDeviceToHost, sx));
+        if (log_pval) HX(cudaMemcpyAsync(log_pval, d_lp, G * 8, cudaMemcpyDeviceToHost, sx));
+        if (sd) HX(cudaMemcpyAsync(sd, d_sd, G * 8, cudaMemcpyDeviceToHost, sx));
+        HX(cudaStreamSynchronize(sx));
+        HX(cudaStreamSynchronize(sc));
     }
 done:
 #undef HX
-    cudaStreamDestroy(s);
+    if (rc != DX_OK) { cudaStreamSynchronize(sx); cudaStreamSynchronize(sc); }
     return rc;
 }
 

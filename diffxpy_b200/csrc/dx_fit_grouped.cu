@@ -451,7 +451,7 @@ template <int SW> __device__ __noinline__ double scale_newton(Slot& s, double& b
 }
 
 struct FitArgs {
-    int64_t n_genes;
+    int64_t n_genes, stride;          // stride: distance (in genes) between coefficient rows of a_var / b_var
     int K, p, ps, KL;
     const double *xu_loc, *xu_scale, *offset, *n_k, *pinv_loc;
     const int32_t* loc_group;
@@ -643,7 +643,7 @@ dx_fit_grouped_kernel(const FitArgs P) {
         }
         __syncwarp(mask);
     } else if (opts.init_a == DX_INIT_GIVEN) {
-        if (sl < p) areg = dx_clip(P.a_var[(int64_t)sl * P.n_genes + g], DX_ETA_MIN, DX_ETA_MAX);
+        if (sl < p) areg = dx_clip(P.a_var[(int64_t)sl * P.stride + g], DX_ETA_MIN, DX_ETA_MAX);
     }
     if (opts.init_b == DX_INIT_STANDARD) {
         const double m = m_sf / n_total;
@@ -651,7 +651,7 @@ dx_fit_grouped_kernel(const FitArgs P) {
         const double denom = fmax(v - m, 2.2227587494850775e-162);
         breg = (sl == 0) ? dx_clip(log(m * m / denom + DX_TINY), DX_ETA_MIN, DX_ETA_MAX) : 0.0;
     } else if (opts.init_b == DX_INIT_GIVEN) {
-        if (sl < ps) breg = dx_clip(P.b_var[(int64_t)sl * P.n_genes + g], DX_ETA_MIN, DX_ETA_MAX);
+        if (sl < ps) breg = dx_clip(P.b_var[(int64_t)sl * P.stride + g], DX_ETA_MIN, DX_ETA_MAX);
     }
 
     // ---- train (batchglm numpy EstimatorGlm.train, per-gene form) -----------------------------------
@@ -745,8 +745,8 @@ dx_fit_grouped_kernel(const FitArgs P) {
         const int i = e / p, j = e - i * p;
         fo[e] = okf ? 0.5 * (Ainv[i * p + j] + Ainv[j * p + i]) : NAN;
     }
-    if (sl < p) P.a_var[(int64_t)sl * P.n_genes + g] = areg;
-    if (sl < ps) P.b_var[(int64_t)sl * P.n_genes + g] = breg;
+    if (sl < p) P.a_var[(int64_t)sl * P.stride + g] = areg;
+    if (sl < ps) P.b_var[(int64_t)sl * P.stride + g] = breg;
     if (sl == 0) {
         P.ll_out[g] = -nll;
         P.jac_out[g] = jac;
@@ -793,9 +793,10 @@ cudaError_t dx_launch_fit_grouped(int64_t n_genes, int K, int p, int ps,
                                   const uint32_t* tail, const int32_t* ovf_count, const int64_t* indptr,
                                   const float* ovf_val, const uint8_t* ovf_group, const dx_fit_opts* opts,
                                   double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
-                                  int32_t* niter, int32_t* flags, cudaStream_t stream) {
+                                  int32_t* niter, int32_t* flags, int64_t coef_stride, cudaStream_t stream) {
     if (n_genes <= 0) return cudaSuccess;
     FitArgs A;
+    A.stride = coef_stride > 0 ? coef_stride : n_genes;
     A.n_genes = n_genes; A.K = K; A.p = p; A.ps = ps; A.KL = n_loc_groups;
     A.xu_loc = xu_loc; A.xu_scale = xu_scale; A.offset = offset; A.n_k = n_k; A.pinv_loc = pinv_loc; A.loc_group = loc_group;
     A.tail_all = tail; A.ovf_count = ovf_count; A.indptr = indptr; A.ovf_val = ovf_val; A.ovf_group = ovf_group;

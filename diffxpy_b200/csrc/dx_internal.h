@@ -20,7 +20,7 @@ cudaError_t dx_launch_fit_grouped(int64_t n_genes, int K, int p, int ps,
                                   const uint32_t* tail, const int32_t* ovf_count, const int64_t* indptr,
                                   const float* ovf_val, const uint8_t* ovf_group, const dx_fit_opts* opts,
                                   double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
-                                  int32_t* niter, int32_t* flags, cudaStream_t stream);
+                                  int32_t* niter, int32_t* flags, int64_t coef_stride, cudaStream_t stream);
 cudaError_t dx_launch_fit_percell(int64_t n_genes, int64_t n_cells, int p, int ps,
                                   const double* design_loc, const double* design_scale, const double* log_sf,
                                   const int64_t* indptr, const int32_t* rows, const float* vals,
@@ -29,7 +29,7 @@ cudaError_t dx_launch_fit_percell(int64_t n_genes, int64_t n_cells, int p, int p
                                   int32_t* niter, int32_t* flags, int sm_count, cudaStream_t stream);
 cudaError_t dx_launch_wald(int64_t n, const double* theta, const double* sd, double* pval, double* logp, cudaStream_t s);
 cudaError_t dx_launch_wald_from_fit(int64_t G, int p, int coef, const double* a_var, const double* fim_inv,
-                                    double* theta, double* sd, double* pval, double* logp, cudaStream_t s);
+                                    double* theta, double* sd, double* pval, double* logp, int64_t coef_stride, cudaStream_t s);
 cudaError_t dx_launch_wald_chisq(int64_t G, int k, const double* theta, const double* cov,
                                  double* stat, double* pval, double* logp, cudaStream_t s);
 cudaError_t dx_launch_lrt(int64_t n, const double* llf, const double* llr, int ddf, double* pval, double* logp, cudaStream_t s);

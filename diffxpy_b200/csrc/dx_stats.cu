@@ -22,12 +22,12 @@ __global__ void dx_wald_kernel(int64_t n, const double* __restrict__ theta, cons
     if (logp) logp[i] = lp;
 }
 
-__global__ void dx_wald_from_fit_kernel(int64_t G, int p, int coef, const double* __restrict__ a_var,
+__global__ void dx_wald_from_fit_kernel(int64_t G, int64_t stride, int p, int coef, const double* __restrict__ a_var,
                                         const double* __restrict__ fim_inv, double* __restrict__ theta,
                                         double* __restrict__ sd, double* __restrict__ pval, double* __restrict__ logp) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
-    const double t = a_var[(int64_t)coef * G + g];
+    const double t = a_var[(int64_t)coef * stride + g];
     double v = fim_inv[g * (int64_t)p * p + coef * p + coef];
     if (v < DX_TINY) v = DX_TINY;                // det.py:796 (NaN stays NaN)
     const double s = sqrt(v);
@@ -378,9 +378,10 @@ cudaError_t dx_launch_wald(int64_t n, const double* theta, const double* sd, dou
     return cudaGetLastError();
 }
 cudaError_t dx_launch_wald_from_fit(int64_t G, int p, int coef, const double* a_var, const double* fim_inv,
-                                    double* theta, double* sd, double* pval, double* logp, cudaStream_t s) {
+                                    double* theta, double* sd, double* pval, double* logp, int64_t coef_stride, cudaStream_t s) {
     if (G <= 0) return cudaSuccess;
-    dx_wald_from_fit_kernel<<<grid1d(G, 256), 256, 0, s>>>(G, p, coef, a_var, fim_inv, theta, sd, pval, logp);
+    dx_wald_from_fit_kernel<<<grid1d(G, 256), 256, 0, s>>>(G, coef_stride > 0 ? coef_stride : G, p, coef, a_var, fim_inv, theta, sd,
+                                                           pval, logp);
     return cudaGetLastError();
 }
 cudaError_t dx_launch_wald_chisq(int64_t G, int k, const double* theta, const double* cov,

@@ -492,6 +492,19 @@ def test_host_entry_point_matches_device_path(de, golden_dir):
     np.testing.assert_array_equal(ni, est.niter)
     np.testing.assert_array_equal(fl, est.error_codes)
     np.testing.assert_array_equal(fi, est.fisher_inv)
+    # the copy/compute pipeline (several gene chunks) gives the same rows as a single chunk
+    os.environ["DXB200_HOST_CHUNKS"] = "5"
+    try:
+        a2 = np.zeros((p, g)); b2 = np.zeros((1, g)); fi2 = np.zeros((g, p, p)); pv2 = np.zeros(g)
+        _lib.call("dx_wald_grouped_host", n, g, P(indptr), P(rows), P(vals), P(grp), k, p, 1, P(xu), P(xs), None, P(nk),
+                  P(pinv), None, k, C.byref(opts), 1, P(a2), P(b2), P(fi2), P(ll), P(jac), P(ni), P(fl), P(pv2), P(lp), P(sdv))
+    finally:
+        del os.environ["DXB200_HOST_CHUNKS"]
+    np.testing.assert_array_equal(a2, a)
+    np.testing.assert_array_equal(b2, b)
+    np.testing.assert_array_equal(fi2, fi)
+    np.testing.assert_array_equal(pv2, pv)
+    np.testing.assert_array_equal(ni, est.niter)
 
 
 # ---------------------------------------------------------------------------------------------------
