@@ -357,12 +357,12 @@ def main_cuda(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     ingest_bytes = 8 * nnz + 8 * (g + 1) + n_cells + 4 * g * k * _lib.DX_HIST_BINS + 4 * g
     fit_bytes = 4 * g * k * _lib.DX_HIST_BINS + 8 * g * (p + ps + p * p + 2) + 8 * g + 8 * (g + 1)
-    kern = {"dx_ingest_kernel": {"ms": ingest_ms, "algorithmic_bytes": ingest_bytes},
+    kern = {"dx_ingest_tma_kernel": {"ms": ingest_ms, "algorithmic_bytes": ingest_bytes},
             "dx_fit_grouped_kernel": {"ms": fit_ms, "algorithmic_bytes": fit_bytes},
             "dx_wald_from_fit_kernel": {"ms": wald_ms}}
     # the roofline object describes the kernel of the step that streams HBM (K_ingest reads the whole shard once);
     # K_fit / Wald / BH work on 4 KB of statistics per gene and are bounded by fp64 issue, not by HBM
-    dom = "dx_ingest_kernel"
+    dom = "dx_ingest_tma_kernel"       # K <= 32 groups and a 16-byte aligned shard: the TMA variant of K_ingest runs
     achieved = kern[dom]["algorithmic_bytes"] / (kern[dom]["ms"] * 1e-3) / 1e9
     traffic = None
     try:
