@@ -46,14 +46,48 @@ def _names_of(d, names, prefix):
     return ["%s%d" % (prefix, i) for i in range(np.asarray(d).shape[1])]
 
 
-def group_rows(mat):
-    """Distinct rows of a float64 matrix and the row -> group map (byte-wise; -0.0 normalised)."""
-    mat = np.ascontiguousarray(mat + 0.0)
-    if mat.shape[1] == 0:
-        return mat[:1], np.zeros(mat.shape[0], dtype=np.int64)
+_HASH_MULT = np.array([0x9E3779B97F4A7C15, 0xC2B2AE3D27D4EB4F, 0x165667B19E3779F9, 0xD6E8FEB86659FD93,
+                       0xFF51AFD7ED558CCD, 0xC4CEB9FE1A85EC53, 0x2545F4914F6CDD1D, 0x9FB21C651E98DF25], dtype=np.uint64)
+
+
+def _group_rows_exact(mat):
     v = mat.view(np.dtype((np.void, mat.dtype.itemsize * mat.shape[1]))).ravel()
     _, idx, inv = np.unique(v, return_index=True, return_inverse=True)
     return mat[idx], np.asarray(inv).reshape(-1)
+
+
+def group_rows(mat):
+    """Distinct rows of a float64 matrix and the row -> group map (byte-wise; -0.0 normalised).  Groups are
+    numbered in the byte order of the rows, like ``np.unique`` on the raw records.  Rows are first reduced to
+    a 64-bit multiplicative hash (one cheap 1-D sort instead of a sort of wide records); the grouping is then
+    verified exactly and recomputed the slow way in the (astronomically unlikely) event of a collision."""
+    mat = np.ascontiguousarray(mat + 0.0)
+    if mat.shape[1] == 0:
+        return mat[:1], np.zeros(mat.shape[0], dtype=np.int64)
+    if mat.shape[0] < 4096:
+        return _group_rows_exact(mat)
+    bits = mat.view(np.uint64)
+    mult = np.resize(_HASH_MULT, mat.shape[1]) * (2 * np.arange(mat.shape[1], dtype=np.uint64) + np.uint64(1))
+    with np.errstate(over="ignore"):
+        h = (bits * mult[None, :]).sum(axis=1, dtype=np.uint64)
+        h ^= h >> np.uint64(29)
+    _, idx, inv = np.unique(h, return_index=True, return_inverse=True)
+    inv = np.asarray(inv).reshape(-1)
+    reps = mat[idx]
+    if idx.shape[0] > 4096 or not np.array_equal(reps[inv].view(np.uint64), bits):
+        return _group_rows_exact(mat)
+    # renumber in the byte order of the representative rows (what the exact method returns)
+    uniq, order_inv = _group_rows_exact(reps)
+    if uniq.shape[0] != reps.shape[0]:
+        return _group_rows_exact(mat)
+    return uniq, order_inv[inv]
+
+
+def rank_of_rows(mat, groups=None):
+    """Rank of a tall matrix through its distinct rows (same row space) when they are few."""
+    if groups is not None and groups[0].shape[0] <= 4096:
+        return int(np.linalg.matrix_rank(groups[0]))
+    return int(np.linalg.matrix_rank(mat))
 
 
 class InputDataGLM:
@@ -83,14 +117,18 @@ class InputDataGLM:
             else np.asarray(constraints_loc, dtype=np.float64)
         self.constraints_scale = np.eye(self.design_scale.shape[1]) if constraints_scale is None \
             else np.asarray(constraints_scale, dtype=np.float64)
-        xh_loc = self.design_loc @ self.constraints_loc
-        xh_scale = self.design_scale @ self.constraints_scale
-        if np.linalg.matrix_rank(xh_loc) != xh_loc.shape[1]:
-            raise ValueError("constrained design matrix design_loc is not full rank: %i %i"
-                             % (xh_loc.shape[1], np.linalg.matrix_rank(xh_loc)))
-        if np.linalg.matrix_rank(xh_scale) != xh_scale.shape[1]:
+        xh_loc = self.design_loc if constraints_loc is None else self.design_loc @ self.constraints_loc
+        xh_scale = self.design_scale if constraints_scale is None else self.design_scale @ self.constraints_scale
+        # distinct rows of the constrained designs: rank check here, design groups in Estimator.initialize()
+        self._groups_loc = group_rows(xh_loc) if n >= 4096 else None
+        self._groups_scale = group_rows(xh_scale) if n >= 4096 else None
+        r_loc = rank_of_rows(xh_loc, self._groups_loc)
+        if r_loc != xh_loc.shape[1]:
+            raise ValueError("constrained design matrix design_loc is not full rank: %i %i" % (xh_loc.shape[1], r_loc))
+        r_scale = rank_of_rows(xh_scale, self._groups_scale)
+        if r_scale != xh_scale.shape[1]:
             raise ValueError("constrained design matrix design_scale is not full rank: %i %i"
-                             % (xh_scale.shape[1], np.linalg.matrix_rank(xh_scale)))
+                             % (xh_scale.shape[1], r_scale))
         self.xh_loc, self.xh_scale = xh_loc, xh_scale
         if size_factors is not None:
             sf = np.asarray(size_factors, dtype=np.float64).reshape(-1)

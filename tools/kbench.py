@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--cells", type=int, default=100000)
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--what", default="ingest,fit")
+    ap.add_argument("--scale-batch", action="store_true", help="scale model '~1+batch' (8 dispersion coefficients, configs[2])")
     ap.add_argument("names", nargs="+")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -53,11 +54,12 @@ def main():
     nnz = shard.nnz
     g = a.genes
     xd = bench.design_for(cond, batch)
-    p, ps = xd.shape[1], 1
-    uniq, inv = group_rows(np.concatenate([xd, np.ones((a.cells, 1))], axis=1))
+    zd = np.delete(xd, 1, axis=1) if a.scale_batch else np.ones((a.cells, 1))
+    p, ps = xd.shape[1], zd.shape[1]
+    uniq, inv = group_rows(np.concatenate([xd, zd], axis=1))
     k = uniq.shape[0]
     xu_loc = np.ascontiguousarray(uniq[:, :p])
-    xu_scale = np.ascontiguousarray(uniq[:, p:p + 1])
+    xu_scale = np.ascontiguousarray(uniq[:, p:p + ps])
     n_k = np.bincount(inv, minlength=k).astype(np.float64)
     pinv = np.ascontiguousarray(np.linalg.pinv(xu_loc))
     cell_group = torch.from_numpy(inv.astype(np.uint8)).to(dev)
