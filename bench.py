@@ -233,6 +233,8 @@ def main_cuda(args):
 
     n_genes, n_cells = args.genes, args.cells
     shard, cond, batch = make_shard(torch, dev, seed=1000 + rank, n_genes=n_genes, n_cells=n_cells)
+    gene_order, int_counts = shard.prepare()       # resident-shard metadata (setup, like the CSC layout itself)
+    ingest_flags = _lib.DX_SHARD_INTEGER_COUNTS if int_counts else 0
     nnz = shard.nnz
     xd = design_for(cond, batch)
     p, ps = xd.shape[1], 1
@@ -265,8 +267,8 @@ def main_cuda(args):
         e = [ev() for _ in range(4)] if record else None
         if record:
             e[0].record()
-        _lib.call("dx_group_suffstats", g, ptr(shard.indptr), ptr(shard.rows), ptr(shard.vals), ptr(cell_group), k,
-                  ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), stream_ptr())
+        _lib.call("dx_group_suffstats_ex", g, ptr(shard.indptr), ptr(shard.rows), ptr(shard.vals), ptr(cell_group), k,
+                  ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), ptr(gene_order), ingest_flags, stream_ptr())
         if record:
             e[1].record()
         _lib.call("dx_nb_fit_grouped", g, k, p, ps, ptr(d_xl), ptr(d_xs), None, ptr(d_nk), ptr(d_pinv), None, k,

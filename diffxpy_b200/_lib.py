@@ -15,6 +15,7 @@ DX_MAX_GROUPS = 255
 DX_SKIP_GROUP = 255
 DX_MAX_COEF = 32
 
+DX_SHARD_INTEGER_COUNTS = 1
 DX_INIT_GIVEN, DX_INIT_STANDARD, DX_INIT_CLOSED_FORM, DX_INIT_ALL_ZERO = 0, 1, 2, 3
 
 FLAG_CONVERGED, FLAG_SINGULAR_FIM, FLAG_SCALE_FROZEN, FLAG_NONFINITE, FLAG_ALL_ZERO, FLAG_RANK_OVERFLOW = 1, 2, 4, 8, 16, 32
@@ -42,6 +43,7 @@ _I64, _I32, _F64 = C.c_int64, C.c_int32, C.c_double
 SIGNATURES = {
     "dx_device_sm_count": [C.POINTER(C.c_int)],
     "dx_group_suffstats": [_I64, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P],
+    "dx_group_suffstats_ex": [_I64, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _I32, _P],
     "dx_gene_moments": [_I64, _P, _P, _P, _P, _P, _P, _P],
     "dx_nb_fit_grouped": [_I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, C.POINTER(DxFitOpts),
                           _P, _P, _P, _P, _P, _P, _P, _P],

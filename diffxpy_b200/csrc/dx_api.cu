@@ -51,7 +51,20 @@ int dx_group_suffstats(int64_t n_genes, const int64_t* indptr, const int32_t* ro
     DX_CHECK(n_groups >= 1 && n_groups <= DX_MAX_GROUPS, "dx_group_suffstats: n_groups must be in 1..255");
     DX_CHECK(indptr && cell_group && hist && ovf_count, "dx_group_suffstats: null pointer");
     DX_CUDA(dx_launch_ingest(n_genes, indptr, rows, vals, cell_group, n_groups, hist, ovf_count, ovf_val, ovf_group,
-                             sm_count_cached(), (cudaStream_t)stream), "dx_group_suffstats");
+                             nullptr, 0, sm_count_cached(), (cudaStream_t)stream), "dx_group_suffstats");
+    return DX_OK;
+}
+
+int dx_group_suffstats_ex(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,
+                          const uint8_t* cell_group, int32_t n_groups,
+                          uint32_t* hist, int32_t* ovf_count, float* ovf_val, uint8_t* ovf_group,
+                          const int32_t* gene_order, int32_t flags, void* stream) {
+    DX_CHECK(n_genes >= 0, "dx_group_suffstats_ex: n_genes < 0");
+    DX_CHECK(n_groups >= 1 && n_groups <= DX_MAX_GROUPS, "dx_group_suffstats_ex: n_groups must be in 1..255");
+    DX_CHECK(indptr && cell_group && hist && ovf_count, "dx_group_suffstats_ex: null pointer");
+    DX_CHECK((flags & ~DX_SHARD_INTEGER_COUNTS) == 0, "dx_group_suffstats_ex: unknown flag");
+    DX_CUDA(dx_launch_ingest(n_genes, indptr, rows, vals, cell_group, n_groups, hist, ovf_count, ovf_val, ovf_group,
+                             gene_order, flags, sm_count_cached(), (cudaStream_t)stream), "dx_group_suffstats_ex");
     return DX_OK;
 }
 
@@ -296,7 +309,7 @@ int dx_wald_grouped_host(int64_t n_cells, int64_t n_genes, const int64_t* indptr
             const int64_t gc = g1 - g0;
             HX(dx_launch_ingest(gc, (const int64_t*)d_indptr + g0, (const int32_t*)d_rows, (const float*)d_vals,
                                 (const uint8_t*)d_grp, K, (uint32_t*)d_hist + g0 * (int64_t)K * DX_HIST_BINS,
-                                (int32_t*)d_oc + g0, (float*)d_ov, (uint8_t*)d_og, sm_count_cached(), sx));
+                                (int32_t*)d_oc + g0, (float*)d_ov, (uint8_t*)d_og, nullptr, 0, sm_count_cached(), sx));
             HX(dx_launch_fit_grouped(gc, K, p, ps, (const double*)d_xl, (const double*)d_xs,
                                      offset ? (const double*)d_off : nullptr, (const double*)d_nk,
                                      pinv_loc ? (const double*)d_pinv : nullptr, loc_group ? (const int32_t*)d_lg : nullptr,

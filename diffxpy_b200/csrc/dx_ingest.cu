@@ -293,12 +293,16 @@ struct TileInfo {          // registers, per fetched tile
     int slot, last;        // gene descriptor slot; 1 when this is the last tile of the gene
 };
 
+// INT_ONLY: the caller guarantees that every stored value is a non-negative integer (< 2^24), which removes the
+// integrality test from the hot loop.  gene_order (nullable): the sequence in which the queue hands out genes
+// (largest first keeps the tail of the launch short).
+template <bool INT_ONLY>
 __global__ void __launch_bounds__(TW * 32, 1)
 dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const int32_t* __restrict__ rows,
                      const float* __restrict__ vals, const uint8_t* __restrict__ cell_group, int K, int ysh, int NW, int NWA,
                      uint32_t* __restrict__ hist_out, int32_t* __restrict__ ovf_count,
                      float* __restrict__ ovf_val, uint8_t* __restrict__ ovf_group, unsigned int* __restrict__ queue,
-                     int warp_bytes) {
+                     const int32_t* __restrict__ gene_order, int warp_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* base = smem_raw + (size_t)warp * warp_bytes;
@@ -340,6 +344,7 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
             if (lane == 0) gq = atomicAdd(queue, 1u);
             gq = __shfl_sync(DX_FULL_MASK, gq, 0);
             if ((int64_t)gq >= n_genes) { done_issue = true; return; }
+            if (gene_order) gq = (unsigned)__ldg(gene_order + gq);
             const long long st_ = __ldg(indptr + gq), en_ = __ldg(indptr + gq + 1);
             if (lane == 0) {
                 GeneDesc d;
@@ -452,27 +457,32 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
     auto process = [&](const float (&v)[TU], const int (&r)[TU], const unsigned (&k)[TU], const TileInfo& m) {
         if (since_flush + TU > 255) flush();
         since_flush += TU;
-        bool slow = false;
+        // counted two elements at a time: the rare path (counts above the private range, non-counts, padding) is
+        // entered per pair, so one unusual entry costs two re-classifications instead of TU
 #pragma unroll
-        for (int u = 0; u < TU; ++u) {
-            const int y = __float2int_rz(v[u]);
-            const unsigned ym1 = (unsigned)(y - 1);
-            const bool fast = (__int2float_rn(y) == v[u]) && (ym1 < YP) && (k[u] < (unsigned)K);
-            const unsigned j8 = (k[u] << ysh3) + (ym1 << 3);
-            const unsigned inc = fast ? (1u << (j8 & 24u)) : 0u;
-            dx_red_shared(priv_addr + ((j8 & row_mask) << 2), inc);
-            slow = slow || !fast;
-        }
-        if (slow) {
+        for (int u0 = 0; u0 < TU; u0 += 2) {
+            bool slow = false;
 #pragma unroll
-            for (int u = 0; u < TU; ++u) {
+            for (int u = u0; u < u0 + 2; ++u) {
                 const int y = __float2int_rz(v[u]);
                 const unsigned ym1 = (unsigned)(y - 1);
-                const bool isbin = (ym1 < (unsigned)DX_HIST_BINS) && (__int2float_rn(y) == v[u]) && (k[u] < (unsigned)K);
-                if (isbin) {
-                    if (ym1 >= YP) atomicAdd(&s_hist[k[u] * DX_HIST_BINS + ym1], 1u);
-                } else if (v[u] != 0.0f && k[u] < (unsigned)K) {
-                    ++n_ovf;
+                const bool fast = (INT_ONLY || __int2float_rn(y) == v[u]) && (ym1 < YP) && (k[u] < (unsigned)K);
+                const unsigned j8 = (k[u] << ysh3) + (ym1 << 3);
+                const unsigned inc = fast ? (1u << (j8 & 24u)) : 0u;
+                dx_red_shared(priv_addr + ((j8 & row_mask) << 2), inc);
+                slow = slow || !fast;
+            }
+            if (slow) {
+#pragma unroll
+                for (int u = u0; u < u0 + 2; ++u) {
+                    const int y = __float2int_rz(v[u]);
+                    const unsigned ym1 = (unsigned)(y - 1);
+                    const bool isbin = (ym1 < (unsigned)DX_HIST_BINS) && (__int2float_rn(y) == v[u]) && (k[u] < (unsigned)K);
+                    if (isbin) {
+                        if (ym1 >= YP) atomicAdd(&s_hist[k[u] * DX_HIST_BINS + ym1], 1u);
+                    } else if (v[u] != 0.0f && k[u] < (unsigned)K) {
+                        ++n_ovf;
+                    }
                 }
             }
         }
@@ -579,7 +589,8 @@ cudaError_t dx_queue_acquire(cudaStream_t stream, unsigned int** out) {
 
 cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,
                              const uint8_t* cell_group, int K, uint32_t* hist, int32_t* ovf_count,
-                             float* ovf_val, uint8_t* ovf_group, int sm_count, cudaStream_t stream) {
+                             float* ovf_val, uint8_t* ovf_group, const int32_t* gene_order, int flags, int sm_count,
+                             cudaStream_t stream) {
     if (n_genes <= 0) return cudaSuccess;
     const int YP = dx_ingest_private_bins(K);
     int ysh = -1;
@@ -603,13 +614,14 @@ cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32
         e = dx_queue_acquire(stream, &queue);
         if (e != cudaSuccess) return e;
         const size_t smem = (size_t)warps * warp_bytes;
-        e = cudaFuncSetAttribute(dx_ingest_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        auto kern = (flags & DX_SHARD_INTEGER_COUNTS) ? dx_ingest_tma_kernel<true> : dx_ingest_tma_kernel<false>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int64_t grid = sm_count;
         const int64_t need = (n_genes + warps - 1) / warps;
         if (grid > need) grid = need;
-        dx_ingest_tma_kernel<<<(unsigned)grid, warps * 32, smem, stream>>>(n_genes, indptr, rows, vals, cell_group, K, ysh, NW,
-                                                                          NWA, hist, ovf_count, ovf_val, ovf_group, queue, warp_bytes);
+        kern<<<(unsigned)grid, warps * 32, smem, stream>>>(n_genes, indptr, rows, vals, cell_group, K, ysh, NW, NWA, hist,
+                                                           ovf_count, ovf_val, ovf_group, queue, gene_order, warp_bytes);
         return cudaGetLastError();
     }
     // ---- CTA-per-gene variant (any K, any alignment) -------------------------------------------------------------

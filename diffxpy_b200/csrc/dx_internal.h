@@ -11,7 +11,8 @@ int dx_ingest_private_bins(int K);
 cudaError_t dx_queue_acquire(cudaStream_t stream, unsigned int** out);
 cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,
                              const uint8_t* cell_group, int K, uint32_t* hist, int32_t* ovf_count,
-                             float* ovf_val, uint8_t* ovf_group, int sm_count, cudaStream_t stream);
+                             float* ovf_val, uint8_t* ovf_group, const int32_t* gene_order, int flags, int sm_count,
+                             cudaStream_t stream);
 cudaError_t dx_launch_gene_moments(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,
                                    const double* inv_sf, double* sum1, double* sum2, cudaStream_t stream);
 cudaError_t dx_launch_fit_grouped(int64_t n_genes, int K, int p, int ps,

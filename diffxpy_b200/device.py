@@ -47,12 +47,35 @@ class CountShard:
         self.gene_offset = int(gene_offset)
         self.device = vals.device
         self._nnz = None
+        self._order = None
+        self._int = None
 
     @property
     def nnz(self):
         if self._nnz is None:
             self._nnz = int(self.indptr[-1].item())
         return self._nnz
+
+    # ---- what a resident shard knows about itself (computed once, reused by every K_ingest launch) ---------
+    @property
+    def gene_order(self):
+        """Genes sorted by non-zero count, largest first (int32): the order the ingest queue hands them out."""
+        if self._order is None:
+            counts = self.indptr[1:] - self.indptr[:-1]
+            self._order = torch.argsort(counts, descending=True, stable=True).to(torch.int32).contiguous()
+        return self._order
+
+    @property
+    def integer_counts(self):
+        """True when every stored value is a non-negative integer below 2^24 (raw counts)."""
+        if self._int is None:
+            v = self.vals
+            self._int = bool(((v >= 0) & (v < 16777216.0) & (v == torch.floor(v))).all().item()) if v.numel() else True
+        return self._int
+
+    def prepare(self):
+        """Materialise the cached shard properties (setup time, like the CSR -> CSC conversion)."""
+        return self.gene_order, self.integer_counts
 
     @property
     def algorithmic_bytes(self):
@@ -150,8 +173,10 @@ class CountShard:
         ovf_count = torch.empty(g, dtype=torch.int32, device=dev)
         ovf_val = torch.empty(max(self.vals.shape[0], 1), dtype=torch.float32, device=dev)
         ovf_group = torch.empty(max(self.vals.shape[0], 1), dtype=torch.uint8, device=dev)
-        _lib.call("dx_group_suffstats", g, ptr(self.indptr), ptr(self.rows), ptr(self.vals), ptr(cell_group),
-                  int(n_groups), ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), stream_ptr())
+        flags = _lib.DX_SHARD_INTEGER_COUNTS if self.integer_counts else 0
+        _lib.call("dx_group_suffstats_ex", g, ptr(self.indptr), ptr(self.rows), ptr(self.vals), ptr(cell_group),
+                  int(n_groups), ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), ptr(self.gene_order), flags,
+                  stream_ptr())
         return SuffStats(self, tail, ovf_count, ovf_val, ovf_group, n_groups)
 
     def gene_moments(self, inv_sf=None):

@@ -82,6 +82,16 @@ int dx_group_suffstats(int64_t n_genes, const int64_t* indptr, const int32_t* ro
                        const uint8_t* cell_group, int32_t n_groups,
                        uint32_t* hist, int32_t* ovf_count, float* ovf_val, uint8_t* ovf_group,
                        void* stream);
+/* Same, with what a resident shard can know about itself:
+ *   gene_order[n_genes] (nullable): permutation of 0..n_genes-1, the order in which genes are handed to the SMs
+ *                       (largest first shortens the tail of the launch); results do not depend on it
+ *   flags: DX_SHARD_INTEGER_COUNTS = every stored value is a non-negative integer below 2^24 (verified by the
+ *          caller); the kernel then skips the per-entry integrality test */
+#define DX_SHARD_INTEGER_COUNTS 1
+int dx_group_suffstats_ex(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,
+                          const uint8_t* cell_group, int32_t n_groups,
+                          uint32_t* hist, int32_t* ovf_count, float* ovf_val, uint8_t* ovf_group,
+                          const int32_t* gene_order, int32_t flags, void* stream);
 
 /* ---- K_fit (grouped): the whole batchglm training schedule + finalize, one warp per gene ----------
  * Replaces Estimator.initialize / train_sequence / finalize (tests.py:222-248) when the rows of

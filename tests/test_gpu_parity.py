@@ -143,6 +143,36 @@ def test_ingest_tail_counts_bit_exact(de, k):
         assert got == sorted(zip(v[isovf].tolist(), gk[isovf].tolist()))
 
 
+def test_ingest_ex_order_and_integer_flag(de):
+    """dx_group_suffstats_ex (largest-first gene order, integer-count fast path) == dx_group_suffstats."""
+    from diffxpy_b200.device import CountShard, ptr, stream_ptr
+    from diffxpy_b200 import _lib
+    rng = np.random.default_rng(11)
+    n, g, k = 5000, 300, 16
+    lam = np.exp(rng.uniform(np.log(0.01), np.log(20), g))
+    x = rng.poisson(rng.gamma(0.7, lam / 0.7, size=(n, g))).astype(np.float32)
+    x[:, 5] = 0
+    x[:, 7] = 70                     # above the direct bins -> overflow entries even for integer data
+    grp = rng.integers(0, k, n).astype(np.uint8)
+    shard = CountShard.from_host(x)
+    assert shard.integer_counts
+    order = shard.gene_order.cpu().numpy()
+    assert sorted(order.tolist()) == list(range(g))
+    nnz_g = np.diff(shard.indptr.cpu().numpy())
+    assert np.all(np.diff(nnz_g[order]) <= 0)
+    cg = torch.from_numpy(grp).cuda()
+    suff = shard.group_suffstats(cg, k)                     # _ex path
+    tail2 = torch.empty_like(suff.tail); oc2 = torch.empty_like(suff.ovf_count)
+    ov2 = torch.zeros_like(suff.ovf_val); og2 = torch.zeros_like(suff.ovf_group)
+    _lib.call("dx_group_suffstats", g, ptr(shard.indptr), ptr(shard.rows), ptr(shard.vals), ptr(cg), k, ptr(tail2), ptr(oc2),
+              ptr(ov2), ptr(og2), stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(suff.tail, tail2) and torch.equal(suff.ovf_count, oc2)
+    assert int(oc2[7].item()) == n
+    x[3, 9] = 0.5
+    assert not CountShard.from_host(x).integer_counts
+
+
 def test_ingest_csr_csc_dense_inputs_agree(de):
     rng = np.random.default_rng(0)
     x = rng.poisson(0.7, size=(500, 30)).astype(np.float32)

@@ -26,6 +26,8 @@ def load_variant(name):
     path = _lib.LIB_PATH if name == "product" else os.path.join(ROOT, "diffxpy_b200", "variants", "libdxb200_%s.so" % name)
     lib = C.CDLL(path)
     for fn, argtypes in _lib.SIGNATURES.items():
+        if not hasattr(lib, fn):
+            continue
         f = getattr(lib, fn)
         f.argtypes = argtypes
         f.restype = C.c_int
@@ -45,6 +47,7 @@ def main():
     ap.add_argument("--cells", type=int, default=100000)
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--what", default="ingest,fit")
+    ap.add_argument("--plain", action="store_true", help="use dx_group_suffstats (no gene order / integer flag)")
     ap.add_argument("--scale-batch", action="store_true", help="scale model '~1+batch' (8 dispersion coefficients, configs[2])")
     ap.add_argument("names", nargs="+")
     a = ap.parse_args()
@@ -82,9 +85,15 @@ def main():
         fim_inv, ll, jac = torch.zeros((g, p, p), **f64), torch.zeros(g, **f64), torch.zeros(g, **f64)
         niter, flags = torch.zeros(g, dtype=torch.int32, device=dev), torch.zeros(g, dtype=torch.int32, device=dev)
 
+        order, is_int = shard.prepare()
+
         def ingest():
-            call(lib, "dx_group_suffstats", g, ptr(shard.indptr), ptr(shard.rows), ptr(shard.vals), ptr(cell_group), k,
-                 ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), stream_ptr())
+            if a.plain or not hasattr(lib, "dx_group_suffstats_ex"):
+                call(lib, "dx_group_suffstats", g, ptr(shard.indptr), ptr(shard.rows), ptr(shard.vals), ptr(cell_group), k,
+                     ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), stream_ptr())
+            else:
+                call(lib, "dx_group_suffstats_ex", g, ptr(shard.indptr), ptr(shard.rows), ptr(shard.vals), ptr(cell_group), k,
+                     ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), ptr(order), 1 if is_int else 0, stream_ptr())
 
         def fit():
             call(lib, "dx_nb_fit_grouped", g, k, p, ps, ptr(d_xl), ptr(d_xs), None, ptr(d_nk), ptr(d_pinv), None, k,
