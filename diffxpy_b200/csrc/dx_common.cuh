@@ -51,6 +51,20 @@ __device__ __forceinline__ long long dx_warp_scan_ll(long long v, int lane) {
     return v;
 }
 
+// fp64 library routines behind one switch: out-of-line single copies (each inlined copy is 1-6 KB of SASS) or inlined
+#ifndef DX_MATH_OUTLINE
+#define DX_MATH_OUTLINE 0      // measured on B200: the call overhead costs more than the instruction-cache misses it saves
+#endif
+#if DX_MATH_OUTLINE
+#define DX_MATH_FN static __device__ __noinline__
+#else
+#define DX_MATH_FN static __device__ __forceinline__
+#endif
+DX_MATH_FN double dx_log(double x) { return log(x); }
+DX_MATH_FN double dx_exp(double x) { return exp(x); }
+DX_MATH_FN double dx_log1p(double x) { return log1p(x); }
+DX_MATH_FN double dx_lgamma(double x) { return lgamma(x); }
+
 // ---------------------------------------------------------------------------------------------
 // digamma / trigamma for x > 0 (recurrence up to x >= 10, then the asymptotic series)
 // ---------------------------------------------------------------------------------------------
@@ -60,7 +74,7 @@ static __device__ __noinline__ double dx_digamma(double x) {
     const double f = 1.0 / (x * x);
     const double t = f * (-1.0 / 12.0 + f * (1.0 / 120.0 + f * (-1.0 / 252.0 + f * (1.0 / 240.0 + f * (-1.0 / 132.0 +
                      f * (691.0 / 32760.0 + f * (-1.0 / 12.0)))))));
-    return res + log(x) - 0.5 / x + t;
+    return res + dx_log(x) - 0.5 / x + t;
 }
 static __device__ __noinline__ double dx_trigamma(double x) {
     double res = 0.0;
@@ -73,7 +87,7 @@ static __device__ __noinline__ double dx_trigamma(double x) {
 // G(r, y) = lgamma(r + y) - lgamma(r) - y log r, stable for large r (second-order Stirling beyond 1e7)
 static __device__ __noinline__ double dx_lgamma_ratio(double r, double y) {
     if (r >= 1e7) return y * (y - 1.0) / (2.0 * r) - y * (y - 1.0) * (2.0 * y - 1.0) / (12.0 * r * r);
-    return lgamma(r + y) - lgamma(r) - y * log(r);
+    return dx_lgamma(r + y) - dx_lgamma(r) - y * dx_log(r);
 }
 
 // ---------------------------------------------------------------------------------------------

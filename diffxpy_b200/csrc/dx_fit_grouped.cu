@@ -8,9 +8,9 @@
 // is exactly equivalent to one independent loop per gene.
 //
 // For design group k (distinct row of [design_loc | design_scale | log size factor], n_k cells):
-//   eta_k = x_k.a + off_k, mu_k = exp(eta_k), zeta_k = z_k.b, r_k = exp(zeta_k), l_k = log1p(mu_k / r_k)
-//   ll   = T(r) + sum_k [ S_k (eta_k - zeta_k - l_k) - n_k r_k l_k ] - sum_i lgamma(y_i + 1)
-//   T(r) = sum_k sum_j c_k(j) log(r_k + j) + sum_ovf [ lgamma(r_k + y) - lgamma(r_k) ]
+//   eta_k = x_k.a + off_k, mu_k = dx_exp(eta_k), zeta_k = z_k.b, r_k = dx_exp(zeta_k), l_k = dx_log1p(mu_k / r_k)
+//   ll   = T(r) + sum_k [ S_k (eta_k - zeta_k - l_k) - n_k r_k l_k ] - sum_i dx_lgamma(y_i + 1)
+//   T(r) = sum_k sum_j c_k(j) dx_log(r_k + j) + sum_ovf [ dx_lgamma(r_k + y) - dx_lgamma(r_k) ]
 //   X^T W X    = sum_k n_k W_k x_k x_k^T,   W_k = mu_k r_k / (r_k + mu_k)
 //   X^T W ybar = sum_k x_k ( S_k r_k/(r_k + mu_k) - n_k W_k )
 // with c_k(j) the tail counts #{i in k: y_i > j} (integer counts <= 64) and S_k = sum_{i in k} y_i.
@@ -29,6 +29,17 @@ namespace {
 extern __shared__ __align__(16) double smem_d[];
 
 constexpr int PTAB_MAX_DOUBLES = 3072;     // product table budget per CTA (24 KB)
+
+// helpers on the IWLS path are inlined (their Slot fields then live in registers); the rarely executed scale-model
+// helpers stay out of line to keep the hot loop inside the instruction cache
+#ifndef DX_FIT_INLINE_HOT
+#define DX_FIT_INLINE_HOT 1
+#endif
+#if DX_FIT_INLINE_HOT
+#define DX_HOT __forceinline__
+#else
+#define DX_HOT __noinline__
+#endif
 
 template <int SW> __device__ __forceinline__ double sw_sum(double v, unsigned m) {
 #pragma unroll
@@ -78,7 +89,7 @@ __device__ __forceinline__ bool slot_group_has_ovf(const Slot& s, int k) {
     return (s.ovf_groups[k >> 6] >> (k & 63)) & 1ull;
 }
 
-// T(r) = sum_k sum_j c_k(j) log(r_k + j) + sum_ovf [lgamma(r_k + y) - lgamma(r_k)]
+// T(r) = sum_k sum_j c_k(j) dx_log(r_k + j) + sum_ovf [dx_lgamma(r_k + y) - dx_lgamma(r_k)]
 template <int SW> __device__ __noinline__ double compute_T(const Slot& s, int o_rr) {
     const double* rr = smem_d + o_rr;
     double part = 0.0;
@@ -88,7 +99,7 @@ template <int SW> __device__ __noinline__ double compute_T(const Slot& s, int o_
 #pragma unroll 1
         for (int j = s.sl; j < s.ymax; j += SW) {
             const double cnt = Cj[j];
-            if (cnt != 0.0) part += cnt * log(r + (double)j);
+            if (cnt != 0.0) part += cnt * dx_log(r + (double)j);
         }
     } else {
 #pragma unroll 1
@@ -97,7 +108,7 @@ template <int SW> __device__ __noinline__ double compute_T(const Slot& s, int o_
 #pragma unroll 1
             for (int j = s.sl; j < s.ymax; j += SW) {
                 const unsigned cnt = __ldg(s.tail + k * DX_HIST_BINS + j);
-                if (cnt) part += (double)cnt * log(r + (double)j);
+                if (cnt) part += (double)cnt * dx_log(r + (double)j);
             }
         }
     }
@@ -105,12 +116,12 @@ template <int SW> __device__ __noinline__ double compute_T(const Slot& s, int o_
     for (int t = s.sl; t < s.novf; t += SW) {
         const double y = (double)__ldg(s.oval + t);
         const double r = rr[__ldg(s.ogrp + t)];
-        part += dx_lgamma_ratio(r, y) + y * log(r);
+        part += dx_lgamma_ratio(r, y) + y * dx_log(r);
     }
     return sw_sum<SW>(part, s.mask);
 }
 
-// zeta_k = clip(z_k . b), r_k = exp(zeta_k) into the given buffers, T(r) into T_out; returns max_k zeta_k.
+// zeta_k = clip(z_k . b), r_k = dx_exp(zeta_k) into the given buffers, T(r) into T_out; returns max_k zeta_k.
 // breg: lane i holds b_i.
 template <int SW> __device__ __noinline__ double set_b(const Slot& s, double breg, int o_zeta, int o_rr, double& T_out) {
     double* vec = smem_d + s.vec;
@@ -125,7 +136,7 @@ template <int SW> __device__ __noinline__ double set_b(const Slot& s, double bre
         for (int i = 0; i < s.ps; ++i) z += xs[k * s.ps + i] * vec[i];
         z = dx_clip(z, DX_ETA_MIN, DX_ETA_MAX);
         smem_d[o_zeta + k] = z;
-        smem_d[o_rr + k] = exp(z);
+        smem_d[o_rr + k] = dx_exp(z);
         zmax = fmax(zmax, z);
     }
     __syncwarp(s.mask);
@@ -133,8 +144,8 @@ template <int SW> __device__ __noinline__ double set_b(const Slot& s, double bre
     return sw_max<SW>(zmax, s.mask);
 }
 
-// eta_k = clip(x_k . a + off_k), mu_k = exp(eta_k); areg: lane i holds a_i
-template <int SW> __device__ __noinline__ void set_a(const Slot& s, double areg, int o_eta, int o_mu) {
+// eta_k = clip(x_k . a + off_k), mu_k = dx_exp(eta_k); areg: lane i holds a_i
+template <int SW> __device__ DX_HOT void set_a(const Slot& s, double areg, int o_eta, int o_mu) {
     double* vec = smem_d + s.vec;
     if (s.sl < s.p) vec[s.sl] = areg;
     __syncwarp(s.mask);
@@ -147,18 +158,18 @@ template <int SW> __device__ __noinline__ void set_a(const Slot& s, double areg,
         for (int i = 0; i < p; ++i) e += xl[k * p + i] * vec[i];
         e = dx_clip(e, DX_ETA_MIN, DX_ETA_MAX);
         smem_d[o_eta + k] = e;
-        smem_d[o_mu + k] = exp(e);
+        smem_d[o_mu + k] = dx_exp(e);
     }
     __syncwarp(s.mask);
 }
 
-// l_k = log1p(mu_k / r_k), irm_k = 1 / (r_k + mu_k)
-template <int SW> __device__ __noinline__ void refresh(const Slot& s, int o_mu, int o_rr, int o_l1p, int o_irm) {
+// l_k = dx_log1p(mu_k / r_k), irm_k = 1 / (r_k + mu_k)
+template <int SW> __device__ DX_HOT void refresh(const Slot& s, int o_mu, int o_rr, int o_l1p, int o_irm) {
 #pragma unroll 1
     for (int k = s.sl; k < s.K; k += SW) {
         const double m = smem_d[o_mu + k], r = smem_d[o_rr + k];
         smem_d[o_irm + k] = 1.0 / (r + m);
-        smem_d[o_l1p + k] = log1p(m / r);
+        smem_d[o_l1p + k] = dx_log1p(m / r);
     }
     __syncwarp(s.mask);
 }
@@ -174,7 +185,7 @@ template <int SW> __device__ __forceinline__ double ll_state(const Slot& s, int 
 }
 
 // A = X^T W X (lower triangle, column-major in s.A) from the current state; returns (X^T W ybar)_i in lane i
-template <int SW> __device__ __noinline__ double loc_terms(const Slot& s) {
+template <int SW> __device__ DX_HOT double loc_terms(const Slot& s) {
     const int K = s.K, p = s.p, nent = s.nent;
     double* w1 = smem_d + s.w1;
     double* w2 = smem_d + s.w2;
@@ -552,7 +563,7 @@ dx_fit_grouped_kernel(const FitArgs P) {
         for (int r = 0; r < R; ++r) cj[r] = 0.0;
 #pragma unroll 1
         for (int k = 0; k < K; ++k) {
-            // lanes over j: S_k = sum_j c_k(j), sum y^2 = sum_j c(j)(2j+1), sum lgamma(y+1) = sum_j c(j) log(j+1)
+            // lanes over j: S_k = sum_j c_k(j), sum y^2 = sum_j c(j)(2j+1), sum dx_lgamma(y+1) = sum_j c(j) dx_log(j+1)
             double sk = 0.0, qk = 0.0;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -572,7 +583,7 @@ dx_fit_grouped_kernel(const FitArgs P) {
         for (int r = 0; r < R; ++r) {
             const int j = sl + r * SW;
             smem_d[s.Cj + j] = cj[r];
-            if (cj[r] != 0.0) lgc += cj[r] * log((double)j + 1.0);
+            if (cj[r] != 0.0) lgc += cj[r] * dx_log((double)j + 1.0);
         }
     }
     s.ymax = sw_max_i<SW>(ymax, mask);
@@ -587,7 +598,7 @@ dx_fit_grouped_kernel(const FitArgs P) {
             for (int t = sl; t < s.novf; t += SW) {
                 if (__ldg(s.ogrp + t) == k) {
                     const double y = (double)__ldg(s.oval + t);
-                    sk += y; qk += y * y; lgc += lgamma(y + 1.0); any = true;
+                    sk += y; qk += y * y; lgc += dx_lgamma(y + 1.0); any = true;
                 }
             }
             sk = sw_sum<SW>(sk, mask); qk = sw_sum<SW>(qk, mask);
@@ -602,7 +613,7 @@ dx_fit_grouped_kernel(const FitArgs P) {
     double n_total = 0.0, sum_all = 0.0, m_sf = 0.0, e2_sf = 0.0;
 #pragma unroll 1
     for (int k = 0; k < K; ++k) {
-        const double isf = P.offset ? exp(-smem_d[t_off + k]) : 1.0;
+        const double isf = P.offset ? dx_exp(-smem_d[t_off + k]) : 1.0;
         n_total += smem_d[t_nk + k];
         sum_all += Sk[k];
         m_sf += Sk[k] * isf;
@@ -617,7 +628,7 @@ dx_fit_grouped_kernel(const FitArgs P) {
     const dx_fit_opts& opts = P.opts;
     double areg = 0.0, breg = 0.0;
     if (opts.init_a == DX_INIT_STANDARD) {
-        areg = (sl == 0) ? dx_clip(log(sum_all / n_total), DX_ETA_MIN, DX_ETA_MAX) : 0.0;
+        areg = (sl == 0) ? dx_clip(dx_log(sum_all / n_total), DX_ETA_MIN, DX_ETA_MAX) : 0.0;
     } else if (opts.init_a == DX_INIT_CLOSED_FORM) {
         // batchglm closedform_glm_mean: log of the mean of x / size_factor over every distinct LOCATION design
         // row, pushed through the pseudo-inverse of those rows (np.linalg.lstsq in the reference)
@@ -628,11 +639,11 @@ dx_fit_grouped_kernel(const FitArgs P) {
 #pragma unroll 1
             for (int k = 0; k < K; ++k) {
                 if ((P.loc_group ? P.loc_group[k] : k) == l) {
-                    num += Sk[k] * (P.offset ? exp(-smem_d[t_off + k]) : 1.0);
+                    num += Sk[k] * (P.offset ? dx_exp(-smem_d[t_off + k]) : 1.0);
                     den += smem_d[t_nk + k];
                 }
             }
-            w1[l] = log(num / den + DX_TINY);
+            w1[l] = dx_log(num / den + DX_TINY);
         }
         __syncwarp(mask);
         if (sl < p) {
@@ -649,7 +660,7 @@ dx_fit_grouped_kernel(const FitArgs P) {
         const double m = m_sf / n_total;
         const double v = e2_sf / n_total - m * m;
         const double denom = fmax(v - m, 2.2227587494850775e-162);
-        breg = (sl == 0) ? dx_clip(log(m * m / denom + DX_TINY), DX_ETA_MIN, DX_ETA_MAX) : 0.0;
+        breg = (sl == 0) ? dx_clip(dx_log(m * m / denom + DX_TINY), DX_ETA_MIN, DX_ETA_MAX) : 0.0;
     } else if (opts.init_b == DX_INIT_GIVEN) {
         if (sl < ps) breg = dx_clip(P.b_var[(int64_t)sl * P.stride + g], DX_ETA_MIN, DX_ETA_MAX);
     }
