@@ -175,8 +175,23 @@ int dx_two_group_tests(int64_t n_genes, double n0, double n1,
     DX_CHECK(n_genes >= 0 && hist && ovf_count && indptr && out, "dx_two_group_tests: bad arguments");
     DX_CHECK(n0 >= 1 && n1 >= 1, "dx_two_group_tests: both groups need at least one cell");
     DX_CHECK(n0 + n1 <= 2097151.0 || !do_rank, "dx_two_group_tests: rank sums are exact up to 2^21-1 cells");
-    DX_CUDA(dx_launch_two_group(n_genes, n0, n1, hist, ovf_count, indptr, ovf_val, ovf_group, do_rank, out, u1x2, tie,
+    DX_CUDA(dx_launch_two_group(n_genes, 2, 0, 1, n0, n1, hist, ovf_count, indptr, ovf_val, ovf_group, do_rank, out, u1x2, tie,
                                 flags, (cudaStream_t)stream), "dx_two_group_tests");
+    return DX_OK;
+}
+
+int dx_group_pair_tests(int64_t n_genes, int32_t n_groups, int32_t group_a, int32_t group_b, double n_a, double n_b,
+                        const uint32_t* hist, const int32_t* ovf_count, const int64_t* indptr,
+                        const float* ovf_val, const uint8_t* ovf_group,
+                        int32_t do_rank, double* out, int64_t* u1x2, int64_t* tie, int32_t* flags, void* stream) {
+    DX_CHECK(n_genes >= 0 && hist && ovf_count && indptr && out, "dx_group_pair_tests: bad arguments");
+    DX_CHECK(n_groups >= 2 && n_groups <= DX_MAX_GROUPS, "dx_group_pair_tests: n_groups must be in 2..255");
+    DX_CHECK(group_a >= 0 && group_a < n_groups && group_b < n_groups && group_b != group_a,
+             "dx_group_pair_tests: group ids out of range");
+    DX_CHECK(n_a >= 1 && n_b >= 1, "dx_group_pair_tests: both samples need at least one cell");
+    DX_CHECK(n_a + n_b <= 2097151.0 || !do_rank, "dx_group_pair_tests: rank sums are exact up to 2^21-1 cells");
+    DX_CUDA(dx_launch_two_group(n_genes, n_groups, group_a, group_b, n_a, n_b, hist, ovf_count, indptr, ovf_val, ovf_group,
+                                do_rank, out, u1x2, tie, flags, (cudaStream_t)stream), "dx_group_pair_tests");
     return DX_OK;
 }
 

@@ -38,7 +38,7 @@ cudaError_t dx_launch_two_coef_z(int64_t n, const double* t0, const double* t1, 
                                  double* pval, cudaStream_t s);
 cudaError_t dx_launch_t_moments(int64_t n, const double* mu0, const double* mu1, const double* var0, const double* var1,
                                 double n0, double n1, double* pval, cudaStream_t s);
-cudaError_t dx_launch_two_group(int64_t G, double n0, double n1, const uint32_t* tail, const int32_t* ovf_count,
-                                const int64_t* indptr, const float* ovf_val, const uint8_t* ovf_group, int do_rank,
-                                double* out, int64_t* u1x2, int64_t* tie, int32_t* flags, cudaStream_t s);
+cudaError_t dx_launch_two_group(int64_t G, int K, int ga, int gb, double n0, double n1, const uint32_t* tail,
+                                const int32_t* ovf_count, const int64_t* indptr, const float* ovf_val, const uint8_t* ovf_group,
+                                int do_rank, double* out, int64_t* u1x2, int64_t* tie, int32_t* flags, cudaStream_t s);
 cudaError_t dx_launch_bh(int64_t n, const double* pval, double* qval, double* work, cudaStream_t s);

@@ -129,7 +129,7 @@ __device__ __forceinline__ unsigned dx_float_key(float v) {   // order-preservin
 }
 
 __global__ void __launch_bounds__(TG_T)
-dx_two_group_kernel(int64_t G, double n0, double n1, const uint32_t* __restrict__ tail_all,
+dx_two_group_kernel(int64_t G, int K, int ga, int gb, double n0, double n1, const uint32_t* __restrict__ tail_all,
                     const int32_t* __restrict__ ovf_count, const int64_t* __restrict__ indptr,
                     const float* __restrict__ ovf_val, const uint8_t* __restrict__ ovf_group, int do_rank,
                     double* __restrict__ out, int64_t* __restrict__ u1x2_out, int64_t* __restrict__ tie_out,
@@ -141,27 +141,45 @@ dx_two_group_kernel(int64_t G, double n0, double n1, const uint32_t* __restrict_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t g = blockIdx.x;
     if (g >= G) return;
-    const uint32_t* tail = tail_all + g * 2 * DX_HIST_BINS;
+    // sample 0 = group ga; sample 1 = group gb, or every other group when gb < 0 ("versus rest").  Tail counts are
+    // additive over groups, so the rest is the sum over k != ga.
+    __shared__ unsigned s_tail[2][DX_HIST_BINS + 1];
+    const uint32_t* tail_g = tail_all + g * (int64_t)K * DX_HIST_BINS;
     const int novf = ovf_count[g];
     const float* oval = ovf_val + indptr[g];
     const uint8_t* ogrp = ovf_group + indptr[g];
+    if (tid < 2 * DX_HIST_BINS) {
+        const int k = tid / DX_HIST_BINS, j = tid % DX_HIST_BINS;
+        unsigned c = 0;
+        if (k == 0) c = tail_g[ga * DX_HIST_BINS + j];
+        else if (gb >= 0) c = tail_g[gb * DX_HIST_BINS + j];
+        else { for (int kk = 0; kk < K; ++kk) if (kk != ga) c += tail_g[kk * DX_HIST_BINS + j]; }
+        s_tail[k][j] = c;
+    }
+    if (tid < 2) s_tail[tid][DX_HIST_BINS] = 0u;
+    __syncthreads();
+    auto member = [&](int t) -> int {      // 0 / 1: sample of overflow entry t; -1: not part of this comparison
+        const int og = ogrp[t];
+        if (og == ga) return 0;
+        if (gb >= 0) return (og == gb) ? 1 : -1;
+        return (og < K) ? 1 : -1;
+    };
     // bins from tail counts
     if (tid < 2 * DX_HIST_BINS) {
         const int k = tid / DX_HIST_BINS, j = tid % DX_HIST_BINS;
-        const unsigned cj = tail[k * DX_HIST_BINS + j];
-        const unsigned cn = (j + 1 < DX_HIST_BINS) ? tail[k * DX_HIST_BINS + j + 1] : 0u;
-        s_cnt[k][j + 1] = cj - cn;
+        s_cnt[k][j + 1] = s_tail[k][j] - s_tail[k][j + 1];
     }
     // moments: sum y, sum y^2, overflow counts per group
     double s0 = 0, q0 = 0, s1 = 0, q1 = 0, c0 = 0, c1 = 0;
     if (tid < 2 * DX_HIST_BINS) {
         const int k = tid / DX_HIST_BINS, j = tid % DX_HIST_BINS;
-        const double cj = (double)tail[k * DX_HIST_BINS + j];
+        const double cj = (double)s_tail[k][j];
         if (k == 0) { s0 += cj; q0 += cj * (2.0 * j + 1.0); } else { s1 += cj; q1 += cj * (2.0 * j + 1.0); }
     }
     for (int t = tid; t < novf; t += TG_T) {
         const double y = (double)oval[t];
-        if (ogrp[t] == 0) { s0 += y; q0 += y * y; c0 += 1.0; } else { s1 += y; q1 += y * y; c1 += 1.0; }
+        const int mb = member(t);
+        if (mb == 0) { s0 += y; q0 += y * y; c0 += 1.0; } else if (mb == 1) { s1 += y; q1 += y * y; c1 += 1.0; }
     }
     s0 = dx_warp_sum(s0); q0 = dx_warp_sum(q0); s1 = dx_warp_sum(s1); q1 = dx_warp_sum(q1);
     c0 = dx_warp_sum(c0); c1 = dx_warp_sum(c1);
@@ -172,8 +190,8 @@ dx_two_group_kernel(int64_t G, double n0, double n1, const uint32_t* __restrict_
     const double mean0 = s0 / n0, mean1 = s1 / n1;
     const double var0 = q0 / n0 - mean0 * mean0, var1 = q1 / n1 - mean1 * mean1;
     if (tid == 0) {
-        s_cnt[0][0] = (unsigned)(n0 - (double)tail[0] - c0);
-        s_cnt[1][0] = (unsigned)(n1 - (double)tail[DX_HIST_BINS] - c1);
+        s_cnt[0][0] = (unsigned)(n0 - (double)s_tail[0][0] - c0);
+        s_cnt[1][0] = (unsigned)(n1 - (double)s_tail[1][0] - c1);
     }
     int flags = 0;
     double p_rank = NAN;
@@ -190,7 +208,7 @@ dx_two_group_kernel(int64_t G, double n0, double n1, const uint32_t* __restrict_
                 for (int i = tid; i < mp; i += TG_T) {
                     unsigned key = 0xffffffffu;
                     if (i <= DX_HIST_BINS) key = dx_float_key((float)i);
-                    else if (i < m) key = dx_float_key(oval[i - DX_HIST_BINS - 1]);
+                    else if (i < m && member(i - DX_HIST_BINS - 1) >= 0) key = dx_float_key(oval[i - DX_HIST_BINS - 1]);
                     s_key[i] = key;
                     s_idx[i] = (unsigned)i;
                 }
@@ -225,7 +243,10 @@ dx_two_group_kernel(int64_t G, double n0, double n1, const uint32_t* __restrict_
                     while (e < m && ((novf > 0) ? s_key[e] : (unsigned)e) == key) {
                         const unsigned id = (novf > 0) ? s_idx[e] : (unsigned)e;
                         if (id <= DX_HIST_BINS) { ta += s_cnt[0][id]; tb += s_cnt[1][id]; }
-                        else if (ogrp[id - DX_HIST_BINS - 1] == 0) ta += 1; else tb += 1;
+                        else if (id < (unsigned)m) {        // (padding of the sort shares the largest key with skipped entries)
+                            const int mb = member((int)id - DX_HIST_BINS - 1);
+                            if (mb == 0) ta += 1; else if (mb == 1) tb += 1;
+                        }
                         ++e;
                     }
                     const long long t = ta + tb;
@@ -409,11 +430,11 @@ cudaError_t dx_launch_t_moments(int64_t n, const double* mu0, const double* mu1,
     dx_t_moments_kernel<<<grid1d(n, 128), 128, 0, s>>>(n, mu0, mu1, var0, var1, n0, n1, pval);
     return cudaGetLastError();
 }
-cudaError_t dx_launch_two_group(int64_t G, double n0, double n1, const uint32_t* tail, const int32_t* ovf_count,
-                                const int64_t* indptr, const float* ovf_val, const uint8_t* ovf_group, int do_rank,
-                                double* out, int64_t* u1x2, int64_t* tie, int32_t* flags, cudaStream_t s) {
+cudaError_t dx_launch_two_group(int64_t G, int K, int ga, int gb, double n0, double n1, const uint32_t* tail,
+                                const int32_t* ovf_count, const int64_t* indptr, const float* ovf_val, const uint8_t* ovf_group,
+                                int do_rank, double* out, int64_t* u1x2, int64_t* tie, int32_t* flags, cudaStream_t s) {
     if (G <= 0) return cudaSuccess;
-    dx_two_group_kernel<<<(unsigned)G, TG_T, 0, s>>>(G, n0, n1, tail, ovf_count, indptr, ovf_val, ovf_group, do_rank,
+    dx_two_group_kernel<<<(unsigned)G, TG_T, 0, s>>>(G, K, ga, gb, n0, n1, tail, ovf_count, indptr, ovf_val, ovf_group, do_rank,
                                                      out, u1x2, tie, flags);
     return cudaGetLastError();
 }

@@ -66,7 +66,7 @@ def _parse_formula(formula):
     intercept = True
     terms = []
     for tok in rhs.split("+"):
-        tok = tok.strip()
+        tok = tok.strip().replace(" ", "")
         if tok == "":
             continue
         if tok in ("1",):

@@ -169,6 +169,23 @@ def two_group_device(shard, cell_group, n0, n1, do_rank=True):
         return dict(out=out.cpu().numpy(), u1x2=u1x2.cpu().numpy(), tie=tie.cpu().numpy(), flags=flags.cpu().numpy())
 
 
+def group_pair_device(suff, group_a, group_b, n_a, n_b, do_rank=True):
+    """K_twogroup between two of the samples of ONE K_ingest pass (``suff``: SuffStats over n_groups samples):
+    sample 0 = group_a, sample 1 = group_b or, for group_b < 0, the union of all other groups."""
+    shard = suff.shard
+    dev = shard.device
+    with torch.cuda.device(dev):
+        g = shard.n_genes
+        out = torch.empty((g, _lib.TG_NCOL), dtype=torch.float64, device=dev)
+        u1x2 = torch.empty(g, dtype=torch.int64, device=dev)
+        tie = torch.empty(g, dtype=torch.int64, device=dev)
+        flags = torch.empty(g, dtype=torch.int32, device=dev)
+        _lib.call("dx_group_pair_tests", g, int(suff.n_groups), int(group_a), int(group_b), float(n_a), float(n_b),
+                  ptr(suff.tail), ptr(suff.ovf_count), ptr(shard.indptr), ptr(suff.ovf_val), ptr(suff.ovf_group),
+                  int(bool(do_rank)), ptr(out), ptr(u1x2), ptr(tie), ptr(flags), stream_ptr())
+        return dict(out=out.cpu().numpy(), u1x2=u1x2.cpu().numpy(), tie=tie.cpu().numpy(), flags=flags.cpu().numpy())
+
+
 def hypergeom_test(*args, **kwargs):
     """stats.py:329-355 belongs to gene-set enrichment, which is outside the accelerated hot path."""
     raise NotImplementedError("hypergeom_test (enrichment) is out of scope of diffxpy_b200")

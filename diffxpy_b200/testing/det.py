@@ -349,6 +349,34 @@ class DifferentialExpressionTestWald(_DifferentialExpressionTestSingle):
         return res
 
 
+def two_group_postprocess(out, flags, n0, n1, do_rank, is_logged=False, is_sig_zerovar=True):
+    """Host-side rules of the model-free tests on the rows K_twogroup produced (det.py:1564-1620, 1691-1743):
+    overall mean, run mask, zero-variance p-values, log fold change of sample 1 over sample 0."""
+    mean_x0 = out[:, _lib.TG_MEAN0].copy()
+    mean_x1 = out[:, _lib.TG_MEAN1].copy()
+    var_x0, var_x1 = out[:, _lib.TG_VAR0], out[:, _lib.TG_VAR1]
+    mean = np.asarray(np.average(a=np.vstack([mean_x0, mean_x1]),
+                                 weights=np.array([n0 / (n0 + n1), n1 / (n0 + n1)]), axis=0, returned=False)).flatten()
+    var_geq_zero = np.logical_or(var_x0 > 0, var_x1 > 0)
+    idx_run = np.where(np.logical_and(mean != 0, var_geq_zero))[0]
+    pval = np.zeros([out.shape[0]]) + np.nan
+    col = _lib.TG_PVAL_RANK if do_rank else _lib.TG_PVAL_T
+    if do_rank and np.any(flags[idx_run] & _lib.FLAG_RANK_OVERFLOW):
+        raise _lib.DxError("rank test: a gene has more non-count values than the on-chip sort holds (4031)")
+    pval[idx_run] = out[idx_run, col]
+    pval[np.where(np.logical_and(np.logical_and(mean_x0 == mean_x1, mean > 0), np.logical_not(var_geq_zero)))[0]] = 1.0
+    if is_sig_zerovar:
+        pval[np.where(np.logical_and(mean_x0 != mean_x1, np.logical_not(var_geq_zero)))[0]] = 0.0
+    res = dict(pval=pval, mean=mean, var_geq_zero=var_geq_zero, mean_x0=mean_x0.copy(), mean_x1=mean_x1.copy(),
+               var_x0=var_x0, var_x1=var_x1)
+    if is_logged:
+        res["logfc"] = mean_x1 - mean_x0
+    else:
+        tiny = np.nextafter(0, np.inf)
+        res["logfc"] = np.log(np.maximum(mean_x1, tiny)) - np.log(np.maximum(mean_x0, tiny))
+    return res
+
+
 class _DifferentialExpressionTestTwoGroup(_DifferentialExpressionTestSingle):
     """Shared constructor of the model-free tests (det.py:1545-1620 and 1672-1743): group split by first
     appearance, group means / ddof-0 variances, run mask, zero-variance rules, log fold change.  The moments,
@@ -378,37 +406,11 @@ class _DifferentialExpressionTestTwoGroup(_DifferentialExpressionTestSingle):
         n1 = int(np.sum(cell_group == 1))
         shard = CountShard.from_host(data)
         res = stats.two_group_device(shard, cell_group, n0, n1, do_rank=self._do_rank)
-        out = res["out"]
         self._u1x2, self._tie, self._flags = res["u1x2"], res["tie"], res["flags"]
-        mean_x0 = out[:, _lib.TG_MEAN0].copy()
-        mean_x1 = out[:, _lib.TG_MEAN1].copy()
-        var_x0, var_x1 = out[:, _lib.TG_VAR0], out[:, _lib.TG_VAR1]
-        self._mean = np.asarray(np.average(
-            a=np.vstack([mean_x0, mean_x1]),
-            weights=np.array([n0 / (n0 + n1), n1 / (n0 + n1)]),
-            axis=0, returned=False)).flatten()
-        self._ave_nonzero = self._mean != 0
-        self._var_geq_zero = np.logical_or(var_x0 > 0, var_x1 > 0)
-        idx_run = np.where(np.logical_and(self._ave_nonzero, self._var_geq_zero))[0]
-        pval = np.zeros([shard.n_genes]) + np.nan
-        col = _lib.TG_PVAL_RANK if self._do_rank else _lib.TG_PVAL_T
-        if self._do_rank and np.any(self._flags[idx_run] & _lib.FLAG_RANK_OVERFLOW):
-            raise _lib.DxError("rank test: a gene has more non-count values than the on-chip sort holds (4031)")
-        pval[idx_run] = out[idx_run, col]
-        pval[np.where(np.logical_and(
-            np.logical_and(mean_x0 == mean_x1, self._mean > 0),
-            np.logical_not(self._var_geq_zero)
-        ))[0]] = 1.0
-        if is_sig_zerovar:
-            pval[np.where(np.logical_and(mean_x0 != mean_x1, np.logical_not(self._var_geq_zero)))[0]] = 0.0
-        self._pval = pval
-        self._mean_x0, self._mean_x1, self._var_x0, self._var_x1 = mean_x0.copy(), mean_x1.copy(), var_x0, var_x1
-        if is_logged:
-            self._logfc = mean_x1 - mean_x0
-        else:
-            mean_x0 = np.nextafter(0, np.inf, out=mean_x0, where=mean_x0 < np.nextafter(0, np.inf))
-            mean_x1 = np.nextafter(0, np.inf, out=mean_x1, where=mean_x1 < np.nextafter(0, np.inf))
-            self._logfc = np.log(mean_x1) - np.log(mean_x0)
+        r = two_group_postprocess(res["out"], res["flags"], n0, n1, self._do_rank, is_logged, is_sig_zerovar)
+        self._mean, self._ave_nonzero, self._var_geq_zero = r["mean"], r["mean"] != 0, r["var_geq_zero"]
+        self._pval, self._logfc = r["pval"], r["logfc"]
+        self._mean_x0, self._mean_x1, self._var_x0, self._var_x1 = r["mean_x0"], r["mean_x1"], r["var_x0"], r["var_x1"]
 
     @property
     def gene_ids(self) -> np.ndarray:

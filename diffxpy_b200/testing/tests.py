@@ -1,6 +1,7 @@
 """
 de.test.* entry points (/root/reference/diffxpy/testing/tests.py): ``wald`` (:448-746), ``lrt`` (:252-445),
-``wald_repeated`` (:749-821), ``t_test`` (:824-863), ``rank_test`` (:866-905), ``two_sample`` (:908-1094) and the
+``wald_repeated`` (:749-821), ``t_test`` (:824-863), ``rank_test`` (:866-905), ``two_sample`` (:908-1094), the
+multi-test wrappers ``pairwise`` (:1097-1330), ``versus_rest`` (:1333-1506), ``partition`` (:1509-1968) and the
 estimator choke-point ``_fit`` (:26-249).  Same argument names, meaning and error behaviour; the estimator
 behind ``_fit`` is the CUDA one (diffxpy_b200.estimator), the only backend of this build.
 """
@@ -9,6 +10,7 @@ from typing import Union, List, Dict, Callable, Tuple
 
 import numpy as np
 import pandas as pd
+import scipy.sparse
 
 from ..data.design import DesignMatrix, design_matrix as _design_matrix
 from ..estimator import Estimator, InputDataGLM
@@ -383,3 +385,225 @@ def two_sample(data, grouping: Union[str, np.ndarray, list], as_numeric=(), test
     elif test.lower() == 'rank':
         return rank_test(data=data, gene_names=gene_names, grouping=grouping, is_sig_zerovar=is_sig_zerovar)
     raise ValueError('two_sample(): Parameter `test="%s"` not recognized.' % test)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# multi-test wrappers (tests.py:1097-1968).  The model-free variants (t-test / rank) of pairwise and versus_rest
+# read the matrix ONCE: K_ingest builds the count histograms of all groups, and every comparison is a launch of
+# K_twogroup on two of them (dx_group_pair_tests).  The model-based variants loop over the single tests like the
+# reference, except the z-test, which needs one fit.
+# ------------------------------------------------------------------------------------------------------------
+def _matrix_of(data):
+    """The cells x genes matrix behind what diffxpy accepts as ``data``."""
+    if isinstance(data, InputDataGLM):
+        return data.x
+    if hasattr(data, "X") and not isinstance(data, np.ndarray) and not scipy.sparse.issparse(data):
+        return data.X
+    return data
+
+
+def _column_means(x):
+    return np.asarray(x.mean(axis=0)).flatten()
+
+
+def _grouped_two_sample_setup(x, grouping, groups):
+    """One K_ingest pass over all groups: (SuffStats, cells per group, first cell of every group)."""
+    from ..device import CountShard
+    import torch
+    code = np.searchsorted(groups, grouping).astype(np.uint8)
+    counts = np.bincount(code, minlength=len(groups)).astype(np.int64)
+    first = np.array([int(np.argmax(code == k)) for k in range(len(groups))])
+    shard = CountShard.from_host(x)
+    with torch.cuda.device(shard.device):
+        suff = shard.group_suffstats(torch.from_numpy(code).to(shard.device), len(groups))
+    return suff, counts, first
+
+
+def pairwise(data, grouping: Union[str, np.ndarray, list], as_numeric=(), test: str = "z-test", lazy: bool = True,
+             gene_names: Union[np.ndarray, list] = None, sample_description: pd.DataFrame = None,
+             noise_model: str = "nb", size_factors: np.ndarray = None, batch_size=None, backend: str = "numpy",
+             train_args: dict = {}, training_strategy="AUTO", is_sig_zerovar: bool = True, quick_scale: bool = False,
+             dtype="float64", pval_correction: str = "global", keep_full_test_objs: bool = False, **kwargs):
+    """All pairs of groups (tests.py:1097-1330): "z-test" (one fit '~ 0 + group', then two-coefficient z-tests),
+    "wald", "lrt", "t-test" or "rank"."""
+    from .det import two_group_postprocess
+    from .det_pair import DifferentialExpressionTestZTest, DifferentialExpressionTestPairwiseStandard
+    from ..stats import stats as dstats
+    if len(kwargs) != 0:
+        logging.getLogger("diffxpy").info("additional kwargs: %s", str(kwargs))
+    is_z = test.lower() in ("z-test", "z_test", "ztest")
+    if lazy and not is_z:
+        raise ValueError("lazy evaluation of pairwise tests only possible if test is z-test")
+    gene_names = parse_gene_names(data, gene_names)
+    grouping = parse_grouping(data, sample_description, grouping)      # (a label array needs no sample_description)
+    sample_description = pd.DataFrame({"grouping": grouping})
+    groups = np.unique(grouping)
+    if is_z:
+        dmat = _design_matrix(sample_description=sample_description, formula="~ 1 - 1 + grouping")
+        # init_b="closed_form" of the reference (tests.py:1245) needs batchglm's group-wise dispersion start;
+        # the standard method-of-moments start converges to the same optimum
+        model = _fit(noise_model=noise_model, data=data, design_loc=dmat, design_scale=dmat, gene_names=gene_names,
+                     size_factors=size_factors, init_a="closed_form", init_b="standard", batch_size=batch_size,
+                     backend=backend, train_args=train_args, training_strategy=training_strategy,
+                     quick_scale=quick_scale, dtype=dtype, **kwargs)
+        return DifferentialExpressionTestZTest(model_estim=model, grouping=grouping, groups=groups,
+                                               correction_type=pval_correction)
+    x = _matrix_of(data)
+    n_genes = x.shape[1]
+    pvals = np.tile(np.nan, [len(groups), len(groups), n_genes])
+    pvals[np.eye(pvals.shape[0]).astype(bool)] = 0
+    logfc = np.tile(np.nan, [len(groups), len(groups), n_genes])
+    logfc[np.eye(logfc.shape[0]).astype(bool)] = 0
+    tests = np.tile([None], [len(groups), len(groups)]) if keep_full_test_objs else None
+    model_free = test.lower() in ("t-test", "t_test", "ttest", "rank")
+    if model_free and not keep_full_test_objs and len(groups) <= 255:
+        do_rank = test.lower() == "rank"
+        suff, counts, first = _grouped_two_sample_setup(x, grouping, groups)
+        for i in range(len(groups)):
+            for j in range(i + 1, len(groups)):
+                a, b = (i, j) if first[i] < first[j] else (j, i)        # sample 0 = the group that appears first
+                res = dstats.group_pair_device(suff, a, b, counts[a], counts[b], do_rank=do_rank)
+                r = two_group_postprocess(res["out"], res["flags"], counts[a], counts[b], do_rank, False, is_sig_zerovar)
+                pvals[i, j] = pvals[j, i] = r["pval"]
+                logfc[i, j] = r["logfc"]
+                logfc[j, i] = -logfc[i, j]
+    else:
+        for i, g1 in enumerate(groups):
+            for j in range(i + 1, len(groups)):
+                g2 = groups[j]
+                idx = np.where(np.logical_or(grouping == g1, grouping == g2))[0]
+                de_test_temp = two_sample(
+                    data=x[idx, :], grouping=grouping[idx], as_numeric=as_numeric, test=test, gene_names=gene_names,
+                    sample_description=sample_description.iloc[idx, :], noise_model=None if model_free else noise_model,
+                    size_factors=size_factors[idx] if size_factors is not None else None, batch_size=batch_size,
+                    backend=backend, train_args=train_args, training_strategy=training_strategy,
+                    quick_scale=quick_scale, is_sig_zerovar=is_sig_zerovar, dtype=dtype, **kwargs)
+                pvals[i, j] = pvals[j, i] = de_test_temp.pval
+                logfc[i, j] = de_test_temp.log_fold_change()
+                logfc[j, i] = -logfc[i, j]
+                if keep_full_test_objs:
+                    tests[i, j] = tests[j, i] = de_test_temp
+    return DifferentialExpressionTestPairwiseStandard(gene_ids=gene_names, pval=pvals, logfc=logfc, ave=_column_means(x),
+                                                      groups=groups, tests=tests, correction_type=pval_correction)
+
+
+def versus_rest(data, grouping: Union[str, np.ndarray, list], as_numeric=(), test: str = "wald",
+                gene_names: Union[np.ndarray, list] = None, sample_description: pd.DataFrame = None,
+                noise_model: str = None, size_factors: np.ndarray = None, batch_size=None, backend: str = "numpy",
+                train_args: dict = {}, training_strategy="AUTO", is_sig_zerovar: bool = True, quick_scale: bool = None,
+                dtype="float64", pval_correction: str = "global", keep_full_test_objs: bool = False, **kwargs):
+    """Every group against the union of all other groups (tests.py:1333-1506)."""
+    from .det import two_group_postprocess
+    from .det_pair import DifferentialExpressionTestVsRest
+    from ..stats import stats as dstats
+    if len(kwargs) != 0:
+        logging.getLogger("diffxpy").info("additional kwargs: %s", str(kwargs))
+    gene_names = parse_gene_names(data, gene_names)
+    grouping = parse_grouping(data, sample_description, grouping)      # (a label array needs no sample_description)
+    sample_description = pd.DataFrame({"grouping": grouping})
+    groups = np.unique(grouping)
+    x = _matrix_of(data)
+    n_genes = x.shape[1]
+    pvals = np.zeros([1, len(groups), n_genes])
+    logfc = np.zeros([1, len(groups), n_genes])
+    tests = np.tile([None], [1, len(groups)]) if keep_full_test_objs else None
+    model_free = test.lower() in ("t-test", "t_test", "ttest", "rank")
+    if model_free and not keep_full_test_objs and 2 <= len(groups) <= 255:
+        do_rank = test.lower() == "rank"
+        suff, counts, first = _grouped_two_sample_setup(x, grouping, groups)
+        n = int(counts.sum())
+        for i in range(len(groups)):
+            res = dstats.group_pair_device(suff, i, -1, counts[i], n - counts[i], do_rank=do_rank)
+            r = two_group_postprocess(res["out"], res["flags"], counts[i], n - counts[i], do_rank, False, is_sig_zerovar)
+            pvals[0, i] = r["pval"]
+            # two_sample() orders the samples by first appearance of "group" / "rest": the fold change is second over first
+            logfc[0, i] = r["logfc"] if first[i] == 0 else -r["logfc"]
+    else:
+        for i, g1 in enumerate(groups):
+            test_grouping = np.where(grouping == g1, "group", "rest")
+            de_test_temp = two_sample(
+                data=x, grouping=test_grouping, as_numeric=as_numeric, test=test, gene_names=gene_names,
+                sample_description=sample_description, noise_model=None if model_free else noise_model,
+                batch_size=batch_size, backend=backend,
+                train_args=train_args, training_strategy=training_strategy, quick_scale=quick_scale,
+                size_factors=size_factors, is_sig_zerovar=is_sig_zerovar, dtype=dtype, **kwargs)
+            pvals[0, i] = de_test_temp.pval
+            logfc[0, i] = de_test_temp.log_fold_change()
+            if keep_full_test_objs:
+                tests[0, i] = de_test_temp
+    return DifferentialExpressionTestVsRest(gene_ids=gene_names, pval=pvals, logfc=logfc, ave=_column_means(x),
+                                            groups=groups, tests=tests, correction_type=pval_correction)
+
+
+def partition(data, parts: Union[str, np.ndarray, list], gene_names: Union[np.ndarray, list] = None,
+              sample_description: pd.DataFrame = None):
+    """Run a single test inside every partition of the cells (tests.py:1509-1538):
+    ``de.test.partition(data, parts="tissue").wald(formula_loc=..., factor_loc_totest=...)``."""
+    return _Partition(data=data, parts=parts, gene_names=gene_names, sample_description=sample_description)
+
+
+class _Partition:
+    """tests.py:1541-1968: the partitioning of the cells, the per-partition test calls and their summary in one
+    DifferentialExpressionTestByPartition."""
+
+    def __init__(self, data, parts, gene_names=None, sample_description=None):
+        self.x = _matrix_of(data)
+        if not (isinstance(self.x, np.ndarray) or scipy.sparse.issparse(self.x)):
+            raise ValueError("data type %s not recognized" % type(data))
+        if scipy.sparse.issparse(self.x):
+            self.x = self.x.tocsr()
+        self.gene_names = parse_gene_names(data, gene_names)
+        self.partition = parse_grouping(data, sample_description, parts)
+        if sample_description is None and not (hasattr(data, "obs")):
+            sample_description = pd.DataFrame({"partition": self.partition})
+        self.sample_description = parse_sample_description(data, sample_description)
+        self.partitions = np.unique(self.partition)
+        self.partition_idx = [np.where(self.partition == x)[0] for x in self.partitions]
+
+    def _collect(self, fn):
+        from .det_pair import DifferentialExpressionTestByPartition
+        tests = [fn(idx) for idx in self.partition_idx]
+        return DifferentialExpressionTestByPartition(partitions=self.partitions, tests=tests, ave=_column_means(self.x),
+                                                     correction_type="by_test")
+
+    def two_sample(self, grouping: str, as_numeric=(), test=None, size_factors: np.ndarray = None, noise_model: str = None,
+                   batch_size=None, backend: str = "numpy", train_args: dict = {}, training_strategy="AUTO",
+                   is_sig_zerovar: bool = True, **kwargs):
+        return self._collect(lambda idx: two_sample(
+            data=self.x[idx, :], grouping=grouping, as_numeric=as_numeric, test=test, gene_names=self.gene_names,
+            sample_description=self.sample_description.iloc[idx, :], noise_model=noise_model,
+            size_factors=size_factors[idx] if size_factors is not None else None, batch_size=batch_size, backend=backend,
+            train_args=train_args, training_strategy=training_strategy, is_sig_zerovar=is_sig_zerovar, **kwargs))
+
+    def t_test(self, grouping: str, is_logged: bool = False, is_sig_zerovar: bool = True, dtype="float64"):
+        return self._collect(lambda idx: t_test(
+            data=self.x[idx, :], grouping=grouping, is_logged=is_logged, gene_names=self.gene_names,
+            sample_description=self.sample_description.iloc[idx, :], is_sig_zerovar=is_sig_zerovar))
+
+    def rank_test(self, grouping: str, is_sig_zerovar: bool = True, dtype="float64"):
+        return self._collect(lambda idx: rank_test(
+            data=self.x[idx, :], grouping=grouping, gene_names=self.gene_names,
+            sample_description=self.sample_description.iloc[idx, :], is_sig_zerovar=is_sig_zerovar))
+
+    def lrt(self, full_formula_loc: str = None, reduced_formula_loc: str = None, full_formula_scale: str = "~1",
+            reduced_formula_scale: str = "~1", as_numeric=(), init_a="AUTO", init_b="AUTO", size_factors: np.ndarray = None,
+            noise_model="nb", batch_size=None, backend: str = "numpy", train_args: dict = {}, training_strategy="AUTO",
+            **kwargs):
+        return self._collect(lambda idx: lrt(
+            data=self.x[idx, :], full_formula_loc=full_formula_loc, reduced_formula_loc=reduced_formula_loc,
+            full_formula_scale=full_formula_scale, reduced_formula_scale=reduced_formula_scale, as_numeric=as_numeric,
+            init_a=init_a, init_b=init_b, gene_names=self.gene_names, sample_description=self.sample_description.iloc[idx, :],
+            noise_model=noise_model, size_factors=size_factors[idx] if size_factors is not None else None,
+            batch_size=batch_size, backend=backend, train_args=train_args, training_strategy=training_strategy, **kwargs))
+
+    def wald(self, factor_loc_totest: str = None, coef_to_test: object = None, formula_loc: str = None,
+             formula_scale: str = "~1", as_numeric=(), constraints_loc: np.ndarray = None,
+             constraints_scale: np.ndarray = None, noise_model: str = "nb", size_factors: np.ndarray = None, batch_size=None,
+             backend: str = "numpy", train_args: dict = {}, training_strategy="AUTO", **kwargs):
+        return self._collect(lambda idx: wald(
+            data=self.x[idx, :], factor_loc_totest=factor_loc_totest, coef_to_test=coef_to_test, formula_loc=formula_loc,
+            formula_scale=formula_scale, as_numeric=as_numeric, constraints_loc=constraints_loc,
+            constraints_scale=constraints_scale, gene_names=self.gene_names,
+            sample_description=self.sample_description.iloc[idx, :], noise_model=noise_model,
+            size_factors=size_factors[idx] if size_factors is not None else None, batch_size=batch_size, backend=backend,
+            train_args=train_args, training_strategy=training_strategy, **kwargs))

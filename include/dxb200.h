@@ -169,6 +169,14 @@ int dx_two_group_tests(int64_t n_genes, double n0, double n1,
                        const float* ovf_val, const uint8_t* ovf_group,
                        int32_t do_rank, double* out, int64_t* u1x2, int64_t* tie, int32_t* flags, void* stream);
 
+/* The same two tests between any two of the n_groups samples of ONE dx_group_suffstats pass (pairwise / versus-rest
+ * comparisons, tests.py:1097-1330, 1333-1506, without re-reading the matrix): sample 0 = group_a; sample 1 =
+ * group_b, or the union of all other groups when group_b < 0.  n_a, n_b: cells per sample. */
+int dx_group_pair_tests(int64_t n_genes, int32_t n_groups, int32_t group_a, int32_t group_b, double n_a, double n_b,
+                        const uint32_t* hist, const int32_t* ovf_count, const int64_t* indptr,
+                        const float* ovf_val, const uint8_t* ovf_group,
+                        int32_t do_rank, double* out, int64_t* u1x2, int64_t* tie, int32_t* flags, void* stream);
+
 /* ---- host-buffer entry point (what bench.py's e2e leg and a foreign-language binding call) ---------
  * Full Wald test of one coefficient on a HOST CSC matrix with a grouped design: copies the inputs to
  * the device, runs ingest + fit + Wald, copies the per-gene rows back.  Pointers are host memory
