@@ -607,3 +607,111 @@ class _Partition:
             sample_description=self.sample_description.iloc[idx, :], noise_model=noise_model,
             size_factors=size_factors[idx] if size_factors is not None else None, batch_size=batch_size, backend=backend,
             train_args=train_args, training_strategy=training_strategy, **kwargs))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# continuous covariates (tests.py:1971-2370)
+# ------------------------------------------------------------------------------------------------------------
+def _replace_continuous(formula: str, continuous: str, new_coefs: List[str]) -> str:
+    """Replace the continuous covariate by its spline basis columns in a formula, distributing over interactions
+    (what the reference obtains by substituting '(c0+c1+...)' into the patsy formula, tests.py:2236-2245)."""
+    from ..data.design import _parse_formula
+    intercept, terms = _parse_formula(formula)
+    out = []
+    for t in terms:
+        parts = t.split(":")
+        if continuous in parts:
+            rest = [x for x in parts if x != continuous]
+            for c in new_coefs:
+                out.append(":".join([c] + rest))
+        else:
+            out.append(t)
+    return "~ " + " + ".join((["1"] if intercept else ["0"]) + out)
+
+
+def continuous_1d(data, continuous: str, factor_loc_totest: Union[str, List[str]], formula_loc: str, formula_scale: str = "~1",
+                  df: int = 5, spline_basis: str = "bs", as_numeric=(), test: str = 'wald', init_a="standard", init_b="standard",
+                  gene_names: Union[np.ndarray, list] = None, sample_description=None, constraints_loc=None,
+                  constraints_scale=None, noise_model: str = 'nb', size_factors=None, batch_size=None, backend: str = "numpy",
+                  train_args: dict = {}, training_strategy="AUTO", quick_scale: bool = None, dtype="float64", **kwargs):
+    """Differential expression along a continuous covariate, modelled by a spline basis with ``df`` degrees of freedom
+    (tests.py:1971-2370).  ``spline_basis="bs"`` (cubic B-splines, the reference default) is built without patsy
+    (diffxpy_b200.data.splines); the natural / cyclic cubic bases "cr" / "cc" are not available.
+
+    LRT: the reduced location model is the location formula without the tested factors.  (The reference derives it
+    from ``formula_scale`` at tests.py:2311, an evident slip that silently drops every untested location term.)"""
+    from ..data.splines import bs
+    from .det_cont import DifferentialExpressionTestWaldCont, DifferentialExpressionTestLRTCont
+    if isinstance(factor_loc_totest, str):
+        factor_loc_totest = [factor_loc_totest]
+    elif isinstance(factor_loc_totest, tuple):
+        factor_loc_totest = list(factor_loc_totest)
+    if isinstance(as_numeric, str):
+        as_numeric = [as_numeric]
+    as_numeric = list(as_numeric)
+    gene_names = parse_gene_names(data, gene_names)
+    sample_description = parse_sample_description(data, sample_description).copy()
+    if continuous not in sample_description.columns:
+        raise ValueError('parameter continuous not found in sample_description')
+    if not pd.api.types.is_numeric_dtype(sample_description[continuous]):
+        raise ValueError("The column corresponding to the continuous covariate ('%s') in " % continuous +
+                         "sample description should be numeric but is '%s'" % sample_description[continuous].dtype)
+    coords = np.asarray(sample_description[continuous].values, dtype=np.float64)
+    if len(np.unique(coords)) <= df - 1:
+        raise ValueError("Use at most (number of observed points in continuous covariate) - 1 degrees of freedom " +
+                         " for spline basis. You chose df=%i for n=%i points." % (df, len(np.unique(coords))))
+    if spline_basis.lower() == "bs":
+        basis = bs(coords, df=df, degree=3, include_intercept=False)
+    elif spline_basis.lower() in ("cr", "cc"):
+        raise ValueError("spline basis %s is not available in diffxpy_b200 (only 'bs')" % spline_basis)
+    else:
+        raise ValueError("spline basis %s not recognized" % spline_basis)
+    new_coefs = [continuous + str(i) for i in range(basis.shape[1])]
+    # interpolated basis on a uniform grid; like the reference (tests.py:2218-2229) its knots come from the grid itself
+    grid = np.linspace(np.min(coords), np.max(coords), 100)
+    interpolated_spline_basis = np.hstack([np.ones([100, 1]), bs(grid, df=df, degree=3, include_intercept=False),
+                                           np.expand_dims(grid, axis=1)])
+    formula_loc_new = _replace_continuous(formula_loc, continuous, new_coefs)
+    formula_scale_new = _replace_continuous(formula_scale, continuous, new_coefs)
+    for i, c in enumerate(new_coefs):
+        sample_description[c] = basis[:, i]
+    as_numeric.extend(new_coefs)
+
+    if test.lower() == 'wald':
+        if noise_model is None:
+            raise ValueError("Please specify noise_model")
+        totest = []
+        for f in factor_loc_totest:
+            parts = f.split(":")
+            if continuous in parts:
+                rest = [x for x in parts if x != continuous]
+                totest.extend(":".join([c] + rest) for c in new_coefs)
+            else:
+                totest.append(f)
+        de_test = wald(data=data, factor_loc_totest=totest, coef_to_test=None, formula_loc=formula_loc_new,
+                       formula_scale=formula_scale_new, as_numeric=as_numeric, init_a=init_a, init_b=init_b,
+                       gene_names=gene_names, sample_description=sample_description, constraints_loc=constraints_loc,
+                       constraints_scale=constraints_scale, noise_model=noise_model, size_factors=size_factors,
+                       batch_size=batch_size, backend=backend, train_args=train_args, training_strategy=training_strategy,
+                       quick_scale=quick_scale, dtype=dtype, **kwargs)
+        return DifferentialExpressionTestWaldCont(de_test=de_test, noise_model=noise_model, size_factors=size_factors,
+                                                  continuous_coords=coords, spline_coefs=new_coefs,
+                                                  interpolated_spline_basis=interpolated_spline_basis)
+    elif test.lower() == 'lrt':
+        if noise_model is None:
+            raise ValueError("Please specify noise_model")
+        from ..data.design import _parse_formula
+        intercept, terms = _parse_formula(formula_loc)
+        kept = [t for t in terms if t not in factor_loc_totest and not (set(t.split(":")) & set(factor_loc_totest))]
+        reduced = "~ " + " + ".join((["1"] if intercept else ["0"]) + kept)
+        reduced_formula_loc = _replace_continuous(reduced, continuous, new_coefs)
+        de_test = lrt(data=data, full_formula_loc=formula_loc_new, reduced_formula_loc=reduced_formula_loc,
+                      full_formula_scale=formula_scale_new, reduced_formula_scale=formula_scale_new, as_numeric=as_numeric,
+                      init_a=init_a, init_b=init_b, gene_names=gene_names, sample_description=sample_description,
+                      noise_model=noise_model, size_factors=size_factors, batch_size=batch_size, backend=backend,
+                      train_args=train_args, training_strategy=training_strategy, quick_scale=quick_scale, dtype=dtype,
+                      **kwargs)
+        return DifferentialExpressionTestLRTCont(de_test=de_test, size_factors=size_factors, continuous_coords=coords,
+                                                 spline_coefs=new_coefs, interpolated_spline_basis=interpolated_spline_basis,
+                                                 noise_model=noise_model)
+    raise ValueError('continuous(): Parameter `test` not recognized.')

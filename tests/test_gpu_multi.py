@@ -141,3 +141,65 @@ def test_partition_equals_tests_on_subsets(de):
     assert list(res.summary().columns) == ["gene", "pval", "qval", "log2fc", "mean"]
     t2 = p.two_sample(grouping="condition", test="t-test")
     assert t2.pval.shape == (1, 2, g)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# continuous_1d (reference unit_test/test_continuous_null.py, test_continuous_de.py re-expressed)
+# ---------------------------------------------------------------------------------------------------------
+def _continuous_data(seed, n=2000, g=100, de_frac=0.5):
+    rng = np.random.default_rng(seed)
+    t = rng.uniform(0, 1, n)
+    base = rng.uniform(np.log(5), np.log(50), g)
+    amp = np.where(np.arange(g) < int(de_frac * g), rng.uniform(0.6, 1.2, g), 0.0)
+    eta = base[None, :] + amp[None, :] * np.sin(2 * np.pi * t)[:, None]
+    x = rng.poisson(rng.gamma(2.0, np.exp(eta) / 2.0)).astype(np.float64)
+    sd = pd.DataFrame({"pseudotime": t, "batch": rng.integers(0, 2, n).astype(str)})
+    return x, sd, amp > 0
+
+
+def test_continuous_1d_null_calibration_and_power(de):
+    x, sd, is_de = _continuous_data(11, de_frac=0.0)
+    names = ["g%d" % i for i in range(x.shape[1])]
+    res = de.test.continuous_1d(data=x, continuous="pseudotime", df=5, formula_loc="~ 1 + pseudotime",
+                                formula_scale="~ 1", factor_loc_totest="pseudotime", test="wald",
+                                sample_description=sd, gene_names=names)
+    assert scipy.stats.kstest(res.pval, "uniform").pvalue > 0.01, "continuous_1d Wald p-values are not calibrated"
+    assert res._de_test.model_estim.a_var.shape[0] == 6                      # intercept + df spline coefficients
+    x, sd, is_de = _continuous_data(12, de_frac=0.5)
+    res = de.test.continuous_1d(data=x, continuous="pseudotime", df=5, formula_loc="~ 1 + pseudotime + batch",
+                                formula_scale="~ 1", factor_loc_totest="pseudotime", test="wald",
+                                sample_description=sd, gene_names=names)
+    q = res.qval
+    assert np.mean(q[is_de] < 0.05) >= 0.5 and np.mean(q[~is_de] < 0.05) <= 0.1
+    summ = res.summary()
+    assert list(summ.columns[:6]) == ["gene", "pval", "qval", "log2fc", "mean", "zero_mean"]
+    # fold change of the fitted curve: GPU scan == per-gene numpy evaluation of the reference recipe
+    genes = [0, 3, 77]
+    vals = res._continuous_model(idx=np.array(genes))
+    want = (np.log(vals.max(axis=0)) - np.log(vals.min(axis=0))) / np.log(2)
+    np.testing.assert_allclose(res.log2_fold_change(genes=genes), want, rtol=1e-10)
+    np.testing.assert_allclose(summ["log2fc"].values[genes], want, rtol=1e-10)
+    np.testing.assert_array_equal(res.argmax(genes), sd["pseudotime"].values[vals.argmax(axis=0)])
+    np.testing.assert_allclose(res.max(genes), vals.max(axis=0), rtol=1e-12)
+    assert np.mean(summ["log2fc"].values[is_de]) > 3 * np.mean(summ["log2fc"].values[~is_de])
+    t_eval, mu = res._continuous_interpolation(idx=0)
+    assert t_eval.shape == (100,) and mu.shape == (100, 1)
+
+
+def test_continuous_1d_lrt_and_errors(de):
+    x, sd, is_de = _continuous_data(13, n=1500, g=40, de_frac=0.5)
+    names = ["g%d" % i for i in range(x.shape[1])]
+    res = de.test.continuous_1d(data=x, continuous="pseudotime", df=4, formula_loc="~ 1 + pseudotime + batch",
+                                formula_scale="~ 1", factor_loc_totest="pseudotime", test="lrt",
+                                sample_description=sd, gene_names=names)
+    assert res._de_test.reduced_estim.a_var.shape[0] == 2 and res._de_test.full_estim.a_var.shape[0] == 6
+    assert np.mean(res.qval[is_de] < 0.05) >= 0.5 and np.mean(res.qval[~is_de] < 0.05) <= 0.15
+    with pytest.raises(ValueError):
+        de.test.continuous_1d(data=x, continuous="nope", df=4, formula_loc="~ 1 + nope", factor_loc_totest="nope",
+                              sample_description=sd, gene_names=names)
+    with pytest.raises(ValueError):
+        de.test.continuous_1d(data=x, continuous="batch", df=4, formula_loc="~ 1 + batch", factor_loc_totest="batch",
+                              sample_description=sd, gene_names=names)
+    with pytest.raises(ValueError):
+        de.test.continuous_1d(data=x, continuous="pseudotime", df=4, spline_basis="cr", formula_loc="~ 1 + pseudotime",
+                              factor_loc_totest="pseudotime", sample_description=sd, gene_names=names)

@@ -96,3 +96,24 @@ def test_gene_ranges_cover_and_balance():
     loads = [w[a:b].sum() for a, b in r]
     assert r[0][0] == 0 and r[-1][1] == 10 and abs(loads[0] - loads[1]) <= 100
     assert dxdist.gene_ranges(5, 1) == [(0, 5)]
+
+
+def test_bs_basis_matches_splev_recipe_and_formula_rewrite():
+    """data/splines.py restates patsy's bs(x, df, degree=3, include_intercept=False) (tests.py:2196-2200)."""
+    from scipy.interpolate import splev
+    from diffxpy_b200.data.splines import bs, bs_knots
+    from diffxpy_b200.testing.tests import _replace_continuous
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-2, 3, 400)
+    for df in (3, 5, 8):
+        b = bs(x, df)
+        assert b.shape == (400, df)
+        k = bs_knots(x, df)
+        assert len(k) == df + 1 + 4 and k[0] == x.min() and k[-1] == x.max()
+        n = len(k) - 4
+        ref = np.stack([splev(x, (k, np.eye(n)[i], 3)) for i in range(n)], axis=1)[:, 1:]
+        np.testing.assert_allclose(b, ref, atol=1e-14)
+        np.testing.assert_allclose(np.quantile(x, np.linspace(0, 1, df - 3 + 2)[1:-1]), k[4:-4])
+    assert _replace_continuous("~ 1 + pt + batch + pt:cond", "pt", ["pt0", "pt1"]) == \
+        "~ 1 + pt0 + pt1 + batch + pt0:cond + pt1:cond"
+    assert _replace_continuous("~ 1", "pt", ["pt0"]) == "~ 1"
