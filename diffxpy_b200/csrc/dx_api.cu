@@ -168,6 +168,12 @@ int dx_bh_qvalues(int64_t n, const double* pval, double* qval, double* work, voi
     return DX_OK;
 }
 
+int dx_bh_qvalues_sorted(int64_t n, const double* p_sorted, const int64_t* order, double* qval, double* work, void* stream) {
+    DX_CHECK(n >= 0 && p_sorted && order && qval && work, "dx_bh_qvalues_sorted: bad arguments");
+    DX_CUDA(dx_launch_bh_sorted(n, p_sorted, order, qval, work, (cudaStream_t)stream), "dx_bh_qvalues_sorted");
+    return DX_OK;
+}
+
 int dx_two_group_tests(int64_t n_genes, double n0, double n1,
                        const uint32_t* hist, const int32_t* ovf_count, const int64_t* indptr,
                        const float* ovf_val, const uint8_t* ovf_group,

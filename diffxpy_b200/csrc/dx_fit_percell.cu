@@ -17,7 +17,6 @@ constexpr int PT = 256;            // threads per CTA
 constexpr int TILE = 2048;         // cells densified per tile
 constexpr int NW = PT / 32;
 
-__device__ unsigned int g_gene_queue;
 
 enum PassMode { PASS_LL = 0, PASS_LOC = 1, PASS_SCALE = 2 };
 
@@ -271,7 +270,7 @@ dx_fit_percell_kernel(int64_t n_genes, int64_t N, int p, int ps,
                       const int64_t* __restrict__ indptr, const int32_t* __restrict__ rows, const float* __restrict__ vals,
                       dx_fit_opts opts, double* __restrict__ a_var, double* __restrict__ b_var,
                       double* __restrict__ fim_inv, double* __restrict__ ll_out, double* __restrict__ jac_out,
-                      int32_t* __restrict__ niter_out, int32_t* __restrict__ flags_out) {
+                      int32_t* __restrict__ niter_out, int32_t* __restrict__ flags_out, unsigned int* __restrict__ gene_queue) {
     using P = Pass<PMAX, PSMAX>;
     extern __shared__ __align__(16) unsigned char smraw[];
     Smem sm;
@@ -288,7 +287,7 @@ dx_fit_percell_kernel(int64_t n_genes, int64_t N, int p, int ps,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ int s_gene;
     for (;;) {
-        if (tid == 0) s_gene = (int)atomicAdd(&g_gene_queue, 1u);
+        if (tid == 0) s_gene = (int)atomicAdd(gene_queue, 1u);
         __syncthreads();
         const int64_t g = s_gene;
         __syncthreads();
@@ -482,15 +481,13 @@ cudaError_t launch_t(int64_t n_genes, int64_t n_cells, int p, int ps, const doub
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PT, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    void* qaddr = nullptr;
-    e = cudaGetSymbolAddress(&qaddr, g_gene_queue);
-    if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(qaddr, 0, sizeof(unsigned int), stream);
+    unsigned int* queue = nullptr;          // per-launch work queue slot (safe with concurrent launches on other streams)
+    e = dx_queue_acquire(stream, &queue);
     if (e != cudaSuccess) return e;
     int64_t grid = (int64_t)sm_count * per_sm;
     if (grid > n_genes) grid = n_genes;
     kern<<<(unsigned)grid, PT, smem, stream>>>(n_genes, n_cells, p, ps, dl, ds, log_sf, indptr, rows, vals, *opts,
-                                               a_var, b_var, fim_inv, ll, jac, niter, flags);
+                                               a_var, b_var, fim_inv, ll, jac, niter, flags, queue);
     return cudaGetLastError();
 }
 

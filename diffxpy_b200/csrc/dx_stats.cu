@@ -360,35 +360,105 @@ dx_bh_scatter_kernel(int64_t G, const double* __restrict__ p, const int* __restr
     }
 }
 
-// running minimum from the right over the sorted table (one CTA), then q_i = min(1, table[cnt_i - 1])
+// ---- running minimum from the right, multi-CTA: chunk minima, then per-chunk suffix scan with the carry of the later
+// chunks.  SORTED: the values are p_sorted[j] / ((j + 1) / n) (n = number of non-NaN = index of the first NaN) and the
+// result is scattered through `order`; otherwise the values are the table of dx_bh_scatter_kernel, scanned in place.
+__device__ __forceinline__ int64_t dx_first_nan(const double* __restrict__ ps, int64_t G) {
+    int64_t lo = 0, hi = G;                 // NaNs sort last: first index with ps[idx] != ps[idx]
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const double v = ps[mid];
+        if (v == v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <bool SORTED>
+__device__ __forceinline__ double dx_bh_value(const double* __restrict__ src, int64_t j, int64_t G, double dn) {
+    if (j >= G) return INFINITY;
+    const double v = src[j];
+    if (!SORTED) return v;
+    return (v == v) ? v / ((double)(j + 1) / dn) : INFINITY;       // statsmodels: p_sorted / (rank / n)
+}
+
+template <bool SORTED>
 __global__ void __launch_bounds__(BH_ST)
-dx_bh_scan_kernel(int64_t G, const double* __restrict__ p, const int* __restrict__ cnt, double* __restrict__ tsorted,
-                  double* __restrict__ q) {
-    __shared__ double s_min[BH_ST];
+dx_bh_chunkmin_kernel(int64_t G, const double* __restrict__ src, double* __restrict__ chunk_min) {
+    __shared__ double s_w[BH_ST / 32];
+    __shared__ double s_n;
     const int tid = threadIdx.x;
-    const int64_t L = (G + BH_ST - 1) / BH_ST;
-    const int64_t lo = (int64_t)tid * L, hi = (lo + L < G) ? lo + L : G;
-    double m = INFINITY;
-    for (int64_t j = lo; j < hi; ++j) m = fmin(m, tsorted[j]);
-    s_min[tid] = m;
+    if (SORTED) { if (tid == 0) s_n = (double)dx_first_nan(src, G); __syncthreads(); }
+    const double dn = SORTED ? s_n : 1.0;
+    double m = dx_bh_value<SORTED>(src, (int64_t)blockIdx.x * BH_ST + tid, G, dn);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(DX_FULL_MASK, m, o));
+    if ((tid & 31) == 0) s_w[tid >> 5] = m;
     __syncthreads();
-    // suffix minimum over the chunk minima: s_min[t] = min over chunks >= t (Hillis-Steele)
-    for (int o = 1; o < BH_ST; o <<= 1) {
-        const double other = (tid + o < BH_ST) ? s_min[tid + o] : INFINITY;
-        __syncthreads();
-        s_min[tid] = fmin(s_min[tid], other);
-        __syncthreads();
+    if (tid == 0) {
+        double r = INFINITY;
+#pragma unroll
+        for (int w = 0; w < BH_ST / 32; ++w) r = fmin(r, s_w[w]);
+        chunk_min[blockIdx.x] = r;
     }
-    double run = (tid + 1 < BH_ST) ? s_min[tid + 1] : INFINITY;
-    for (int64_t j = hi - 1; j >= lo; --j) {
-        run = fmin(run, tsorted[j]);
-        tsorted[j] = run;
+}
+
+template <bool SORTED>
+__global__ void __launch_bounds__(BH_ST)
+dx_bh_suffix_kernel(int64_t G, double* __restrict__ src, const double* __restrict__ chunk_min, int n_chunks,
+                    const int64_t* __restrict__ order, double* __restrict__ q) {
+    __shared__ double s_w[BH_ST / 32];
+    __shared__ double s_carry, s_n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (SORTED) { if (tid == 0) s_n = (double)dx_first_nan(src, G); }
+    // carry = minimum over all later chunks
+    double c = INFINITY;
+    for (int b = blockIdx.x + 1 + tid; b < n_chunks; b += BH_ST) c = fmin(c, chunk_min[b]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c = fmin(c, __shfl_xor_sync(DX_FULL_MASK, c, o));
+    if (lane == 0) s_w[warp] = c;
+    __syncthreads();
+    if (tid == 0) {
+        double r = INFINITY;
+#pragma unroll
+        for (int w = 0; w < BH_ST / 32; ++w) r = fmin(r, s_w[w]);
+        s_carry = r;
     }
     __syncthreads();
-    for (int64_t i = tid; i < G; i += BH_ST) {
-        const double pi = p[i];
-        q[i] = (pi == pi) ? fmin(tsorted[cnt[i] - 1], 1.0) : NAN;
+    const double carry = s_carry;
+    const double dn = SORTED ? s_n : 1.0;
+    const int64_t j = (int64_t)blockIdx.x * BH_ST + tid;
+    const double v = dx_bh_value<SORTED>(src, j, G, dn);
+    // suffix minimum inside the warp, then across the warps of the CTA
+    double m = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_down_sync(DX_FULL_MASK, m, o);
+        if (lane + o < 32) m = fmin(m, t);
     }
+    __syncthreads();
+    if (lane == 0) s_w[warp] = m;          // minimum of the whole warp
+    __syncthreads();
+    double later = carry;
+    for (int w = warp + 1; w < BH_ST / 32; ++w) later = fmin(later, s_w[w]);
+    m = fmin(m, later);
+    if (j < G) {
+        if (SORTED) {
+            const double pj = src[j];
+            q[order[j]] = (pj == pj) ? fmin(m, 1.0) : NAN;
+        } else {
+            src[j] = m;
+        }
+    }
+}
+
+// q_i = min(1, table[cnt_i - 1]) after the in-place suffix scan of the table
+__global__ void __launch_bounds__(256)
+dx_bh_gather_kernel(int64_t G, const double* __restrict__ p, const int* __restrict__ cnt, const double* __restrict__ table,
+                    double* __restrict__ q) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= G) return;
+    const double pi = p[i];
+    q[i] = (pi == pi) ? fmin(table[cnt[i] - 1], 1.0) : NAN;
 }
 
 }  // namespace
@@ -441,13 +511,26 @@ cudaError_t dx_launch_two_group(int64_t G, int K, int ga, int gb, double n0, dou
 
 cudaError_t dx_launch_bh(int64_t n, const double* pval, double* qval, double* work, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
-    // work: n doubles (table sorted by p) followed by n ints (cnt)
-    int* cnt = reinterpret_cast<int*>(work + n);
+    // work: n doubles (table sorted by p) + ceil(n / 1024) doubles (chunk minima) + n ints (cnt)
+    const int n_chunks = (int)((n + BH_ST - 1) / BH_ST);
+    double* chunk_min = work + n;
+    int* cnt = reinterpret_cast<int*>(chunk_min + n_chunks);
     cudaError_t e = cudaMemsetAsync(cnt, 0, (size_t)n * sizeof(int), s);
     if (e != cudaSuccess) return e;
     const dim3 grid((unsigned)((n + BH_T * BH_R - 1) / (BH_T * BH_R)), BH_JS);
     dx_bh_rank_kernel<<<grid, BH_T, 0, s>>>(n, pval, cnt, work);
     dx_bh_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, pval, cnt, work);
-    dx_bh_scan_kernel<<<1, BH_ST, 0, s>>>(n, pval, cnt, work, qval);
+    dx_bh_chunkmin_kernel<false><<<n_chunks, BH_ST, 0, s>>>(n, work, chunk_min);
+    dx_bh_suffix_kernel<false><<<n_chunks, BH_ST, 0, s>>>(n, work, chunk_min, n_chunks, nullptr, nullptr);
+    dx_bh_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, pval, cnt, work, qval);
+    return cudaGetLastError();
+}
+
+cudaError_t dx_launch_bh_sorted(int64_t n, const double* p_sorted, const int64_t* order, double* qval, double* work,
+                                cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    const int n_chunks = (int)((n + BH_ST - 1) / BH_ST);      // work: ceil(n / 1024) doubles
+    dx_bh_chunkmin_kernel<true><<<n_chunks, BH_ST, 0, s>>>(n, p_sorted, work);
+    dx_bh_suffix_kernel<true><<<n_chunks, BH_ST, 0, s>>>(n, const_cast<double*>(p_sorted), work, n_chunks, order, qval);
     return cudaGetLastError();
 }

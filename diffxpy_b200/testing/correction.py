@@ -9,7 +9,7 @@ import torch
 from .. import _lib
 from ..device import cuda_device, ptr, stream_ptr
 
-BH_KERNEL_MAX = 65536     # above this the all-pairs kernel loses to a device sort
+BH_KERNEL_MAX = 32768     # above this the all-pairs kernel loses to a device sort
 
 
 def bh_device(p):
@@ -17,20 +17,14 @@ def bh_device(p):
     if p.shape[0] <= BH_KERNEL_MAX:
         p = p.contiguous()
         q = torch.empty_like(p)
-        work = torch.empty((p.shape[0] * 3 + 1) // 2, dtype=torch.float64, device=p.device)   # n doubles + n int32
+        work = torch.empty((p.shape[0] * 3 + 1) // 2 + p.shape[0] // 1024 + 2, dtype=torch.float64, device=p.device)
         _lib.call("dx_bh_qvalues", p.shape[0], ptr(p), ptr(q), ptr(work), stream_ptr())
         return q
-    # sort path, no host synchronisation: NaNs sort last and are masked out of the running minimum
-    g = p.shape[0]
-    ps, order = torch.sort(p, stable=True)
-    bad = torch.isnan(ps)
-    n = (g - bad.sum()).to(torch.float64)                       # 0-d tensor: true division like numpy's
-    ecdf = torch.arange(1, g + 1, dtype=torch.float64, device=p.device) / n
-    qs = torch.where(bad, torch.full_like(ps, float("inf")), ps / ecdf)
-    qs = torch.flip(torch.cummin(torch.flip(qs, [0]), 0).values, [0])
-    qs = torch.where(bad, torch.full_like(ps, float("nan")), torch.clamp(qs, max=1.0))
-    q = torch.empty_like(qs)
-    q[order] = qs
+    # large n: device sort (NaNs last) + one kernel for ranks, running minimum and the scatter back
+    ps, order = torch.sort(p.contiguous())
+    q = torch.empty_like(ps)
+    work = torch.empty(ps.shape[0] // 1024 + 2, dtype=torch.float64, device=p.device)
+    _lib.call("dx_bh_qvalues_sorted", ps.shape[0], ptr(ps), ptr(order), ptr(q), ptr(work), stream_ptr())
     return q
 
 

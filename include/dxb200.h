@@ -151,8 +151,12 @@ int dx_t_test_moments(int64_t n, const double* mu0, const double* mu1, const dou
 
 /* Benjamini-Hochberg q-values of the non-NaN p-values (correction.py:5-24 -> statsmodels fdr_bh arithmetic,
  * bit-identical values; all-pairs formulation without a sort, meant for n up to ~1e5).
- * work: 12 * n bytes (n doubles + n int32), 8-byte aligned. */
+ * work: 8 * (n + ceil(n / 1024)) + 4 * n bytes, 8-byte aligned. */
 int dx_bh_qvalues(int64_t n, const double* pval, double* qval, double* work, void* stream);
+/* Same q-values for large n, after a device sort done by the caller: p_sorted ascending with NaNs last, order[j] =
+ * position of p_sorted[j] in the unsorted vector (what torch.sort / cub return); qval is written unsorted.
+ * work: ceil(n / 1024) doubles. */
+int dx_bh_qvalues_sorted(int64_t n, const double* p_sorted, const int64_t* order, double* qval, double* work, void* stream);
 
 /* ---- K_twogroup: det.py:1545-1620 (Welch t) and det.py:1672-1743 (Mann-Whitney U) from the
  * 2-group sufficient statistics of dx_group_suffstats (group 0 = first sample, group 1 = second).

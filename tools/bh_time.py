@@ -1,7 +1,8 @@
 import torch, numpy as np, sys
 sys.path.insert(0, '/root/repo')
 from diffxpy_b200.testing import correction
-p = torch.rand(20000, dtype=torch.float64, device='cuda')
+import sys as _s
+p = torch.rand(int(_s.argv[1]) if len(_s.argv) > 1 else 20000, dtype=torch.float64, device='cuda')
 def t(fn, n=20):
     for _ in range(3): fn()
     torch.cuda.synchronize()
