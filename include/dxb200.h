@@ -17,6 +17,12 @@
  *   - return 0 on success, a DX_ERR_* code otherwise; dx_last_error() gives the message (thread local).
  *   - the count matrix shard is gene-major compressed (CSC of the cells x genes matrix):
  *       indptr[G+1] int64, rows[nnz] int32 (cell index, ascending inside a gene), vals[nnz] float32.
+ *     When rows and vals are 16-byte aligned (any cudaMalloc / pool allocation) K_ingest streams them with TMA bulk
+ *     copies in 16-byte units: both arrays must then be readable up to the next 16-byte boundary past their last
+ *     element (allocation granularity guarantees it; the extra bytes are never used).  Unaligned arrays take the
+ *     plain-load kernel.
+ *   - work queues of the dynamic-scheduling kernels live in a 1 KB device array owned by the library (one slot per
+ *     launch, ring of 256): launches on different streams do not interfere.
  */
 #ifndef DXB200_H
 #define DXB200_H
