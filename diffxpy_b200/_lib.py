@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdxb200.so")
+LIB_PATH = os.environ.get("DXB200_LIB") or os.path.join(_HERE, "libdxb200.so")   # env override: tuning builds
 
 DX_HIST_BINS = 64
 DX_MAX_GROUPS = 255
@@ -16,6 +16,7 @@ DX_SKIP_GROUP = 255
 DX_MAX_COEF = 32
 
 DX_SHARD_INTEGER_COUNTS = 1
+DX_OPT_SCALE_CONST = 1
 DX_INIT_GIVEN, DX_INIT_STANDARD, DX_INIT_CLOSED_FORM, DX_INIT_ALL_ZERO = 0, 1, 2, 3
 
 FLAG_CONVERGED, FLAG_SINGULAR_FIM, FLAG_SCALE_FROZEN, FLAG_NONFINITE, FLAG_ALL_ZERO, FLAG_RANK_OVERFLOW = 1, 2, 4, 8, 16, 32

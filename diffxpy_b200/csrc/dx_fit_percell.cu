@@ -34,10 +34,16 @@ struct Smem {
 __device__ __forceinline__ double g_ratio(double r, double y) {
     const int yi = (int)y;
     if ((double)yi == y && yi >= 1 && yi <= 12) {
-        double s = 0.0;
+        // sum_{j<y} log(1 + j/r) = log(prod_{j<y} (1 + j/r)): one log; the product stays far below overflow for
+        // y <= 12 unless r < 1e-24, where the lgamma form takes over
+        if (yi == 1) return 0.0;
+        if (r > 1e-24) {
+            const double ir = 1.0 / r;
+            double prod = 1.0 + ir;
 #pragma unroll 1
-        for (int j = 1; j < yi; ++j) s += log1p((double)j / r);
-        return s;
+            for (int j = 2; j < yi; ++j) prod *= fma((double)j, ir, 1.0);
+            return log(prod);
+        }
     }
     return dx_lgamma_ratio(r, y);
 }
@@ -87,7 +93,7 @@ struct Pass {
                                  int64_t N, int p, int ps, const double* __restrict__ dl, const double* __restrict__ ds,
                                  const double* __restrict__ log_sf, const int32_t* __restrict__ rows,
                                  const float* __restrict__ vals, int64_t e_start, int64_t e_end,
-                                 double* A_out, double* rhs_out, double lgam_const) {
+                                 double* A_out, double* rhs_out, double lgam_const, bool scale_const) {
         const int tid = threadIdx.x;
         double acc[NRED];
 #pragma unroll
@@ -97,6 +103,10 @@ struct Pass {
         for (int j = 0; j < PMAX; ++j) av[j] = (j < p) ? avec[j] : 0.0;
 #pragma unroll
         for (int j = 0; j < PSMAX; ++j) bv[j] = (j < ps) ? bvec[j] : 0.0;
+        // constant dispersion model (one scale coefficient, identical design value in every cell): r is a per-pass scalar
+        const double z_const = scale_const ? __ldg(ds) : 0.0;
+        const double zeta_const = scale_const ? dx_clip(z_const * bv[0], DX_ETA_MIN, DX_ETA_MAX) : 0.0;
+        const double r_const = scale_const ? exp(zeta_const) : 0.0;
         if (tid == 0) sm.ictl[0] = 0;       // entry cursor (relative to e_start)
         __syncthreads();
         for (int64_t t0 = 0; t0 < N; t0 += TILE) {
@@ -126,21 +136,41 @@ struct Pass {
                 const double y = (double)sm.ytile[c];
                 double x[PMAX];
                 double eta = log_sf ? log_sf[i] : 0.0;
+                {
+#ifdef DX_PC_OLDLOAD
 #pragma unroll
-                for (int j = 0; j < PMAX; ++j) {
-                    x[j] = (j < p) ? dl[(int64_t)j * N + i] : 0.0;
-                    eta += x[j] * av[j];
+                    for (int j = 0; j < PMAX; ++j) {
+                        x[j] = (j < p) ? dl[(int64_t)j * N + i] : 0.0;
+                        eta += x[j] * av[j];
+                    }
+#else
+                    const double* px = dl + i;           // coefficient-major design: column j of cell i at px + j * N
+#pragma unroll
+                    for (int j = 0; j < PMAX; ++j) {
+                        x[j] = (j < p) ? *px : 0.0;
+                        px += N;
+                        eta += x[j] * av[j];
+                    }
+#endif
                 }
                 eta = dx_clip(eta, DX_ETA_MIN, DX_ETA_MAX);
                 double z[PSMAX];
-                double zeta = 0.0;
+                double zeta = zeta_const;
+                if (!scale_const) {
+                    zeta = 0.0;
+                    const double* pz = ds + i;
 #pragma unroll
-                for (int j = 0; j < PSMAX; ++j) {
-                    z[j] = (j < ps) ? ds[(int64_t)j * N + i] : 0.0;
-                    zeta += z[j] * bv[j];
+                    for (int j = 0; j < PSMAX; ++j) {
+                        z[j] = (j < ps) ? __ldg(pz) : 0.0;
+                        pz += N;
+                        zeta += z[j] * bv[j];
+                    }
+                    zeta = dx_clip(zeta, DX_ETA_MIN, DX_ETA_MAX);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < PSMAX; ++j) z[j] = (j == 0) ? z_const : 0.0;
                 }
-                zeta = dx_clip(zeta, DX_ETA_MIN, DX_ETA_MAX);
-                const double mu = exp(eta), r = exp(zeta);
+                const double mu = exp(eta), r = scale_const ? r_const : exp(zeta);
                 const double l1p = log1p(mu / r);
                 double ll = -r * l1p;
                 if (y != 0.0) ll += g_ratio(r, y) + y * (eta - l1p);
@@ -245,7 +275,9 @@ __device__ bool percell_direction(const Smem& sm, int ps, int lane) {
 }
 
 // max_i clip(z_i . b): decides whether the scale predictor sits on the numerical plateau (all threads get it)
-__device__ double scale_eta_max(const Smem& sm, const double* __restrict__ ds, const double* bvec, int64_t N, int ps) {
+__device__ double scale_eta_max(const Smem& sm, const double* __restrict__ ds, const double* bvec, int64_t N, int ps,
+                                bool scale_const) {
+    if (scale_const) return dx_clip(__ldg(ds) * bvec[0], DX_ETA_MIN, DX_ETA_MAX);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double m = -INFINITY;
 #pragma unroll 1
@@ -285,6 +317,7 @@ dx_fit_percell_kernel(int64_t n_genes, int64_t N, int p, int ps,
         sm.ytile = reinterpret_cast<float*>(d);
     }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool scale_const = (ps == 1) && (opts.reserved & DX_OPT_SCALE_CONST);
     __shared__ int s_gene;
     for (;;) {
         if (tid == 0) s_gene = (int)atomicAdd(gene_queue, 1u);
@@ -309,7 +342,7 @@ dx_fit_percell_kernel(int64_t n_genes, int64_t N, int p, int ps,
         const int freq = train_scale ? (train_loc ? opts.update_b_freq : 1) : 0x7fffffff;
         int epochs_until_b = freq;
         bool loc_conv = false, fully = false, have_terms = true;
-        double nll = -P::run(PASS_LOC, sm, sm.a, sm.b, N, p, ps, dl, ds, log_sf, rows, vals, e0, e1, sm.A, sm.rhs, lgam_const);
+        double nll = -P::run(PASS_LOC, sm, sm.a, sm.b, N, p, ps, dl, ds, log_sf, rows, vals, e0, e1, sm.A, sm.rhs, lgam_const, scale_const);
         int step = 0;
         while (!fully && step < opts.max_steps) {
             double nll_new = nll;
@@ -319,12 +352,12 @@ dx_fit_percell_kernel(int64_t n_genes, int64_t N, int p, int ps,
                     // ---- safeguarded Newton in b (oracle _b_step_newton) -------------------------------------
                     for (int i = tid; i < ps; i += PT) sm.bt[i] = sm.b[i];       // bt = working copy, b = old
                     __syncthreads();
-                    double zmax = scale_eta_max(sm, ds, sm.bt, N, ps);
+                    double zmax = scale_eta_max(sm, ds, sm.bt, N, ps, scale_const);
                     bool moved = false;
                     double f = -nll;
                     if (zmax < DX_ETA_SCALE_FROZEN) {
                         for (int it = 0; it < opts.newton_max_iter; ++it) {
-                            P::run(PASS_SCALE, sm, sm.a, sm.bt, N, p, ps, dl, ds, log_sf, rows, vals, e0, e1, nullptr, nullptr, lgam_const);
+                            P::run(PASS_SCALE, sm, sm.a, sm.bt, N, p, ps, dl, ds, log_sf, rows, vals, e0, e1, nullptr, nullptr, lgam_const, scale_const);
                             if (warp == 0) {
                                 bool ok = percell_direction(sm, ps, lane);
                                 double smax = 0.0, pred = 0.0;
@@ -348,7 +381,7 @@ dx_fit_percell_kernel(int64_t n_genes, int64_t N, int p, int ps,
                                 for (int i = tid; i < ps; i += PT)
                                     sm.gb[i] = dx_clip(sm.bt[i] + t * sm.sb[i], DX_ETA_MIN, DX_ETA_MAX);
                                 __syncthreads();
-                                f_try = P::run(PASS_LL, sm, sm.a, sm.gb, N, p, ps, dl, ds, log_sf, rows, vals, e0, e1, nullptr, nullptr, lgam_const);
+                                f_try = P::run(PASS_LL, sm, sm.a, sm.gb, N, p, ps, dl, ds, log_sf, rows, vals, e0, e1, nullptr, nullptr, lgam_const, scale_const);
                                 if (isfinite(f_try) && f_try >= f) { accepted = true; break; }
                                 t *= 0.5;
                             }
@@ -357,7 +390,7 @@ dx_fit_percell_kernel(int64_t n_genes, int64_t N, int p, int ps,
                             __syncthreads();
                             f = f_try;
                             moved = true;
-                            zmax = scale_eta_max(sm, ds, sm.bt, N, ps);
+                            zmax = scale_eta_max(sm, ds, sm.bt, N, ps, scale_const);
                             if (zmax >= DX_ETA_SCALE_FROZEN) break;
                         }
                     }
@@ -375,7 +408,7 @@ dx_fit_percell_kernel(int64_t n_genes, int64_t N, int p, int ps,
             } else {
                 if (train_loc && !loc_conv) {
                     if (!have_terms) {
-                        P::run(PASS_LOC, sm, sm.a, sm.b, N, p, ps, dl, ds, log_sf, rows, vals, e0, e1, sm.A, sm.rhs, lgam_const);
+                        P::run(PASS_LOC, sm, sm.a, sm.b, N, p, ps, dl, ds, log_sf, rows, vals, e0, e1, sm.A, sm.rhs, lgam_const, scale_const);
                         have_terms = true;
                     }
                     if (warp == 0) {
@@ -395,7 +428,7 @@ dx_fit_percell_kernel(int64_t n_genes, int64_t N, int p, int ps,
                     }
                     __syncthreads();
                     if (!sm.ictl[2]) flags |= DX_FLAG_SINGULAR_FIM;
-                    const double nll_prop = -P::run(PASS_LOC, sm, sm.at, sm.b, N, p, ps, dl, ds, log_sf, rows, vals, e0, e1, sm.A2, sm.rhs2, lgam_const);
+                    const double nll_prop = -P::run(PASS_LOC, sm, sm.at, sm.b, N, p, ps, dl, ds, log_sf, rows, vals, e0, e1, sm.A2, sm.rhs2, lgam_const, scale_const);
                     if (!isfinite(nll_prop)) flags |= DX_FLAG_NONFINITE;
                     if (isfinite(nll_prop) && !(nll_prop > nll)) {
                         for (int i = tid; i < p; i += PT) { sm.a[i] = sm.at[i]; sm.rhs[i] = sm.rhs2[i]; }
@@ -420,9 +453,9 @@ dx_fit_percell_kernel(int64_t n_genes, int64_t N, int p, int ps,
         if (fully) flags |= DX_FLAG_CONVERGED;
         // ---- finalize --------------------------------------------------------------------------------------
         if (!have_terms)
-            P::run(PASS_LOC, sm, sm.a, sm.b, N, p, ps, dl, ds, log_sf, rows, vals, e0, e1, sm.A, sm.rhs, lgam_const);
-        P::run(PASS_SCALE, sm, sm.a, sm.b, N, p, ps, dl, ds, log_sf, rows, vals, e0, e1, nullptr, nullptr, lgam_const);
-        if (scale_eta_max(sm, ds, sm.b, N, ps) >= DX_ETA_SCALE_FROZEN) flags |= DX_FLAG_SCALE_FROZEN;
+            P::run(PASS_LOC, sm, sm.a, sm.b, N, p, ps, dl, ds, log_sf, rows, vals, e0, e1, sm.A, sm.rhs, lgam_const, scale_const);
+        P::run(PASS_SCALE, sm, sm.a, sm.b, N, p, ps, dl, ds, log_sf, rows, vals, e0, e1, nullptr, nullptr, lgam_const, scale_const);
+        if (scale_eta_max(sm, ds, sm.b, N, ps, scale_const) >= DX_ETA_SCALE_FROZEN) flags |= DX_FLAG_SCALE_FROZEN;
         if (warp == 0) {
             double jac = 0.0;
             for (int i = lane; i < p; i += 32) jac += fabs(sm.rhs[i]);

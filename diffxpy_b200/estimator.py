@@ -74,13 +74,24 @@ def group_rows(mat):
     _, idx, inv = np.unique(h, return_index=True, return_inverse=True)
     inv = np.asarray(inv).reshape(-1)
     reps = mat[idx]
-    if idx.shape[0] > 4096 or not np.array_equal(reps[inv].view(np.uint64), bits):
+    if idx.shape[0] > 65536:
+        return _group_rows_exact(mat)
+    if not np.array_equal(reps[inv].view(np.uint64), bits):
         return _group_rows_exact(mat)
     # renumber in the byte order of the representative rows (what the exact method returns)
     uniq, order_inv = _group_rows_exact(reps)
     if uniq.shape[0] != reps.shape[0]:
         return _group_rows_exact(mat)
     return uniq, order_inv[inv]
+
+
+def few_distinct_rows(mat, limit=4096, probe=8192):
+    """group_rows(mat) when the matrix has at most ``limit`` distinct rows, else None (decided on a prefix first, so a
+    continuous design costs one small probe instead of a sort of all its rows)."""
+    if mat.shape[0] > probe and group_rows(mat[:probe])[0].shape[0] > limit:
+        return None
+    g = group_rows(mat)
+    return g if g[0].shape[0] <= limit else None
 
 
 def rank_of_rows(mat, groups=None):
@@ -120,8 +131,8 @@ class InputDataGLM:
         xh_loc = self.design_loc if constraints_loc is None else self.design_loc @ self.constraints_loc
         xh_scale = self.design_scale if constraints_scale is None else self.design_scale @ self.constraints_scale
         # distinct rows of the constrained designs: rank check here, design groups in Estimator.initialize()
-        self._groups_loc = group_rows(xh_loc) if n >= 4096 else None
-        self._groups_scale = group_rows(xh_scale) if n >= 4096 else None
+        self._groups_loc = few_distinct_rows(xh_loc) if n >= 4096 else None
+        self._groups_scale = few_distinct_rows(xh_scale) if n >= 4096 else None
         r_loc = rank_of_rows(xh_loc, self._groups_loc)
         if r_loc != xh_loc.shape[1]:
             raise ValueError("constrained design matrix design_loc is not full rank: %i %i" % (xh_loc.shape[1], r_loc))
@@ -411,6 +422,8 @@ class Estimator:
                 if first:
                     self._percell_init(a_var, b_var, a_mode, b_mode)
                     opts.init_a = opts.init_b = _lib.DX_INIT_GIVEN
+                if ps == 1 and np.all(idata.xh_scale == idata.xh_scale[0, 0]):
+                    opts.reserved |= _lib.DX_OPT_SCALE_CONST          # constant dispersion model
                 _lib.call("dx_nb_fit_percell", g, shard.n_cells, p, ps, ptr(plan["design_loc"]),
                           ptr(plan["design_scale"]), ptr(plan["log_sf"]), ptr(shard.indptr), ptr(shard.rows),
                           ptr(shard.vals), opts, ptr(a_var), ptr(b_var), ptr(fim_inv), ptr(ll), ptr(jac),

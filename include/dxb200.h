@@ -56,6 +56,10 @@ extern "C" {
 #define DX_INIT_CLOSED_FORM 2  /* a: pinv(unique design) @ log(group means)  (location model only) */
 #define DX_INIT_ALL_ZERO 3
 
+/* dx_fit_opts.reserved bits */
+#define DX_OPT_SCALE_CONST 1   /* per-cell path: p_scale == 1 and design_scale is the same value in every cell (the caller
+                                  verified it): the dispersion is evaluated once per pass instead of once per cell */
+
 typedef struct dx_fit_opts {
     int32_t max_steps;        /* train(): max_steps, DEFAULT strategy 1000 */
     int32_t update_b_freq;    /* train(): update_b_freq, DEFAULT strategy 5 */
@@ -64,7 +68,7 @@ typedef struct dx_fit_opts {
     int32_t init_a;           /* DX_INIT_* */
     int32_t init_b;           /* DX_INIT_* (closed form for b is resolved by the host into GIVEN) */
     int32_t newton_max_iter;  /* scale Newton iterations per scale step (100) */
-    int32_t reserved;
+    int32_t reserved;         /* option bits: DX_OPT_SCALE_CONST */
     double lltol;             /* batchglm LLTOL_BY_FEATURE 1e-10 */
     double newton_xtol;       /* 1e-8 */
 } dx_fit_opts;
