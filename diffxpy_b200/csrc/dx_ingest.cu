@@ -617,9 +617,8 @@ cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32
         auto kern = (flags & DX_SHARD_INTEGER_COUNTS) ? dx_ingest_tma_kernel<true> : dx_ingest_tma_kernel<false>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        int64_t grid = sm_count;
-        const int64_t need = (n_genes + warps - 1) / warps;
-        if (grid > need) grid = need;
+        int64_t grid = sm_count;                    // persistent CTAs; the warps pull genes from the queue
+        if (grid > n_genes) grid = n_genes;
         kern<<<(unsigned)grid, warps * 32, smem, stream>>>(n_genes, indptr, rows, vals, cell_group, K, ysh, NW, NWA, hist,
                                                            ovf_count, ovf_val, ovf_group, queue, gene_order, warp_bytes);
         return cudaGetLastError();
