@@ -260,6 +260,7 @@ def main_cuda(args):
     fim_inv, ll, jac = torch.empty((g, p, p), **f64), torch.empty(g, **f64), torch.empty(g, **f64)
     niter, flags = torch.empty(g, dtype=torch.int32, device=dev), torch.empty(g, dtype=torch.int32, device=dev)
     rows_out = torch.empty((4, g), **f64)          # theta, sd, pval, log pval
+    pv_all = torch.empty(world * g, **f64) if world > 1 else None
     ev = lambda: torch.cuda.Event(enable_timing=True)
     kern_events = []
 
@@ -282,10 +283,9 @@ def main_cuda(args):
             e[3].record()
             kern_events.append(e)
         pv = rows_out[2]
-        if world > 1:      # the one collective of the path: per-gene rows of every rank
-            parts = [torch.empty_like(rows_out) for _ in range(world)]
-            td.all_gather(parts, rows_out)
-            pv = torch.cat([q[2] for q in parts])
+        if world > 1:      # the one collective of the path: the per-gene p-values of every rank (q-values couple all genes)
+            td.all_gather_into_tensor(pv_all, pv)
+            pv = pv_all
         return bh_device(pv)
 
     def barrier():
