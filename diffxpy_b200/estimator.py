@@ -409,6 +409,8 @@ class Estimator:
                                   train_loc=int(plan["train_loc"]), train_scale=int(plan["train_scale"]),
                                   init_a=a_mode, init_b=b_mode, newton_max_iter=100, reserved=0,
                                   lltol=LLTOL_BY_FEATURE, newton_xtol=1e-8)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
             if plan["kind"] == "grouped":
                 if "suff" not in plan:
                     plan["suff"] = shard.group_suffstats(plan["cell_group"], plan["k"])
@@ -428,6 +430,8 @@ class Estimator:
                           ptr(plan["design_scale"]), ptr(plan["log_sf"]), ptr(shard.indptr), ptr(shard.rows),
                           ptr(shard.vals), opts, ptr(a_var), ptr(b_var), ptr(fim_inv), ptr(ll), ptr(jac),
                           ptr(niter), ptr(flags), stream_ptr())
+            ev1.record()
+            self._timings["train_events"] = (ev0, ev1)
             if first:
                 self._niter_total = niter
             else:
@@ -496,6 +500,15 @@ class Estimator:
         )
         self._gathered = packed
         return self
+
+    @property
+    def device_train_ms(self):
+        """Device time of the last train() call (K_ingest on first use + K_fit), from CUDA events."""
+        ev = self._timings.get("train_events")
+        if ev is None:
+            return None
+        ev[1].synchronize()
+        return ev[0].elapsed_time(ev[1])
 
     def _h(self, key):
         if getattr(self, "_host", None) is None:

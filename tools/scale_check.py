@@ -108,6 +108,7 @@ def cfg4(n_cells=250_000, n_genes=512):
     bytes_iter = 8.0 * shard.nnz + n_cells * (xd.shape[1] * 8 + 8) * n_genes      # design + log sf re-read per gene (L2)
     return {"config": "configs[3]: de.test.wald, %d cells x %d genes (of 30k), 12 spline coefficients, size factors" % (n_cells, n_genes),
             "nnz": shard.nnz, "p_loc": int(xd.shape[1]), "seconds": sec, "genes_per_s": n_genes / sec,
+            "device_train_ms": est.device_train_ms,
             "frac_converged": float(np.mean((est.error_codes & 1) != 0)), "mean_niter": float(np.mean(nit)),
             "seconds_per_gene_iteration": sec / float(np.sum(nit)),
             "count_stream_gbs_per_iteration": 8.0 * shard.nnz * float(np.mean(nit)) / sec / 1e9}
