@@ -173,6 +173,42 @@ def test_ingest_ex_order_and_integer_flag(de):
     assert not CountShard.from_host(x).integer_counts
 
 
+def test_ingest_long_ragged_genes_all_alignments(de):
+    """TMA ingest edge cases: empty genes (first / middle / last), every start alignment modulo 4 elements, genes longer
+    than one counter-flush interval (> 255 entries per lane), exact multiples of the tile size, K = 2 and K = 32."""
+    from diffxpy_b200.device import CountShard
+    rng = np.random.default_rng(3)
+    n = 40000
+    lens = [0, 1, 2, 3, 5, 255, 256, 257, 511, 512, 513, 0, 0, 1023, 1024, 8160, 8161, 8192, 30000, 39999, 7, 0]
+    cols, rws, vls = [], [], []
+    for gi, m in enumerate(lens):
+        r = np.sort(rng.choice(n, size=m, replace=False))
+        v = rng.integers(1, 12, size=m).astype(np.float32)
+        if m > 100:
+            v[::97] = 70.0          # above the direct bins
+            v[5::89] = 2.5          # non-integer
+        cols.append(np.full(m, gi)); rws.append(r); vls.append(v)
+    x = scipy.sparse.csc_matrix((np.concatenate(vls), (np.concatenate(rws), np.concatenate(cols))), shape=(n, len(lens)))
+    dense = np.asarray(x.todense())
+    for k in (2, 32):
+        grp = rng.integers(0, k, n).astype(np.uint8)
+        grp[::501] = 255
+        shard = CountShard.from_host(x)
+        assert not shard.integer_counts
+        suff = shard.group_suffstats(torch.from_numpy(grp).cuda(), k)
+        torch.cuda.synchronize()
+        tail = suff.tail.cpu().numpy().view(np.uint32)
+        oc = suff.ovf_count.cpu().numpy()
+        for gi in range(len(lens)):
+            col = dense[:, gi]
+            isbin = (col >= 1) & (col <= 64) & (col == np.floor(col))
+            for kk in range(k):
+                sel = isbin & (grp == kk)
+                want = np.array([(col[sel] > j).sum() for j in range(64)])
+                np.testing.assert_array_equal(tail[gi, kk], want, err_msg="gene %d group %d" % (gi, kk))
+            assert oc[gi] == ((col != 0) & ~isbin & (grp != 255)).sum()
+
+
 def test_ingest_csr_csc_dense_inputs_agree(de):
     rng = np.random.default_rng(0)
     x = rng.poisson(0.7, size=(500, 30)).astype(np.float32)
