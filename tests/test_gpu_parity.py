@@ -293,6 +293,51 @@ def test_fit_size_factor_groups_and_scale_model(de, fmt):
     np.testing.assert_allclose(est.b_var, ref["b_var"], rtol=1e-5, atol=1e-6)
 
 
+def test_cfg2_full_cell_count_against_oracle(de):
+    """BASELINE configs[1] at its full cell count (100 000 cells, '~ 1 + condition + batch' with 8 batches, sparse input),
+    on a handful of genes the CPU oracle can afford: coefficients, Fisher inverse, ll, niter and flags."""
+    rng = np.random.default_rng(2024)
+    n, g = 100_000, 10
+    cond = rng.integers(0, 2, n)
+    batch = rng.integers(0, 8, n)
+    xd = np.concatenate([np.ones((n, 1)), cond[:, None], (batch[:, None] == np.arange(1, 8)[None])], axis=1).astype(float)
+    log_mu = rng.uniform(np.log(0.005), np.log(1.0), g)
+    log_mu[0], log_mu[1] = np.log(0.002), np.log(3.0)
+    r = rng.uniform(0.5, 4.0, g)
+    beta_c = np.where(np.arange(g) % 3 == 0, rng.normal(0, 0.5, g), 0.0)
+    beta_b = rng.normal(0, 0.2, (8, g)); beta_b[0] = 0
+    mu = np.exp(log_mu[None] + cond[:, None] * beta_c[None] + beta_b[batch])
+    y = rng.poisson(rng.gamma(r[None], mu / r[None])).astype(np.float64)
+    est = _fit(de, scipy.sparse.csr_matrix(y.astype(np.float32)), xd, np.ones((n, 1)))
+    assert est._plan["kind"] == "grouped" and est._plan["k"] == 16
+    ref = onb.fit_nb(y, xd, np.ones((n, 1)), method_b="newton")
+    # the schedule's decisions are identical ...
+    np.testing.assert_array_equal(est.niter, ref["niter"])
+    np.testing.assert_array_equal(est.error_codes, ref["error_codes"])
+    np.testing.assert_allclose(est.log_likelihood, ref["log_likelihood"], rtol=1e-11)
+    # ... and so are the coefficients, except where the LAST accepted / reverted step improves the likelihood by less
+    # than its rounding noise (|ll| ~ 1e5, noise ~ 1e-8): batchglm's rule "revert the step if ll got worse" then flips
+    # between the two summation orders, and the coefficient moves by that last step, ~ sqrt(noise / information)
+    # ~ 1e-6 absolute, i.e. < 1e-4 standard errors.  Tolerance: 1e-5 relative + 2e-4 standard errors.
+    sd_all = np.sqrt(np.diagonal(ref["fisher_inv"], axis1=-2, axis2=-1).T)
+    tol = 1e-5 * np.abs(ref["a_var"]) + 2e-6 + 2e-4 * sd_all
+    assert np.all(np.abs(est.a_var - ref["a_var"]) <= tol), np.max(np.abs(est.a_var - ref["a_var"]) / sd_all)
+    exact = np.max(np.abs(est.a_var - ref["a_var"]), axis=0) < 1e-9
+    assert exact.sum() >= g // 2, "most genes must agree to rounding"
+    np.testing.assert_allclose(est.b_var, ref["b_var"], rtol=1e-4, atol=2e-5)
+    fi_ref = ref["fisher_inv"]
+    scale = np.abs(fi_ref).max(axis=(1, 2), keepdims=True)
+    assert np.all(np.abs(est.fisher_inv - fi_ref) <= 2e-5 * scale)
+    sd = np.sqrt(np.diagonal(est.fisher_inv, axis1=-2, axis2=-1).T[1])
+    ref_sd = np.sqrt(ref["fisher_inv"][:, 1, 1])
+    np.testing.assert_allclose(sd, ref_sd, rtol=1e-5)
+    p_ref = ost.wald_test(ref["a_var"][1], ref_sd)
+    from diffxpy_b200.stats import stats as dstats
+    p_gpu = dstats.wald_test(est.a_var[1], sd)
+    keep = p_ref > 1e-11            # the reference's 1 - cdf form carries >= 5 digits there (SURVEY 7.3-4)
+    np.testing.assert_allclose(np.log(p_gpu[keep]), np.log(p_ref[keep]), rtol=1e-4, atol=1e-4)
+
+
 def test_fit_high_counts_overflow_path(de):
     """Counts far above the 64 direct bins and non-integer values go through the overflow entries."""
     rng = np.random.default_rng(4)
