@@ -510,11 +510,17 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
         const unsigned total = __reduce_add_sync(DX_FULL_MASK, n_ovf);
         if (lane == 0) ovf_count[g] = (int32_t)total;
         if (total) {
-            unsigned inc = n_ovf;
+            // Canonical order of the overflow entries, independent of where the gene starts in the shard: by
+            // (i - start) mod 32, then ascending i.  Lane l counted the entries with (i - a0) mod 32 == l (a0 = start
+            // rounded down to 4), i.e. canonical class (l - d) mod 32 with d = start & 3: scan the counts in class order.
+            const int d = (int)(gd.start & 3ll);
+            const unsigned cnt_c = __shfl_sync(DX_FULL_MASK, n_ovf, (lane + d) & 31);     // count of canonical class `lane`
+            unsigned inc = cnt_c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(DX_FULL_MASK, inc, o); if (lane >= o) inc += t; }
-            // lane l re-visits exactly the entries it counted: i = a0 + l (mod 32), in ascending order
-            int64_t pos = gd.start + (inc - n_ovf);
+            const unsigned excl_c = inc - cnt_c;                                             // exclusive scan, class order
+            const unsigned base = __shfl_sync(DX_FULL_MASK, excl_c, (lane - d) & 31);       // this lane's class is (lane - d) mod 32
+            int64_t pos = gd.start + base;
             for (int64_t i = (gd.start & ~3ll) + lane; i < gd.end; i += 32) {
                 if (i < gd.start) continue;
                 const float vv = __ldg(vals + i);
