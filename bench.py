@@ -245,6 +245,8 @@ def main_cuda(args):
     n_k = np.bincount(inv, minlength=k).astype(np.float64)
     pinv = np.ascontiguousarray(np.linalg.pinv(xu_loc))
     cell_group = torch.from_numpy(inv.astype(np.uint8)).to(dev)
+    if n_k.max() <= 65535:          # what CountShard.group_suffstats checks: the on-chip histograms fit 16-bit bins
+        ingest_flags |= _lib.DX_GROUPS_FIT_U16
     d_xl, d_xs = torch.from_numpy(xu_loc).to(dev), torch.from_numpy(xu_scale).to(dev)
     d_nk, d_pinv = torch.from_numpy(n_k).to(dev), torch.from_numpy(pinv).to(dev)
     opts = _lib.DxFitOpts(max_steps=1000, update_b_freq=5, train_loc=1, train_scale=1,

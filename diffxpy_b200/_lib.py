@@ -16,6 +16,7 @@ DX_SKIP_GROUP = 255
 DX_MAX_COEF = 32
 
 DX_SHARD_INTEGER_COUNTS = 1
+DX_GROUPS_FIT_U16 = 2
 DX_OPT_SCALE_CONST = 1
 DX_INIT_GIVEN, DX_INIT_STANDARD, DX_INIT_CLOSED_FORM, DX_INIT_ALL_ZERO = 0, 1, 2, 3
 

@@ -62,7 +62,7 @@ int dx_group_suffstats_ex(int64_t n_genes, const int64_t* indptr, const int32_t*
     DX_CHECK(n_genes >= 0, "dx_group_suffstats_ex: n_genes < 0");
     DX_CHECK(n_groups >= 1 && n_groups <= DX_MAX_GROUPS, "dx_group_suffstats_ex: n_groups must be in 1..255");
     DX_CHECK(indptr && cell_group && hist && ovf_count, "dx_group_suffstats_ex: null pointer");
-    DX_CHECK((flags & ~DX_SHARD_INTEGER_COUNTS) == 0, "dx_group_suffstats_ex: unknown flag");
+    DX_CHECK((flags & ~(DX_SHARD_INTEGER_COUNTS | DX_GROUPS_FIT_U16)) == 0, "dx_group_suffstats_ex: unknown flag");
     DX_CUDA(dx_launch_ingest(n_genes, indptr, rows, vals, cell_group, n_groups, hist, ovf_count, ovf_val, ovf_group,
                              gene_order, flags, sm_count_cached(), (cudaStream_t)stream), "dx_group_suffstats_ex");
     return DX_OK;

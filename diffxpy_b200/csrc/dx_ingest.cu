@@ -15,6 +15,7 @@
 // > 64) is an "overflow" entry that is copied out in a deterministic order by a second, L2-resident pass.
 #include <atomic>
 #include <cstdlib>
+#include <type_traits>
 #include "dx_common.cuh"
 #include "dx_internal.h"
 
@@ -253,7 +254,10 @@ dx_ingest_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const int3
 #ifndef DX_TMA_TILE
 #define DX_TMA_TILE 256
 #endif
-constexpr int TW = 16;            // max warps per CTA
+#ifndef DX_TMA_TW
+#define DX_TMA_TW 20
+#endif
+constexpr int TW = DX_TMA_TW;     // max warps per CTA (sets the register budget: 65536 / (32 TW))
 constexpr int NS = DX_TMA_NS;     // ring stages per warp
 constexpr int TILE = DX_TMA_TILE; // elements per stage
 constexpr int TU = TILE / 32;     // elements per lane and tile
@@ -296,7 +300,9 @@ struct TileInfo {          // registers, per fetched tile
 // INT_ONLY: the caller guarantees that every stored value is a non-negative integer (< 2^24), which removes the
 // integrality test from the hot loop.  gene_order (nullable): the sequence in which the queue hands out genes
 // (largest first keeps the tail of the launch short).
-template <bool INT_ONLY>
+// H16: the caller guarantees that no design group has more than 65535 cells, so the per-warp histogram fits 16-bit
+// bins (half the shared memory -> more resident warps).
+template <bool INT_ONLY, bool H16>
 __global__ void __launch_bounds__(TW * 32, 1)
 dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const int32_t* __restrict__ rows,
                      const float* __restrict__ vals, const uint8_t* __restrict__ cell_group, int K, int ysh, int NW, int NWA,
@@ -308,8 +314,9 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
     unsigned char* base = smem_raw + (size_t)warp * warp_bytes;
     float* ring_v = reinterpret_cast<float*>(base);                               // [NS][TILE]
     int32_t* ring_r = reinterpret_cast<int32_t*>(base + NS * TILE * 4);           // [NS][TILE]
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(base + 2 * NS * TILE * 4);     // [K][64]
-    uint32_t* s_priv = s_hist + K * DX_HIST_BINS;                                 // [NWA][32]
+    using hist_t = typename std::conditional<H16, uint16_t, uint32_t>::type;
+    hist_t* s_hist = reinterpret_cast<hist_t*>(base + 2 * NS * TILE * 4);         // [K][64]
+    uint32_t* s_priv = reinterpret_cast<uint32_t*>(s_hist + K * DX_HIST_BINS);    // [NWA][32]
     GeneDesc* s_gene = reinterpret_cast<GeneDesc*>(s_priv + NWA * 32);            // [NG]
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_gene + NG);   // [NS]
     const unsigned YP = (ysh >= 0) ? (1u << ysh) : 0u;
@@ -328,7 +335,8 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     for (int i = lane; i < NWA * 32; i += 32) s_priv[i] = 0u;
-    for (int i = lane; i < K * DX_HIST_BINS; i += 32) s_hist[i] = 0u;
+    for (int i = lane; i < K * DX_HIST_BINS; i += 32) s_hist[i] = 0;
+    const uint32_t hist_addr = dx_smem_u32(s_hist);
     __syncwarp();
 
     // ---- issue side (warp-uniform state; lane 0 performs the side effects) ----------------------------------
@@ -447,7 +455,7 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 const unsigned idx = 4u * lane + b;
-                if (cnt[b] && idx < n_priv) s_hist[(idx >> ysh_u) * DX_HIST_BINS + (idx & (YP - 1u))] += cnt[b];
+                if (cnt[b] && idx < n_priv) s_hist[(idx >> ysh_u) * DX_HIST_BINS + (idx & (YP - 1u))] += (hist_t)cnt[b];
             }
         }
         __syncwarp();
@@ -479,7 +487,11 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
                     const unsigned ym1 = (unsigned)(y - 1);
                     const bool isbin = (ym1 < (unsigned)DX_HIST_BINS) && (__int2float_rn(y) == v[u]) && (k[u] < (unsigned)K);
                     if (isbin) {
-                        if (ym1 >= YP) atomicAdd(&s_hist[k[u] * DX_HIST_BINS + ym1], 1u);
+                        if (ym1 >= YP) {
+                            const unsigned b = k[u] * DX_HIST_BINS + ym1;
+                            if (H16) dx_red_shared(hist_addr + ((b >> 1) << 2), 1u << ((b & 1u) << 4));   // 16-bit bin inside its word
+                            else dx_red_shared(hist_addr + (b << 2), 1u);
+                        }
                     } else if (v[u] != 0.0f && k[u] < (unsigned)K) {
                         ++n_ovf;
                     }
@@ -495,8 +507,8 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
 #pragma unroll 1
         for (int kk = 0; kk < K; ++kk) {
             const unsigned lo = s_hist[kk * DX_HIST_BINS + lane], hi = s_hist[kk * DX_HIST_BINS + 32 + lane];
-            s_hist[kk * DX_HIST_BINS + lane] = 0u;
-            s_hist[kk * DX_HIST_BINS + 32 + lane] = 0u;
+            s_hist[kk * DX_HIST_BINS + lane] = 0;
+            s_hist[kk * DX_HIST_BINS + 32 + lane] = 0;
             unsigned plo = lo, phi = hi;   // inclusive prefix sums
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -609,9 +621,10 @@ cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32
     static const char* impl_env = getenv("DXB200_INGEST_IMPL");          // tuning hooks (development only)
     static const char* warps_env = getenv("DXB200_INGEST_WARPS");
     const bool aligned = ((reinterpret_cast<uintptr_t>(vals) | reinterpret_cast<uintptr_t>(rows)) & 15u) == 0;
-    int warp_bytes = 2 * NS * TILE * 4 + K * DX_HIST_BINS * 4 + NWA * 32 * 4 + NG * (int)sizeof(GeneDesc) + NS * 8;
+    const bool h16 = (flags & DX_GROUPS_FIT_U16) != 0;
+    int warp_bytes = 2 * NS * TILE * 4 + K * DX_HIST_BINS * (h16 ? 2 : 4) + NWA * 32 * 4 + NG * (int)sizeof(GeneDesc) + NS * 8;
     warp_bytes = (warp_bytes + 15) & ~15;
-    int warps = (220 * 1024) / warp_bytes;
+    int warps = (227 * 1024) / warp_bytes;
     if (warps > TW) warps = TW;
     if (warps_env && atoi(warps_env) > 0 && atoi(warps_env) < warps) warps = atoi(warps_env);
     const bool want_tma = !(impl_env && impl_env[0] == 'c');
@@ -620,7 +633,9 @@ cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32
         e = dx_queue_acquire(stream, &queue);
         if (e != cudaSuccess) return e;
         const size_t smem = (size_t)warps * warp_bytes;
-        auto kern = (flags & DX_SHARD_INTEGER_COUNTS) ? dx_ingest_tma_kernel<true> : dx_ingest_tma_kernel<false>;
+        const bool io = (flags & DX_SHARD_INTEGER_COUNTS) != 0;
+        auto kern = io ? (h16 ? dx_ingest_tma_kernel<true, true> : dx_ingest_tma_kernel<true, false>)
+                       : (h16 ? dx_ingest_tma_kernel<false, true> : dx_ingest_tma_kernel<false, false>);
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int64_t grid = sm_count;                    // persistent CTAs; the warps pull genes from the queue

@@ -174,6 +174,8 @@ class CountShard:
         ovf_val = torch.empty(max(self.vals.shape[0], 1), dtype=torch.float32, device=dev)
         ovf_group = torch.empty(max(self.vals.shape[0], 1), dtype=torch.uint8, device=dev)
         flags = _lib.DX_SHARD_INTEGER_COUNTS if self.integer_counts else 0
+        if int(torch.bincount(cell_group.to(torch.int64), minlength=256)[:255].max().item()) <= 65535:
+            flags |= _lib.DX_GROUPS_FIT_U16
         _lib.call("dx_group_suffstats_ex", g, ptr(self.indptr), ptr(self.rows), ptr(self.vals), ptr(cell_group),
                   int(n_groups), ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), ptr(self.gene_order), flags,
                   stream_ptr())

@@ -96,8 +96,11 @@ int dx_group_suffstats(int64_t n_genes, const int64_t* indptr, const int32_t* ro
  *   gene_order[n_genes] (nullable): permutation of 0..n_genes-1, the order in which genes are handed to the SMs
  *                       (largest first shortens the tail of the launch); results do not depend on it
  *   flags: DX_SHARD_INTEGER_COUNTS = every stored value is a non-negative integer below 2^24 (verified by the
- *          caller); the kernel then skips the per-entry integrality test */
+ *          caller); the kernel then skips the per-entry integrality test
+ *          DX_GROUPS_FIT_U16 = every group of cell_group has at most 65535 cells; the on-chip histograms then use
+ *          16-bit bins, which lets more warps stay resident */
 #define DX_SHARD_INTEGER_COUNTS 1
+#define DX_GROUPS_FIT_U16 2      /* no design group has more than 65535 cells (verified by the caller): 16-bit on-chip bins */
 int dx_group_suffstats_ex(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,
                           const uint8_t* cell_group, int32_t n_groups,
                           uint32_t* hist, int32_t* ovf_count, float* ovf_val, uint8_t* ovf_group,

@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--cells", type=int, default=100000)
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--what", default="ingest,fit")
+    ap.add_argument("--flags", type=int, default=3, help="dx_group_suffstats_ex flags (1 integer counts, 2 groups fit u16)")
     ap.add_argument("--plain", action="store_true", help="use dx_group_suffstats (no gene order / integer flag)")
     ap.add_argument("--scale-batch", action="store_true", help="scale model '~1+batch' (8 dispersion coefficients, configs[2])")
     ap.add_argument("names", nargs="+")
@@ -93,7 +94,7 @@ def main():
                      ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), stream_ptr())
             else:
                 call(lib, "dx_group_suffstats_ex", g, ptr(shard.indptr), ptr(shard.rows), ptr(shard.vals), ptr(cell_group), k,
-                     ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), ptr(order), 1 if is_int else 0, stream_ptr())
+                     ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), ptr(order), (a.flags if is_int else a.flags & 2), stream_ptr())
 
         def fit():
             call(lib, "dx_nb_fit_grouped", g, k, p, ps, ptr(d_xl), ptr(d_xs), None, ptr(d_nk), ptr(d_pinv), None, k,
