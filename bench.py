@@ -185,6 +185,7 @@ def make_shard(torch, dev, seed, n_genes=N_GENES, n_cells=N_CELLS, chunk=400):
     log_mu, r, beta_c, beta_b = gene_params(rng, n_genes)
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed)
+    torch.cuda.manual_seed(seed)        # torch._standard_gamma draws from the default CUDA generator
     cond_t = torch.from_numpy(cond.astype(np.float32)).to(dev)
     batch_t = torch.from_numpy(batch).to(dev)
     rows_l, vals_l, counts_l = [], [], []
@@ -405,7 +406,7 @@ def main_cuda(args):
             "config": {"workload": WORKLOAD, "n_cells": n_cells, "genes_per_gpu": g, "nnz_per_gpu": nnz,
                        "density": nnz / (n_cells * g), "design_groups": k, "p_loc": p, "p_scale": ps,
                        "l2": "inputs (%.2f GB per pass) larger than L2; no explicit flush" % (8 * nnz / 1e9),
-                       "frac_converged": conv, "mean_niter": mean_iter,
+                       "frac_converged": conv, "mean_niter": mean_iter, "max_niter": int(niter.max().item()),
                        "equivalent_iter_stream_gbs": equiv_gbs},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "genes/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

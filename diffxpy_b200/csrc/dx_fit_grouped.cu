@@ -29,7 +29,6 @@ namespace {
 
 extern __shared__ __align__(16) double smem_d[];
 
-constexpr int PTAB_MAX_DOUBLES = 3072;     // product table budget per CTA (24 KB)
 
 // helpers on the IWLS path are inlined (their Slot fields then live in registers); the rarely executed scale-model
 // helpers stay out of line to keep the hot loop inside the instruction cache
@@ -70,9 +69,11 @@ struct Slot {
     unsigned mask;
     int sl;                                  // lane inside the sub-warp
     int K, p, ps, ymax, novf, nent;
-    bool shared_r, has_ptab;
+    bool shared_r, has_nz;
     // CTA-wide tables
-    int t_xl, t_xs, t_off, t_nk, t_ptab;     // [K][p], [K][ps], [K], [K], [K][nent]
+    int t_xl, t_xs, t_off, t_nk, t_nzv;      // [K][p], [K][ps], [K], [K], non-zero design products [nz]
+    const unsigned short* nz_ptr;            // [nent + 1] entry -> range of its non-zero products (shared memory)
+    const unsigned char* nz_k;               // [nz] design group of every non-zero product
     const unsigned char *ei, *ej;            // entry -> (row, column) of the lower triangle (shared memory)
     // per-slot state: a-dependent, b-dependent, (a, b)-dependent; current and trial copies
     int eta, mu, eta_t, mu_t;
@@ -204,10 +205,12 @@ template <int SW> __device__ DX_HOT double loc_terms(const Slot& s) {
     for (int e = s.sl; e < nent; e += SW) {
         const int i = s.ei[e], j = s.ej[e];
         double acc = 0.0;
-        if (s.has_ptab) {
-            const double* P = smem_d + s.t_ptab + e;
-#pragma unroll 4
-            for (int k = 0; k < K; ++k) acc += w1[k] * P[k * nent];
+        if (s.has_nz) {
+            // categorical designs: most products x_ki x_kj vanish; the CTA-wide list holds the others (same k order,
+            // so the sum is bit-identical to the dense loop)
+            const double* nzv = smem_d + s.t_nzv;
+#pragma unroll 1
+            for (int t = s.nz_ptr[e], t1 = s.nz_ptr[e + 1]; t < t1; ++t) acc += w1[s.nz_k[t]] * nzv[t];
         } else {
 #pragma unroll 4
             for (int k = 0; k < K; ++k) acc += w1[k] * (xl[k * p + i] * xl[k * p + j]);
@@ -475,7 +478,7 @@ struct FitArgs {
     dx_fit_opts opts;
     double *a_var, *b_var, *fim_inv, *ll_out, *jac_out;
     int32_t *niter_out, *flags_out;
-    int slot_doubles, table_doubles, nent, has_ptab, ainv_extra;
+    int slot_doubles, table_doubles, nent, nz_max, ainv_extra;
 };
 
 template <int SW>
@@ -487,10 +490,13 @@ dx_fit_grouped_kernel(const FitArgs P) {
     const int slots_per_cta = (blockDim.x >> 5) * SLOTS_PER_WARP;
 
     // ---- CTA tables: design rows, offsets, group sizes, product table, entry decode --------------------------
-    const int t_xl = 0, t_xs = t_xl + K * p, t_off = t_xs + K * ps, t_nk = t_off + K, t_ptab = t_nk + K;
-    const int t_dec = t_ptab + (P.has_ptab ? K * nent : 0);          // entry decode bytes live here
+    const int t_xl = 0, t_xs = t_xl + K * p, t_off = t_xs + K * ps, t_nk = t_off + K, t_nzv = t_nk + K;
+    const int t_dec = t_nzv + P.nz_max;                              // byte tables live here
     unsigned char* dec_i = reinterpret_cast<unsigned char*>(smem_d + t_dec);
     unsigned char* dec_j = dec_i + ((nent + 7) & ~7);
+    unsigned short* nz_ptr = reinterpret_cast<unsigned short*>(dec_j + ((nent + 7) & ~7));
+    unsigned char* nz_k = reinterpret_cast<unsigned char*>(nz_ptr + ((nent + 1 + 3) & ~3));
+    __shared__ int s_nz_total;
     for (int i = tid; i < K * p; i += blockDim.x) smem_d[t_xl + i] = P.xu_loc[i];
     for (int i = tid; i < K * ps; i += blockDim.x) smem_d[t_xs + i] = P.xu_scale[i];
     for (int i = tid; i < K; i += blockDim.x) {
@@ -505,10 +511,28 @@ dx_fit_grouped_kernel(const FitArgs P) {
         dec_j[e] = (unsigned char)(e - i * (i + 1) / 2);
     }
     __syncthreads();
-    if (P.has_ptab) {
-        for (int t = tid; t < K * nent; t += blockDim.x) {
-            const int k = t / nent, e = t - k * nent;
-            smem_d[t_ptab + t] = smem_d[t_xl + k * p + dec_i[e]] * smem_d[t_xl + k * p + dec_j[e]];
+    // sparse table of the non-zero design products x_ki x_kj (count, exclusive scan, fill); too many -> dense loop
+    for (int e = tid; e < nent; e += blockDim.x) {
+        int c = 0;
+        for (int k = 0; k < K; ++k) c += (smem_d[t_xl + k * p + dec_i[e]] * smem_d[t_xl + k * p + dec_j[e]] != 0.0) ? 1 : 0;
+        nz_ptr[e] = (unsigned short)c;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int e = 0; e < nent; ++e) { const int c = nz_ptr[e]; nz_ptr[e] = (unsigned short)run; run += c; }
+        nz_ptr[nent] = (unsigned short)run;
+        s_nz_total = run;
+    }
+    __syncthreads();
+    const bool has_nz = s_nz_total <= P.nz_max;
+    if (has_nz) {
+        for (int e = tid; e < nent; e += blockDim.x) {
+            int t = nz_ptr[e];
+            for (int k = 0; k < K; ++k) {
+                const double v = smem_d[t_xl + k * p + dec_i[e]] * smem_d[t_xl + k * p + dec_j[e]];
+                if (v != 0.0) { nz_k[t] = (unsigned char)k; smem_d[t_nzv + t] = v; ++t; }
+            }
         }
     }
     __syncthreads();
@@ -521,8 +545,9 @@ dx_fit_grouped_kernel(const FitArgs P) {
     s.sl = lane % SW;
     s.mask = (SW == 32) ? 0xffffffffu : (((1u << SW) - 1u) << ((lane / SW) * SW));
     s.K = K; s.p = p; s.ps = ps; s.nent = nent;
-    s.has_ptab = P.has_ptab != 0;
-    s.t_xl = t_xl; s.t_xs = t_xs; s.t_off = t_off; s.t_nk = t_nk; s.t_ptab = t_ptab;
+    s.has_nz = has_nz;
+    s.nz_ptr = nz_ptr; s.nz_k = nz_k;
+    s.t_xl = t_xl; s.t_xs = t_xs; s.t_off = t_off; s.t_nk = t_nk; s.t_nzv = t_nzv;
     s.ei = dec_i; s.ej = dec_j;
     {
         int o = P.table_doubles + slot * P.slot_doubles;
@@ -743,6 +768,7 @@ dx_fit_grouped_kernel(const FitArgs P) {
     double dinv_f;
     const bool okf = ldl_factor<SW>(smem_d + s.A, p, sl, mask, dinv_f);
     double* Ainv = smem_d + s.Ainv;                         // aliases w1 | w2 | Cj: none of them is needed any more
+#ifdef DX_FIT_OLDINV
     if (okf) {
 #pragma unroll 1
         for (int c = 0; c < p; ++c) {
@@ -750,6 +776,31 @@ dx_fit_grouped_kernel(const FitArgs P) {
             if (sl < p) Ainv[c * p + sl] = x;
         }
     }
+#else
+    {   // inverse: lane c solves (L D L^T) x = e_c serially into its own column (all columns in parallel)
+        double* dv = smem_d + s.vec;
+        if (sl < p) dv[sl] = dinv_f;
+        __syncwarp(mask);
+        if (okf && sl < p) {
+            const double* L = smem_d + s.A;                 // L_ik (i > k) at L[k * p + i]
+            double* x = Ainv + sl * p;
+#pragma unroll 1
+            for (int i = 0; i < p; ++i) {
+                double acc = (i == sl) ? 1.0 : 0.0;
+#pragma unroll 1
+                for (int k = 0; k < i; ++k) acc -= L[k * p + i] * x[k];
+                x[i] = acc;
+            }
+#pragma unroll 1
+            for (int i = p - 1; i >= 0; --i) {
+                double acc = x[i] * dv[i];
+#pragma unroll 1
+                for (int k = i + 1; k < p; ++k) acc -= L[i * p + k] * x[k];
+                x[i] = acc;
+            }
+        }
+    }
+#endif
     __syncwarp(mask);
     double* fo = P.fim_inv + g * (int64_t)p * p;
 #pragma unroll 1
@@ -772,13 +823,13 @@ cudaError_t launch_sw(FitArgs& A, int sm_count, cudaStream_t stream) {
     const int slots_per_warp = 32 / SW;
     const size_t table_bytes = (size_t)A.table_doubles * 8, slot_bytes = (size_t)A.slot_doubles * 8;
     // warps per CTA: maximise the number of resident gene slots per SM under the shared-memory budget
-    const size_t budget = 220 * 1024;
+    const size_t budget = 228 * 1024;      // per SM; every resident CTA also pays 1 KB of system-reserved shared memory
     int best_w = 1;
     long best_res = -1;
     const int cand[] = {1, 2, 3, 4, 6, 8};
     for (int w : cand) {
-        const size_t need = table_bytes + (size_t)w * slots_per_warp * slot_bytes;
-        if (need > budget) continue;
+        const size_t need = table_bytes + (size_t)w * slots_per_warp * slot_bytes + 1024 + 64;
+        if (need > 227 * 1024) continue;
         long ctas = (long)(budget / need);
         if (ctas > 32) ctas = 32;
         long warps = ctas * w;
@@ -818,11 +869,9 @@ cudaError_t dx_launch_fit_grouped(int64_t n_genes, int K, int p, int ps,
     A.opts = *opts;
     A.a_var = a_var; A.b_var = b_var; A.fim_inv = fim_inv; A.ll_out = ll; A.jac_out = jac; A.niter_out = niter; A.flags_out = flags;
     A.nent = p * (p + 1) / 2;
-    static const char* ptab_env = getenv("DXB200_FIT_PTAB");     // tuning hook (development only)
-    // measured on B200 (cfg2): the staged product table saves ~10% instructions in X^T W X but its shared memory costs
-    // resident gene slots; without it the kernel is as fast or faster, so it is opt-in
-    A.has_ptab = (A.nent * K <= PTAB_MAX_DOUBLES && ptab_env && ptab_env[0] == '1') ? 1 : 0;
-    A.table_doubles = K * p + K * ps + 2 * K + (A.has_ptab ? K * A.nent : 0) + 2 * ((A.nent + 7) / 8) + 2;
+    static const char* nz_env = getenv("DXB200_FIT_NZ");         // tuning hook (development only)
+    A.nz_max = nz_env ? atoi(nz_env) : 96;   // capacity of the non-zero design-product list (0.9 KB); denser designs use the dense loop
+    A.table_doubles = K * p + K * ps + 2 * K + A.nz_max + (2 * ((A.nent + 7) & ~7) + 2 * ((A.nent + 1 + 3) & ~3) + A.nz_max + 7) / 8 + 2;
     A.ainv_extra = (p * p > 2 * K + DX_HIST_BINS) ? p * p - (2 * K + DX_HIST_BINS) : 0;
     A.slot_doubles = 13 * K + 2 * K + DX_HIST_BINS + A.ainv_extra + p * p + (p > ps ? p : ps) + 2 * ps * ps;
     A.slot_doubles = (A.slot_doubles + 1) & ~1;
