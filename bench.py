@@ -185,7 +185,8 @@ def make_shard(torch, dev, seed, n_genes=N_GENES, n_cells=N_CELLS, chunk=400):
     log_mu, r, beta_c, beta_b = gene_params(rng, n_genes)
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed)
-    torch.cuda.manual_seed(seed)        # torch._standard_gamma draws from the default CUDA generator
+    torch.cuda.manual_seed(7919 * seed + 17)   # torch._standard_gamma draws from the default CUDA generator; a
+    # different Philox key than `gen`, or the gamma and Poisson draws would be correlated
     cond_t = torch.from_numpy(cond.astype(np.float32)).to(dev)
     batch_t = torch.from_numpy(batch).to(dev)
     rows_l, vals_l, counts_l = [], [], []
