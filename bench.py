@@ -43,9 +43,12 @@ def design_for(cond, batch):
                            (batch[:, None] == np.arange(1, N_BATCH)[None, :]).astype(np.float64)], axis=1)
 
 
+MU_HI = 1.0       # upper end of the log-uniform gene means (tools/kbench.py raises it to probe heavy-tailed shards)
+
+
 def gene_params(rng, g):
     """SURVEY.md section 8(d) synthetic distribution of configs[1]."""
-    log_mu = rng.uniform(np.log(0.005), np.log(1.0), g)
+    log_mu = rng.uniform(np.log(0.005), np.log(MU_HI), g)
     r = rng.uniform(0.5, 4.0, g)
     beta_c = np.where(rng.uniform(size=g) < 0.1, rng.normal(0, 0.5, g), 0.0)
     beta_b = rng.normal(0, 0.2, (N_BATCH, g))

@@ -391,7 +391,8 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
     int r0[TU], r1[TU];
     unsigned k0[TU], k1[TU];
     TileInfo m0, m1;
-    unsigned n_ovf = 0;
+    unsigned n_ovf = 0;               // overflow entries this lane saw in the current tile
+    unsigned ovf_base = 0;            // overflow entries of the current gene written so far (warp-uniform)
     int since_flush = 0;
     int c_tiles = 0;                  // tiles of the current consume gene not yet fetched
     int c_lo = 0, c_hi = 0;           // valid element range of the next tile, relative to the tile start
@@ -498,8 +499,27 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
                 }
             }
         }
+        if (__any_sync(DX_FULL_MASK, n_ovf != 0u)) {
+            // Overflow entries of this tile, appended in ascending shard position (element lane + 32 u of the tile):
+            // an order that does not depend on where the gene starts, so a sharded run writes the same list.
+            const int64_t obase = s_gene[m.slot].start;
+#pragma unroll
+            for (int u = 0; u < TU; ++u) {
+                const int y = __float2int_rz(v[u]);
+                const bool isbin = ((unsigned)(y - 1) < (unsigned)DX_HIST_BINS) && (__int2float_rn(y) == v[u]);
+                const bool ovf = !isbin && v[u] != 0.0f && k[u] < (unsigned)K;
+                const unsigned bal = __ballot_sync(DX_FULL_MASK, ovf);
+                if (ovf) {
+                    const int64_t pos = obase + ovf_base + __popc(bal & ((1u << lane) - 1u));
+                    ovf_val[pos] = v[u];
+                    ovf_group[pos] = (uint8_t)k[u];
+                }
+                ovf_base += __popc(bal);
+            }
+            n_ovf = 0;
+        }
         if (!m.last) return;
-        // ---- the gene is complete: tail counts, overflow entries, reset ----------------------------------------
+        // ---- the gene is complete: tail counts, overflow count, reset ----------------------------------------
         flush();
         const GeneDesc gd = s_gene[m.slot];      // still valid: at most NS + 1 < NG genes are in flight
         const int64_t g = gd.gene;
@@ -519,33 +539,8 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
             out[kk * DX_HIST_BINS + 32 + lane] = tot_hi - phi + hi;
             out[kk * DX_HIST_BINS + lane] = tot_hi + (tot_lo - plo + lo);
         }
-        const unsigned total = __reduce_add_sync(DX_FULL_MASK, n_ovf);
-        if (lane == 0) ovf_count[g] = (int32_t)total;
-        if (total) {
-            // Canonical order of the overflow entries, independent of where the gene starts in the shard: by
-            // (i - start) mod 32, then ascending i.  Lane l counted the entries with (i - a0) mod 32 == l (a0 = start
-            // rounded down to 4), i.e. canonical class (l - d) mod 32 with d = start & 3: scan the counts in class order.
-            const int d = (int)(gd.start & 3ll);
-            const unsigned cnt_c = __shfl_sync(DX_FULL_MASK, n_ovf, (lane + d) & 31);     // count of canonical class `lane`
-            unsigned inc = cnt_c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(DX_FULL_MASK, inc, o); if (lane >= o) inc += t; }
-            const unsigned excl_c = inc - cnt_c;                                             // exclusive scan, class order
-            const unsigned base = __shfl_sync(DX_FULL_MASK, excl_c, (lane - d) & 31);       // this lane's class is (lane - d) mod 32
-            int64_t pos = gd.start + base;
-            for (int64_t i = (gd.start & ~3ll) + lane; i < gd.end; i += 32) {
-                if (i < gd.start) continue;
-                const float vv = __ldg(vals + i);
-                const int kk = __ldg(cell_group + __ldg(rows + i));
-                int y;
-                if (!dx_classify(vv, kk, K, y) && vv != 0.0f && kk < K) {
-                    ovf_val[pos] = vv;
-                    ovf_group[pos] = (uint8_t)kk;
-                    ++pos;
-                }
-            }
-        }
-        n_ovf = 0;
+        if (lane == 0) ovf_count[g] = (int32_t)ovf_base;
+        ovf_base = 0;
         __syncwarp();
     };
 

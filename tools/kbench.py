@@ -50,10 +50,12 @@ def main():
     ap.add_argument("--flags", type=int, default=3, help="dx_group_suffstats_ex flags (1 integer counts, 2 groups fit u16)")
     ap.add_argument("--plain", action="store_true", help="use dx_group_suffstats (no gene order / integer flag)")
     ap.add_argument("--scale-batch", action="store_true", help="scale model '~1+batch' (8 dispersion coefficients, configs[2])")
+    ap.add_argument("--mu-hi", type=float, default=1.0, help="upper end of the log-uniform gene means (default: the bench workload)")
     ap.add_argument("names", nargs="+")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
+    bench.MU_HI = a.mu_hi
     shard, cond, batch = bench.make_shard(torch, dev, seed=1000, n_genes=a.genes, n_cells=a.cells)
     nnz = shard.nnz
     g = a.genes
