@@ -263,6 +263,7 @@ def main_cuda(args):
     ovf_count = torch.empty(g, dtype=torch.int32, device=dev)
     ovf_val = torch.empty(nnz, dtype=torch.float32, device=dev)
     ovf_group = torch.empty(nnz, dtype=torch.uint8, device=dev)
+    ovf_packed = torch.empty((g, 2), dtype=torch.int32, device=dev)
     a_var, b_var = torch.empty((p, g), **f64), torch.empty((ps, g), **f64)
     fim_inv, ll, jac = torch.empty((g, p, p), **f64), torch.empty(g, **f64), torch.empty(g, **f64)
     niter, flags = torch.empty(g, dtype=torch.int32, device=dev), torch.empty(g, dtype=torch.int32, device=dev)
@@ -272,16 +273,21 @@ def main_cuda(args):
     kern_events = []
 
     def step(record=False):
-        e = [ev() for _ in range(4)] if record else None
+        e = [ev() for _ in range(5)] if record else None
         if record:
             e[0].record()
         _lib.call("dx_group_suffstats_ex", g, ptr(shard.indptr), ptr(shard.rows), ptr(shard.vals), ptr(cell_group), k,
                   ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), ptr(gene_order), ingest_flags, stream_ptr())
         if record:
             e[1].record()
-        _lib.call("dx_nb_fit_grouped", g, k, p, ps, ptr(d_xl), ptr(d_xs), None, ptr(d_nk), ptr(d_pinv), None, k,
-                  ptr(tail), ptr(ovf_count), ptr(shard.indptr), ptr(ovf_val), ptr(ovf_group), opts, ptr(a_var),
-                  ptr(b_var), ptr(fim_inv), ptr(ll), ptr(jac), ptr(niter), ptr(flags), stream_ptr())
+        # what SuffStats.pack_overflow() does in the estimator: nothing to pack on this workload (gene means <= 1)
+        _lib.call("dx_pack_overflow", g, k, 0, ptr(ovf_count), ptr(shard.indptr), ptr(ovf_val), ptr(ovf_group),
+                  ptr(ovf_packed), stream_ptr())
+        if record:
+            e[4].record()
+        _lib.call("dx_nb_fit_grouped_packed", g, k, p, ps, ptr(d_xl), ptr(d_xs), None, ptr(d_nk), ptr(d_pinv), None, k,
+                  ptr(tail), ptr(ovf_count), ptr(shard.indptr), ptr(ovf_val), ptr(ovf_group), ptr(ovf_packed), opts,
+                  ptr(a_var), ptr(b_var), ptr(fim_inv), ptr(ll), ptr(jac), ptr(niter), ptr(flags), stream_ptr())
         if record:
             e[2].record()
         _lib.call("dx_wald_from_fit", g, p, 1, ptr(a_var), ptr(fim_inv), ptr(rows_out[0]), ptr(rows_out[1]),
@@ -319,7 +325,8 @@ def main_cuda(args):
         td.all_reduce(t, op=td.ReduceOp.MAX)
     elapsed_ms = float(t.item())
     ingest_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in kern_events]))
-    fit_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in kern_events]))
+    pack_ms = float(np.mean([e[1].elapsed_time(e[4]) for e in kern_events]))
+    fit_ms = float(np.mean([e[4].elapsed_time(e[2]) for e in kern_events]))
     wald_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in kern_events]))
     value = world * g * args.steps / (elapsed_ms * 1e-3)
 
@@ -367,6 +374,7 @@ def main_cuda(args):
     ingest_bytes = 8 * nnz + 8 * (g + 1) + n_cells + 4 * g * k * _lib.DX_HIST_BINS + 4 * g
     fit_bytes = 4 * g * k * _lib.DX_HIST_BINS + 8 * g * (p + ps + p * p + 2) + 8 * g + 8 * (g + 1)
     kern = {"dx_ingest_tma_kernel": {"ms": ingest_ms, "algorithmic_bytes": ingest_bytes},
+            "dx_pack_overflow_kernel": {"ms": pack_ms},
             "dx_fit_grouped_kernel": {"ms": fit_ms, "algorithmic_bytes": fit_bytes},
             "dx_wald_from_fit_kernel": {"ms": wald_ms}}
     # the roofline object describes the kernel of the step that streams HBM (K_ingest reads the whole shard once);
@@ -398,9 +406,9 @@ def main_cuda(args):
                          "one process per core)" % (gps, N_CELLS)}
 
     from diffxpy_b200.testing import correction as _corr
-    # own kernels per step: ingest, fit, wald + BH (all-pairs path: rank, scatter, chunk-min, suffix, gather; sort path
+    # own kernels per step: ingest, pack, fit, wald + BH (all-pairs path: rank, scatter, chunk-min, suffix, gather; sort path
     # for the gathered vector of several GPUs: chunk-min, suffix after torch.sort)
-    launches_per_step = 3 + (5 if world * g <= _corr.BH_KERNEL_MAX else 2)
+    launches_per_step = 4 + (5 if world * g <= _corr.BH_KERNEL_MAX else 2)
     if rank == 0:
         conv = float((flags & 1).to(torch.float64).mean().item())
         line = {

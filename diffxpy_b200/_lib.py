@@ -49,6 +49,9 @@ SIGNATURES = {
     "dx_gene_moments": [_I64, _P, _P, _P, _P, _P, _P, _P],
     "dx_nb_fit_grouped": [_I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, C.POINTER(DxFitOpts),
                           _P, _P, _P, _P, _P, _P, _P, _P],
+    "dx_pack_overflow": [_I64, _I32, _I32, _P, _P, _P, _P, _P, _P],
+    "dx_nb_fit_grouped_packed": [_I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P,
+                                 C.POINTER(DxFitOpts), _P, _P, _P, _P, _P, _P, _P, _P],
     "dx_nb_fit_percell": [_I64, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, C.POINTER(DxFitOpts),
                           _P, _P, _P, _P, _P, _P, _P, _P],
     "dx_wald_test": [_I64, _P, _P, _P, _P, _P],

@@ -94,7 +94,42 @@ int dx_nb_fit_grouped(int64_t n_genes, int32_t n_groups, int32_t p_loc, int32_t 
     DX_CHECK(opts->init_b != DX_INIT_CLOSED_FORM, "dx_nb_fit_grouped: closed-form init_b must be resolved by the host");
     DX_CUDA(dx_launch_fit_grouped(n_genes, n_groups, p_loc, p_scale, xu_loc, xu_scale, offset, n_k, pinv_loc, loc_group,
                                   n_loc_groups, hist, ovf_count, indptr, ovf_val, ovf_group, opts, a_var, b_var, fim_inv, ll, jac, niter,
-                                  flags, 0, (cudaStream_t)stream), "dx_nb_fit_grouped");
+                                  flags, 0, nullptr, (cudaStream_t)stream), "dx_nb_fit_grouped");
+    return DX_OK;
+}
+
+int dx_pack_overflow(int64_t n_genes, int32_t n_groups, int32_t min_entries, const int32_t* ovf_count,
+                     const int64_t* indptr, float* ovf_val, uint8_t* ovf_group, int32_t* ovf_packed, void* stream) {
+    DX_CHECK(n_genes >= 0, "dx_pack_overflow: n_genes < 0");
+    DX_CHECK(n_groups >= 1 && n_groups <= DX_MAX_GROUPS, "dx_pack_overflow: n_groups must be in 1..255");
+    DX_CHECK(ovf_count && indptr && ovf_val && ovf_group && ovf_packed, "dx_pack_overflow: null pointer");
+    DX_CUDA(dx_launch_pack_overflow(n_genes, n_groups, min_entries > 0 ? min_entries : DX_PACK_MIN_ENTRIES, ovf_count, indptr,
+                                    ovf_val, ovf_group, ovf_packed, sm_count_cached(), (cudaStream_t)stream),
+            "dx_pack_overflow");
+    return DX_OK;
+}
+
+int dx_nb_fit_grouped_packed(int64_t n_genes, int32_t n_groups, int32_t p_loc, int32_t p_scale,
+                             const double* xu_loc, const double* xu_scale, const double* offset, const double* n_k,
+                             const double* pinv_loc, const int32_t* loc_group, int32_t n_loc_groups,
+                             const uint32_t* hist, const int32_t* ovf_count, const int64_t* indptr,
+                             const float* ovf_val, const uint8_t* ovf_group, const int32_t* ovf_packed,
+                             const dx_fit_opts* opts,
+                             double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
+                             int32_t* niter, int32_t* flags, void* stream) {
+    DX_CHECK(n_genes >= 0, "dx_nb_fit_grouped_packed: n_genes < 0");
+    DX_CHECK(n_groups >= 1 && n_groups <= DX_MAX_GROUPS, "dx_nb_fit_grouped_packed: n_groups must be in 1..255");
+    DX_CHECK(p_loc >= 1 && p_loc <= DX_MAX_COEF && p_scale >= 1 && p_scale <= DX_MAX_COEF,
+             "dx_nb_fit_grouped_packed: coefficient counts must be in 1..32");
+    DX_CHECK(!bad_opts(opts), "dx_nb_fit_grouped_packed: bad options");
+    DX_CHECK(xu_loc && xu_scale && n_k && hist && ovf_count && indptr, "dx_nb_fit_grouped_packed: null input pointer");
+    DX_CHECK(a_var && b_var && fim_inv && ll && jac && niter && flags, "dx_nb_fit_grouped_packed: null output pointer");
+    DX_CHECK(opts->init_a != DX_INIT_CLOSED_FORM || (pinv_loc && n_loc_groups >= 1 && n_loc_groups <= n_groups),
+             "dx_nb_fit_grouped_packed: closed-form init needs pinv_loc and 1 <= n_loc_groups <= n_groups");
+    DX_CHECK(opts->init_b != DX_INIT_CLOSED_FORM, "dx_nb_fit_grouped_packed: closed-form init_b must be resolved by the host");
+    DX_CUDA(dx_launch_fit_grouped(n_genes, n_groups, p_loc, p_scale, xu_loc, xu_scale, offset, n_k, pinv_loc, loc_group,
+                                  n_loc_groups, hist, ovf_count, indptr, ovf_val, ovf_group, opts, a_var, b_var, fim_inv, ll, jac, niter,
+                                  flags, 0, ovf_packed, (cudaStream_t)stream), "dx_nb_fit_grouped_packed");
     return DX_OK;
 }
 
@@ -291,7 +326,7 @@ int dx_wald_grouped_host(int64_t n_cells, int64_t n_genes, const int64_t* indptr
     cudaStream_t sc = g_pipe.s_copy, sx = g_pipe.s_comp;
     int rc = DX_OK;
     void *d_indptr, *d_rows, *d_vals, *d_grp, *d_hist, *d_oc, *d_ov, *d_og, *d_xl, *d_xs, *d_off, *d_nk, *d_pinv, *d_lg;
-    void *d_a, *d_b, *d_fi, *d_ll, *d_jac, *d_ni, *d_fl, *d_p, *d_lp, *d_sd;
+    void *d_a, *d_b, *d_fi, *d_ll, *d_jac, *d_ni, *d_fl, *d_p, *d_lp, *d_sd, *d_pk;
 #define HX(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail_cuda(e__, "dx_wald_grouped_host"); goto done; } } while (0)
     {
         int sl = 0;
@@ -306,6 +341,7 @@ int dx_wald_grouped_host(int64_t n_cells, int64_t n_genes, const int64_t* indptr
         HX(g_pipe.ensure(sl++, (size_t)G * p * p * 8, &d_fi)); HX(g_pipe.ensure(sl++, G * 8, &d_ll));
         HX(g_pipe.ensure(sl++, G * 8, &d_jac)); HX(g_pipe.ensure(sl++, G * 4, &d_ni)); HX(g_pipe.ensure(sl++, G * 4, &d_fl));
         HX(g_pipe.ensure(sl++, G * 8, &d_p)); HX(g_pipe.ensure(sl++, G * 8, &d_lp)); HX(g_pipe.ensure(sl++, G * 8, &d_sd));
+        HX(g_pipe.ensure(sl++, G * 8, &d_pk));
         // small inputs first
         HX(cudaMemcpyAsync(d_indptr, indptr, (G + 1) * 8, cudaMemcpyHostToDevice, sc));
         HX(cudaMemcpyAsync(d_grp, cell_group, n_cells, cudaMemcpyHostToDevice, sc));
@@ -331,6 +367,8 @@ int dx_wald_grouped_host(int64_t n_cells, int64_t n_genes, const int64_t* indptr
             HX(dx_launch_ingest(gc, (const int64_t*)d_indptr + g0, (const int32_t*)d_rows, (const float*)d_vals,
                                 (const uint8_t*)d_grp, K, (uint32_t*)d_hist + g0 * (int64_t)K * DX_HIST_BINS,
                                 (int32_t*)d_oc + g0, (float*)d_ov, (uint8_t*)d_og, nullptr, 0, sm_count_cached(), sx));
+            HX(dx_launch_pack_overflow(gc, K, DX_PACK_MIN_ENTRIES, (const int32_t*)d_oc + g0, (const int64_t*)d_indptr + g0,
+                                       (float*)d_ov, (uint8_t*)d_og, (int32_t*)d_pk + 2 * g0, sm_count_cached(), sx));
             HX(dx_launch_fit_grouped(gc, K, p, ps, (const double*)d_xl, (const double*)d_xs,
                                      offset ? (const double*)d_off : nullptr, (const double*)d_nk,
                                      pinv_loc ? (const double*)d_pinv : nullptr, loc_group ? (const int32_t*)d_lg : nullptr,
@@ -338,7 +376,7 @@ int dx_wald_grouped_host(int64_t n_cells, int64_t n_genes, const int64_t* indptr
                                      (const int32_t*)d_oc + g0, (const int64_t*)d_indptr + g0, (const float*)d_ov,
                                      (const uint8_t*)d_og, opts, (double*)d_a + g0, (double*)d_b + g0,
                                      (double*)d_fi + g0 * (int64_t)p * p, (double*)d_ll + g0, (double*)d_jac + g0,
-                                     (int32_t*)d_ni + g0, (int32_t*)d_fl + g0, G, sx));
+                                     (int32_t*)d_ni + g0, (int32_t*)d_fl + g0, G, (const int32_t*)d_pk + 2 * g0, sx));
             HX(dx_launch_wald_from_fit(gc, p, coef, (const double*)d_a + g0, (const double*)d_fi + g0 * (int64_t)p * p, nullptr,
                                        (double*)d_sd + g0, (double*)d_p + g0, (double*)d_lp + g0, G, sx));
         }

@@ -83,9 +83,19 @@ struct Slot {
     double T_r, lgam_const, n_total;
     unsigned long long ovf_groups[4];        // bitmask of groups that own overflow entries (K <= 255)
     const uint32_t* __restrict__ tail;       // [K][64]
+    // overflow entries.  Plain list: (oval[t], ogrp[t]), t < novf, ostep = 1.  Packed by dx_pack_overflow: records
+    // (value, multiplicity) every ostep = 2 floats; `oval/ogrp/novf` view the per-(group, value) records and
+    // `oval_r/novf_r` the per-value records the shared-dispersion loops use (same list when not packed).
     const float* __restrict__ oval;
     const uint8_t* __restrict__ ogrp;
+    const float* __restrict__ oval_r;
+    const float* __restrict__ ohead;         // packed: per group {sum y, sum y^2, sum lgamma(y + 1), count} as 4 doubles
+    int novf_r, ostep;
 };
+
+__device__ __forceinline__ double slot_ovf_weight(const float* rec, int ostep) {
+    return ostep == 2 ? (double)__float_as_uint(__ldg(rec + 1)) : 1.0;
+}
 
 __device__ __forceinline__ bool slot_group_has_ovf(const Slot& s, int k) {
     return (s.ovf_groups[k >> 6] >> (k & 63)) & 1ull;
@@ -114,11 +124,22 @@ template <int SW> __device__ __noinline__ double compute_T(const Slot& s, int o_
             }
         }
     }
+    if (s.shared_r) {
+        const double r = rr[0], lr = dx_log(r);
 #pragma unroll 1
-    for (int t = s.sl; t < s.novf; t += SW) {
-        const double y = (double)__ldg(s.oval + t);
-        const double r = rr[__ldg(s.ogrp + t)];
-        part += dx_lgamma_ratio(r, y) + y * dx_log(r);
+        for (int t = s.sl; t < s.novf_r; t += SW) {
+            const float* rec = s.oval_r + t * s.ostep;
+            const double y = (double)__ldg(rec);
+            part += slot_ovf_weight(rec, s.ostep) * (dx_lgamma_ratio(r, y) + y * lr);
+        }
+    } else {
+#pragma unroll 1
+        for (int t = s.sl; t < s.novf; t += SW) {
+            const float* rec = s.oval + t * s.ostep;
+            const double y = (double)__ldg(rec);
+            const double r = rr[__ldg(s.ogrp + t * s.ostep)];
+            part += slot_ovf_weight(rec, s.ostep) * (dx_lgamma_ratio(r, y) + y * dx_log(r));
+        }
     }
     return sw_sum<SW>(part, s.mask);
 }
@@ -293,10 +314,11 @@ template <int SW> __device__ __noinline__ double scale_terms(const Slot& s) {
         if (s.novf > 0) {
             const double psi_r = dx_digamma(r), psi1_r = dx_trigamma(r);
 #pragma unroll 1
-            for (int t = s.sl; t < s.novf; t += SW) {
-                const double y = (double)__ldg(s.oval + t);
-                D += dx_digamma(r + y) - psi_r;
-                E += dx_trigamma(r + y) - psi1_r;
+            for (int t = s.sl; t < s.novf_r; t += SW) {
+                const float* rec = s.oval_r + t * s.ostep;
+                const double y = (double)__ldg(rec), w = slot_ovf_weight(rec, s.ostep);
+                D += w * (dx_digamma(r + y) - psi_r);
+                E += w * (dx_trigamma(r + y) - psi1_r);
             }
         }
         double G = 0.0, H = 0.0;
@@ -345,10 +367,11 @@ template <int SW> __device__ __noinline__ double scale_terms(const Slot& s) {
             double D = 0.0, E = 0.0;
 #pragma unroll 1
             for (int t = s.sl; t < s.novf; t += SW) {
-                if (__ldg(s.ogrp + t) == k) {
-                    const double y = (double)__ldg(s.oval + t);
-                    D += dx_digamma(r + y) - psi_r;
-                    E += dx_trigamma(r + y) - psi1_r;
+                if (__ldg(s.ogrp + t * s.ostep) == k) {
+                    const float* rec = s.oval + t * s.ostep;
+                    const double y = (double)__ldg(rec), w = slot_ovf_weight(rec, s.ostep);
+                    D += w * (dx_digamma(r + y) - psi_r);
+                    E += w * (dx_trigamma(r + y) - psi1_r);
                 }
             }
             D = sw_sum<SW>(D, s.mask);
@@ -475,6 +498,7 @@ struct FitArgs {
     const int64_t* indptr;
     const float* ovf_val;
     const uint8_t* ovf_group;
+    const int32_t* ovf_packed;        // [n_genes][2] record counts of dx_pack_overflow (0, 0 = plain list); may be null
     dx_fit_opts opts;
     double *a_var, *b_var, *fim_inv, *ll_out, *jac_out;
     int32_t *niter_out, *flags_out;
@@ -566,6 +590,16 @@ dx_fit_grouped_kernel(const FitArgs P) {
     s.novf = P.ovf_count[g];
     s.oval = P.ovf_val + P.indptr[g];
     s.ogrp = P.ovf_group + P.indptr[g];
+    s.oval_r = s.oval; s.novf_r = s.novf; s.ostep = 1; s.ohead = nullptr;
+    if (P.ovf_packed && s.novf > 0) {
+        const int n_a = P.ovf_packed[2 * g], n_b = P.ovf_packed[2 * g + 1];
+        if (n_a > 0) {       // layout written by dx_pack_overflow_kernel (dx_overflow.cu)
+            s.ohead = s.oval;
+            s.oval += 8 * K; s.ogrp += 8 * K;
+            s.oval_r = s.oval + 2 * n_a;
+            s.novf = n_a; s.novf_r = n_b; s.ostep = 2;
+        }
+    }
     {   // constant dispersion model <=> every group carries the same scale design row
         bool same = true;
 #pragma unroll 1
@@ -615,7 +649,24 @@ dx_fit_grouped_kernel(const FitArgs P) {
     s.ymax = sw_max_i<SW>(ymax, mask);
     s.ovf_groups[0] = s.ovf_groups[1] = s.ovf_groups[2] = s.ovf_groups[3] = 0ull;
     __syncwarp(mask);
-    if (s.novf > 0) {
+    if (s.ohead) {
+#pragma unroll 1
+        for (int k = sl; k < K; k += SW) {
+            const float* h = s.ohead + 8 * k;
+            const double sy = __hiloint2double(__float_as_int(__ldg(h + 1)), __float_as_int(__ldg(h + 0)));
+            const double sq = __hiloint2double(__float_as_int(__ldg(h + 3)), __float_as_int(__ldg(h + 2)));
+            const double sg = __hiloint2double(__float_as_int(__ldg(h + 5)), __float_as_int(__ldg(h + 4)));
+            const double cn = __hiloint2double(__float_as_int(__ldg(h + 7)), __float_as_int(__ldg(h + 6)));
+            if (cn > 0.0) { Sk[k] += sy; w2[k] += sq; lgc += sg; }
+        }
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) {      // every lane needs the whole mask
+            const float* h = s.ohead + 8 * k;
+            const double cn = __hiloint2double(__float_as_int(__ldg(h + 7)), __float_as_int(__ldg(h + 6)));
+            if (cn > 0.0) s.ovf_groups[k >> 6] |= (1ull << (k & 63));
+        }
+        __syncwarp(mask);
+    } else if (s.novf > 0) {
 #pragma unroll 1
         for (int k = 0; k < K; ++k) {
             double sk = 0.0, qk = 0.0;
@@ -859,9 +910,11 @@ cudaError_t dx_launch_fit_grouped(int64_t n_genes, int K, int p, int ps,
                                   const uint32_t* tail, const int32_t* ovf_count, const int64_t* indptr,
                                   const float* ovf_val, const uint8_t* ovf_group, const dx_fit_opts* opts,
                                   double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
-                                  int32_t* niter, int32_t* flags, int64_t coef_stride, cudaStream_t stream) {
+                                  int32_t* niter, int32_t* flags, int64_t coef_stride, const int32_t* ovf_packed,
+                                  cudaStream_t stream) {
     if (n_genes <= 0) return cudaSuccess;
     FitArgs A;
+    A.ovf_packed = ovf_packed;
     A.stride = coef_stride > 0 ? coef_stride : n_genes;
     A.n_genes = n_genes; A.K = K; A.p = p; A.ps = ps; A.KL = n_loc_groups;
     A.xu_loc = xu_loc; A.xu_scale = xu_scale; A.offset = offset; A.n_k = n_k; A.pinv_loc = pinv_loc; A.loc_group = loc_group;

@@ -21,7 +21,11 @@ cudaError_t dx_launch_fit_grouped(int64_t n_genes, int K, int p, int ps,
                                   const uint32_t* tail, const int32_t* ovf_count, const int64_t* indptr,
                                   const float* ovf_val, const uint8_t* ovf_group, const dx_fit_opts* opts,
                                   double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
-                                  int32_t* niter, int32_t* flags, int64_t coef_stride, cudaStream_t stream);
+                                  int32_t* niter, int32_t* flags, int64_t coef_stride, const int32_t* ovf_packed,
+                                  cudaStream_t stream);
+cudaError_t dx_launch_pack_overflow(int64_t n_genes, int K, int min_entries, const int32_t* ovf_count,
+                                    const int64_t* indptr, float* ovf_val, uint8_t* ovf_group, int32_t* ovf_packed,
+                                    int sm_count, cudaStream_t stream);
 cudaError_t dx_launch_fit_percell(int64_t n_genes, int64_t n_cells, int p, int ps,
                                   const double* design_loc, const double* design_scale, const double* log_sf,
                                   const int64_t* indptr, const int32_t* rows, const float* vals,

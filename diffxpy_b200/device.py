@@ -226,3 +226,14 @@ class SuffStats:
     def __init__(self, shard, tail, ovf_count, ovf_val, ovf_group, n_groups):
         self.shard, self.tail, self.ovf_count, self.ovf_val, self.ovf_group = shard, tail, ovf_count, ovf_val, ovf_group
         self.n_groups = int(n_groups)
+        self.ovf_packed = None       # set by pack_overflow(): the overflow arrays are then only valid for the fit
+
+    def pack_overflow(self, min_entries=0):
+        """K_pack: rewrite long overflow lists (highly expressed genes) as (value, multiplicity) records, in place.
+        Afterwards the statistics feed dx_nb_fit_grouped_packed only (not the rank / t tests)."""
+        if self.ovf_packed is None:
+            packed = torch.empty((self.tail.shape[0], 2), dtype=torch.int32, device=self.tail.device)
+            _lib.call("dx_pack_overflow", self.tail.shape[0], self.n_groups, int(min_entries), ptr(self.ovf_count),
+                      ptr(self.shard.indptr), ptr(self.ovf_val), ptr(self.ovf_group), ptr(packed), stream_ptr())
+            self.ovf_packed = packed
+        return self

@@ -413,12 +413,13 @@ class Estimator:
             ev0.record()
             if plan["kind"] == "grouped":
                 if "suff" not in plan:
-                    plan["suff"] = shard.group_suffstats(plan["cell_group"], plan["k"])
+                    plan["suff"] = shard.group_suffstats(plan["cell_group"], plan["k"]).pack_overflow()
                 suff = plan["suff"]
-                _lib.call("dx_nb_fit_grouped", g, plan["k"], p, ps, ptr(plan["xu_loc"]), ptr(plan["xu_scale"]),
+                _lib.call("dx_nb_fit_grouped_packed", g, plan["k"], p, ps, ptr(plan["xu_loc"]), ptr(plan["xu_scale"]),
                           ptr(plan["offset"]), ptr(plan["n_k"]), ptr(plan["pinv"]), ptr(plan["loc_group"]),
                           int(plan["kl"]), ptr(suff.tail), ptr(suff.ovf_count), ptr(shard.indptr),
-                          ptr(suff.ovf_val), ptr(suff.ovf_group), opts, ptr(a_var), ptr(b_var), ptr(fim_inv),
+                          ptr(suff.ovf_val), ptr(suff.ovf_group), ptr(suff.ovf_packed), opts, ptr(a_var), ptr(b_var),
+                          ptr(fim_inv),
                           ptr(ll), ptr(jac), ptr(niter), ptr(flags), stream_ptr())
             else:
                 if first:

@@ -173,6 +173,8 @@ def group_pair_device(suff, group_a, group_b, n_a, n_b, do_rank=True):
     """K_twogroup between two of the samples of ONE K_ingest pass (``suff``: SuffStats over n_groups samples):
     sample 0 = group_a, sample 1 = group_b or, for group_b < 0, the union of all other groups."""
     shard = suff.shard
+    if suff.ovf_packed is not None:
+        raise ValueError("group_pair_device: these statistics were packed for the NB fit (SuffStats.pack_overflow)")
     dev = shard.device
     with torch.cuda.device(dev):
         g = shard.n_genes

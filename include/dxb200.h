@@ -125,6 +125,28 @@ int dx_nb_fit_grouped(int64_t n_genes, int32_t n_groups, int32_t p_loc, int32_t 
                       double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
                       int32_t* niter, int32_t* flags, void* stream);
 
+/* ---- K_pack: multiplicity compression of long overflow lists (optional, between K_ingest and K_fit) ---------------
+ * Genes whose counts exceed 64 in many cells (mean expression in the tens or hundreds) carry overflow lists as long
+ * as the cell count, which K_fit walks at every likelihood evaluation.  dx_pack_overflow rewrites, IN PLACE, the list
+ * of every gene with at least min_entries entries (<= 0: DX_PACK_MIN_ENTRIES) as records (value, multiplicity) plus
+ * per-group sums -- layout in diffxpy_b200/csrc/dx_overflow.cu -- and writes ovf_packed[n_genes][2], the two record
+ * counts of a packed gene or {0, 0} for a gene it left alone.  Packed arrays are only understood by
+ * dx_nb_fit_grouped_packed (same arguments as dx_nb_fit_grouped plus ovf_packed; a null ovf_packed = plain lists):
+ * run dx_group_pair_tests / dx_two_group_tests on the statistics BEFORE packing them.  Results agree with the plain
+ * path to summation order (<= 1e-12 relative on the log-likelihood); nothing changes for genes without long lists.
+ * Replaces nothing in the reference: it bounds the cost of tests.py:242-245 on highly expressed genes. */
+#define DX_PACK_MIN_ENTRIES 256
+int dx_pack_overflow(int64_t n_genes, int32_t n_groups, int32_t min_entries, const int32_t* ovf_count,
+                     const int64_t* indptr, float* ovf_val, uint8_t* ovf_group, int32_t* ovf_packed, void* stream);
+int dx_nb_fit_grouped_packed(int64_t n_genes, int32_t n_groups, int32_t p_loc, int32_t p_scale,
+                             const double* xu_loc, const double* xu_scale, const double* offset, const double* n_k,
+                             const double* pinv_loc, const int32_t* loc_group, int32_t n_loc_groups,
+                             const uint32_t* hist, const int32_t* ovf_count, const int64_t* indptr,
+                             const float* ovf_val, const uint8_t* ovf_group, const int32_t* ovf_packed,
+                             const dx_fit_opts* opts,
+                             double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
+                             int32_t* niter, int32_t* flags, void* stream);
+
 /* ---- K_fit (per cell): same schedule, one CTA per gene, streams all cells every step --------------
  * General path: arbitrary numeric design, per-cell size factors (tests.py:177-191 arguments).
  *   design_loc[p_loc][n_cells], design_scale[p_scale][n_cells] (coefficient-major, constraints applied)

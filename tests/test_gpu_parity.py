@@ -254,7 +254,9 @@ def test_cfg1_golden_and_oracle(de, golden_dir):
     _check_fit(est, newton, flags_exact=True)
     _check_fit(est, brent, flags_exact=False)          # reference schedule with scipy brent
     np.testing.assert_allclose(est.b_var, newton["b_var"], rtol=1e-5, atol=2e-6)
-    np.testing.assert_allclose(est.jacobian, newton["jacobian"], rtol=1e-3, atol=1e-6)
+    # the residual gradient is whatever the last scale step left: ~1e-13 when that step was accepted, ~1e-6 when it was
+    # reverted (a decision taken on a log-likelihood difference at rounding level)
+    np.testing.assert_allclose(est.jacobian, newton["jacobian"], rtol=1e-3, atol=1e-5)
 
 
 def test_batch_design_golden(de, golden_dir):
@@ -351,6 +353,107 @@ def test_fit_high_counts_overflow_path(de):
     est = _fit(de, y, xd, np.ones((n, 1)))
     ref = onb.fit_nb(y, xd, np.ones((n, 1)), method_b="newton")
     _check_fit(est, ref, flags_exact=True)
+
+
+@pytest.mark.parametrize("scale_model", ["const", "batch"])
+def test_fit_packed_overflow_lists(de, scale_model):
+    """Highly expressed genes: K_pack rewrites their overflow lists as (value, multiplicity) records.  The packed fit
+    must agree with the oracle like the plain one, with the plain fit to summation order, and keep entries that cannot
+    be packed (non-integer values, counts beyond the table) verbatim."""
+    from diffxpy_b200 import _lib
+    from diffxpy_b200.device import ptr, stream_ptr
+    rng = np.random.default_rng(17)
+    n, g = 20_000, 12
+    cond = rng.integers(0, 2, n)
+    batch = rng.integers(0, 4, n)
+    xd = np.concatenate([np.ones((n, 1)), cond[:, None], (batch[:, None] == np.arange(1, 4)[None])], axis=1).astype(float)
+    zd = np.ones((n, 1)) if scale_model == "const" else np.delete(xd, 1, axis=1)
+    mu = np.exp(rng.uniform(np.log(20), np.log(400), g))[None] * np.exp(0.3 * cond)[:, None] * np.exp(0.1 * batch)[:, None]
+    mu[:, 2] *= 0.02                 # a gene with a short overflow list (left alone)
+    y = rng.poisson(rng.gamma(1.5, mu / 1.5)).astype(np.float64)
+    y[:40, 0] += 0.5                 # a few entries that must stay verbatim
+    y[:5, 3] = 70000.0               # beyond the table range
+    y[:, 1] = y[:, 1] / 4.0          # nothing to pack: (almost) every value is distinct / non-integer
+    est = _fit(de, scipy.sparse.csc_matrix(y.astype(np.float32)), xd, zd)
+    suff = est._plan["suff"]
+    packed = suff.ovf_packed.cpu().numpy()
+    oc = suff.ovf_count.cpu().numpy()
+    assert packed[0, 0] > 0 and packed[3, 0] > 0 and (packed[4:, 0] > 0).all(), packed
+    assert packed[1, 0] == 0 and packed[2, 0] == 0
+    assert (packed[:, 1] <= packed[:, 0]).all() and (16 * 8 + 2 * packed.sum(axis=1) <= np.maximum(oc, 16 * 8)).all()
+    assert packed[5, 1] * 8 < oc[5], "pooled records must be far fewer than entries"
+    ref = onb.fit_nb(y, xd, zd, method_b="newton")
+    _check_fit(est, ref, flags_exact=True)
+    np.testing.assert_allclose(est.b_var, ref["b_var"], rtol=1e-5, atol=2e-6)
+    # plain lists through the C ABI on a fresh K_ingest pass: same decisions, same likelihood to rounding
+    plan, shard = est._plan, est.shard
+    plain = shard.group_suffstats(plan["cell_group"], plan["k"])
+    p, ps = xd.shape[1], zd.shape[1]
+    dev = plain.tail.device
+    f64 = dict(dtype=torch.float64, device=dev)
+    a2, b2 = torch.zeros((p, g), **f64), torch.zeros((ps, g), **f64)
+    fi2, ll2, jac2 = torch.zeros((g, p, p), **f64), torch.zeros(g, **f64), torch.zeros(g, **f64)
+    ni2, fl2 = torch.zeros(g, dtype=torch.int32, device=dev), torch.zeros(g, dtype=torch.int32, device=dev)
+    opts = _lib.DxFitOpts(max_steps=1000, update_b_freq=5, train_loc=1, train_scale=1, init_a=_lib.DX_INIT_CLOSED_FORM,
+                          init_b=_lib.DX_INIT_STANDARD, newton_max_iter=100, reserved=0, lltol=1e-10, newton_xtol=1e-8)
+    _lib.call("dx_nb_fit_grouped", g, plan["k"], p, ps, ptr(plan["xu_loc"]), ptr(plan["xu_scale"]), ptr(plan["offset"]),
+              ptr(plan["n_k"]), ptr(plan["pinv"]), ptr(plan["loc_group"]), int(plan["kl"]), ptr(plain.tail),
+              ptr(plain.ovf_count), ptr(shard.indptr), ptr(plain.ovf_val), ptr(plain.ovf_group), opts, ptr(a2), ptr(b2),
+              ptr(fi2), ptr(ll2), ptr(jac2), ptr(ni2), ptr(fl2), stream_ptr())
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(ni2.cpu().numpy(), est.niter)
+    np.testing.assert_allclose(ll2.cpu().numpy(), est.log_likelihood, rtol=1e-12)
+    np.testing.assert_allclose(a2.cpu().numpy(), est.a_var, rtol=1e-8, atol=1e-9)
+
+
+def test_pack_overflow_records_bit_exact(de):
+    """K_pack: unpacking the (value, multiplicity) records gives back the plain overflow list as a multiset, per group
+    and pooled; the per-group header holds the sums K_fit needs at set-up; short lists are left untouched."""
+    from scipy.special import gammaln
+    rng = np.random.default_rng(23)
+    n, g, k = 30_000, 16, 5
+    grp = rng.integers(0, k, n)
+    mu = np.exp(rng.uniform(np.log(0.5), np.log(500), g))
+    y = rng.poisson(rng.gamma(1.2, mu[None] / 1.2, size=(n, g))).astype(np.float32)
+    y[:17, 0] += 0.25                                        # kept verbatim
+    y[:3, 1] = 50000.0                                       # beyond the table
+    shard, plain = _ingest(y, grp, k)
+    _, pk = _ingest(y, grp, k)
+    pk.pack_overflow()
+    torch.cuda.synchronize()
+    oc, ip = plain.ovf_count.cpu().numpy(), shard.indptr.cpu().numpy()
+    pv, pg = plain.ovf_val.cpu().numpy(), plain.ovf_group.cpu().numpy()
+    qv, qg = pk.ovf_val.cpu().numpy(), pk.ovf_group.cpu().numpy()
+    packed = pk.ovf_packed.cpu().numpy()
+    assert (packed[:, 0] > 0).sum() >= 4 and (packed[:, 0] == 0).sum() >= 2
+    np.testing.assert_array_equal(pk.ovf_count.cpu().numpy(), oc)
+    for gi in range(g):
+        na, nb = packed[gi]
+        s = ip[gi]
+        if na == 0:
+            np.testing.assert_array_equal(pv[s:s + oc[gi]], qv[s:s + oc[gi]])
+            np.testing.assert_array_equal(pg[s:s + oc[gi]], qg[s:s + oc[gi]])
+            continue
+        assert 8 * k + 2 * na + 2 * nb <= oc[gi]
+        vals, grps = pv[s:s + oc[gi]].astype(np.float64), pg[s:s + oc[gi]]
+        head = np.frombuffer(qv[s:s + 8 * k].tobytes(), dtype=np.float64).reshape(k, 4)
+        rec_a = qv[s + 8 * k: s + 8 * k + 2 * na]
+        v_a, m_a = rec_a[0::2].astype(np.float64), rec_a[1::2].copy().view(np.uint32).astype(np.int64)
+        g_a = qg[s + 8 * k: s + 8 * k + 2 * na][0::2]
+        rec_b = qv[s + 8 * k + 2 * na: s + 8 * k + 2 * na + 2 * nb]
+        v_b, m_b = rec_b[0::2].astype(np.float64), rec_b[1::2].copy().view(np.uint32).astype(np.int64)
+        for kk in range(k):
+            want = np.sort(vals[grps == kk])
+            np.testing.assert_array_equal(np.sort(np.repeat(v_a[g_a == kk], m_a[g_a == kk])), want)
+            np.testing.assert_allclose(head[kk], [want.sum(), (want ** 2).sum(), gammaln(want + 1).sum(), len(want)], rtol=1e-12)
+        np.testing.assert_array_equal(np.sort(np.repeat(v_b, m_b)), np.sort(vals))
+        # records of the table part are ordered (group, value); verbatim entries follow in their original order
+        tab = m_a > 1
+        key = g_a[tab].astype(np.int64) * 100000 + v_a[tab].astype(np.int64)
+        assert np.all(np.diff(key) > 0)
+    from diffxpy_b200.stats import stats as dstats
+    with pytest.raises(ValueError):
+        dstats.group_pair_device(pk, 0, 1, 10, 10)
 
 
 def test_quick_scale_and_given_init(de):

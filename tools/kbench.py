@@ -50,6 +50,7 @@ def main():
     ap.add_argument("--flags", type=int, default=3, help="dx_group_suffstats_ex flags (1 integer counts, 2 groups fit u16)")
     ap.add_argument("--plain", action="store_true", help="use dx_group_suffstats (no gene order / integer flag)")
     ap.add_argument("--scale-batch", action="store_true", help="scale model '~1+batch' (8 dispersion coefficients, configs[2])")
+    ap.add_argument("--pack", action="store_true", help="dx_pack_overflow after the ingest + dx_nb_fit_grouped_packed")
     ap.add_argument("--mu-hi", type=float, default=1.0, help="upper end of the log-uniform gene means (default: the bench workload)")
     ap.add_argument("names", nargs="+")
     a = ap.parse_args()
@@ -89,6 +90,7 @@ def main():
         niter, flags = torch.zeros(g, dtype=torch.int32, device=dev), torch.zeros(g, dtype=torch.int32, device=dev)
 
         order, is_int = shard.prepare()
+        packed = torch.zeros((g, 2), dtype=torch.int32, device=dev)
 
         def ingest():
             if a.plain or not hasattr(lib, "dx_group_suffstats_ex"):
@@ -97,8 +99,16 @@ def main():
             else:
                 call(lib, "dx_group_suffstats_ex", g, ptr(shard.indptr), ptr(shard.rows), ptr(shard.vals), ptr(cell_group), k,
                      ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), ptr(order), (a.flags if is_int else a.flags & 2), stream_ptr())
+            if a.pack:
+                call(lib, "dx_pack_overflow", g, k, 0, ptr(ovf_count), ptr(shard.indptr), ptr(ovf_val), ptr(ovf_group),
+                     ptr(packed), stream_ptr())
 
         def fit():
+            if a.pack:
+                call(lib, "dx_nb_fit_grouped_packed", g, k, p, ps, ptr(d_xl), ptr(d_xs), None, ptr(d_nk), ptr(d_pinv), None, k,
+                     ptr(tail), ptr(ovf_count), ptr(shard.indptr), ptr(ovf_val), ptr(ovf_group), ptr(packed), opts, ptr(a_var),
+                     ptr(b_var), ptr(fim_inv), ptr(ll), ptr(jac), ptr(niter), ptr(flags), stream_ptr())
+                return
             call(lib, "dx_nb_fit_grouped", g, k, p, ps, ptr(d_xl), ptr(d_xs), None, ptr(d_nk), ptr(d_pinv), None, k,
                  ptr(tail), ptr(ovf_count), ptr(shard.indptr), ptr(ovf_val), ptr(ovf_group), opts, ptr(a_var),
                  ptr(b_var), ptr(fim_inv), ptr(ll), ptr(jac), ptr(niter), ptr(flags), stream_ptr())
@@ -126,7 +136,8 @@ def main():
         res = {"tail": tail, "ovf_count": ovf_count, "a": a_var, "b": b_var, "fim": fim_inv, "ll": ll, "niter": niter, "flags": flags}
         if not ref:
             ref = {kk: v.clone() for kk, v in res.items()}
-            out.append("mean niter %.3f conv %.4f" % (niter.double().mean().item(), (flags & 1).double().mean().item()))
+            out.append("mean niter %.3f conv %.4f packed genes %d" % (niter.double().mean().item(), (flags & 1).double().mean().item(),
+                                                                       int((packed[:, 0] > 0).sum().item())))
         else:
             ok_int = all(torch.equal(ref[kk], res[kk]) for kk in ("tail", "ovf_count"))
             out.append("suffstats_equal=%s" % ok_int)
