@@ -64,6 +64,7 @@ SIGNATURES = {
     "dx_bh_qvalues_sorted": [_I64, _P, _P, _P, _P, _P],
     "dx_two_group_tests": [_I64, _F64, _F64, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P],
     "dx_group_pair_tests": [_I64, _I32, _I32, _I32, _F64, _F64, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P],
+    "dx_group_pair_tests_big": [_I64, _I32, _I32, _I32, _F64, _F64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P],
     "dx_wald_grouped_host": [_I64, _I64, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, C.POINTER(DxFitOpts),
                              _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
 }

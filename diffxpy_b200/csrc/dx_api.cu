@@ -236,6 +236,25 @@ int dx_group_pair_tests(int64_t n_genes, int32_t n_groups, int32_t group_a, int3
     return DX_OK;
 }
 
+int dx_group_pair_tests_big(int64_t n_genes, int32_t n_groups, int32_t group_a, int32_t group_b, double n_a, double n_b,
+                            const uint32_t* hist, const int32_t* ovf_count, const int64_t* indptr,
+                            const float* ovf_val, const uint8_t* ovf_group,
+                            double* out, int64_t* u1x2, int64_t* tie, int32_t* flags, void* work, int64_t work_bytes,
+                            int64_t slice_bytes, void* stream) {
+    DX_CHECK(n_genes >= 0 && hist && ovf_count && indptr && out && flags, "dx_group_pair_tests_big: bad arguments");
+    DX_CHECK(n_groups >= 2 && n_groups <= DX_MAX_GROUPS, "dx_group_pair_tests_big: n_groups must be in 2..255");
+    DX_CHECK(group_a >= 0 && group_a < n_groups && group_b < n_groups && group_b != group_a,
+             "dx_group_pair_tests_big: group ids out of range");
+    DX_CHECK(n_a >= 1 && n_b >= 1, "dx_group_pair_tests_big: both samples need at least one cell");
+    DX_CHECK(n_a + n_b <= 2097151.0, "dx_group_pair_tests_big: rank sums are exact up to 2^21-1 cells");
+    DX_CHECK(work && slice_bytes >= DX_RANK_WORK_MIN_BYTES && work_bytes >= slice_bytes,
+             "dx_group_pair_tests_big: workspace smaller than one slice of DX_RANK_WORK_MIN_BYTES");
+    DX_CUDA(dx_launch_two_group_big(n_genes, n_groups, group_a, group_b, n_a, n_b, hist, ovf_count, indptr, ovf_val, ovf_group,
+                                    out, u1x2, tie, flags, work, work_bytes, slice_bytes, sm_count_cached(), (cudaStream_t)stream),
+            "dx_group_pair_tests_big");
+    return DX_OK;
+}
+
 // ---- host-buffer entry point ------------------------------------------------------------------------
 // The host shard is cut into chunks of genes with about equal non-zero counts; chunk c+1 crosses PCIe on the copy
 // stream while chunk c is ingested, fitted and tested on the compute stream, so the call costs about one

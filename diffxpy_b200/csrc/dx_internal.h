@@ -45,6 +45,10 @@ cudaError_t dx_launch_t_moments(int64_t n, const double* mu0, const double* mu1,
 cudaError_t dx_launch_two_group(int64_t G, int K, int ga, int gb, double n0, double n1, const uint32_t* tail,
                                 const int32_t* ovf_count, const int64_t* indptr, const float* ovf_val, const uint8_t* ovf_group,
                                 int do_rank, double* out, int64_t* u1x2, int64_t* tie, int32_t* flags, cudaStream_t s);
+cudaError_t dx_launch_two_group_big(int64_t G, int K, int ga, int gb, double n0, double n1, const uint32_t* tail,
+                                    const int32_t* ovf_count, const int64_t* indptr, const float* ovf_val,
+                                    const uint8_t* ovf_group, double* out, int64_t* u1x2, int64_t* tie, int32_t* flags,
+                                    void* work, int64_t work_bytes, int64_t slice_bytes, int sm_count, cudaStream_t s);
 cudaError_t dx_launch_bh(int64_t n, const double* pval, double* qval, double* work, cudaStream_t s);
 cudaError_t dx_launch_bh_sorted(int64_t n, const double* p_sorted, const int64_t* order, double* qval, double* work,
                                 cudaStream_t s);

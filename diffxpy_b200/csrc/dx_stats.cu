@@ -280,6 +280,218 @@ dx_two_group_kernel(int64_t G, int K, int ga, int gb, double n0, double n1, cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// rank test of genes whose overflow list does not fit the on-chip sort of dx_two_group_kernel (normalised /
+// log-transformed data: every non-zero is a non-count value; highly expressed genes).  One CTA of 1024 threads per
+// flagged gene, bitonic sort of 64-bit elements (value key << 32 | block id) in a per-CTA slice of the caller's
+// workspace: sub-sequences of TGB_TILE elements are sorted / merged in shared memory, the wider strides run on the
+// workspace (L2-resident).  The tie blocks are then merged in parallel: every thread owns a contiguous piece of the
+// sorted sequence and the runs of equal values that START in it; counts are integers, so rank sum and tie term are
+// exact and independent of the order of the additions.
+// ------------------------------------------------------------------------------------------------
+constexpr int TGB_T = 1024;
+constexpr int TGB_TILE = 8192;       // elements per shared-memory tile (64 KB)
+
+__device__ __forceinline__ void tgb_cmpx(unsigned long long& a, unsigned long long& b, bool up) {
+    if ((a > b) == up) { const unsigned long long t = a; a = b; b = t; }
+}
+
+__global__ void __launch_bounds__(TGB_T, 1)
+dx_two_group_big_kernel(int64_t G, int K, int ga, int gb, double n0, double n1, const uint32_t* __restrict__ tail_all,
+                        const int32_t* __restrict__ ovf_count, const int64_t* __restrict__ indptr,
+                        const float* __restrict__ ovf_val, const uint8_t* __restrict__ ovf_group,
+                        double* __restrict__ out, int64_t* __restrict__ u1x2_out, int64_t* __restrict__ tie_out,
+                        int32_t* __restrict__ flags_out, unsigned long long* __restrict__ work, int64_t work_elems) {
+    extern __shared__ __align__(16) unsigned long long tgb_tile[];       // [TGB_TILE]
+    __shared__ unsigned s_cnt[2][DX_HIST_BINS + 1];
+    __shared__ unsigned s_tail[2][DX_HIST_BINS + 1];
+    __shared__ long long s_part[TGB_T / 32][2];
+    __shared__ unsigned long long s_scan[TGB_T / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned long long* E = work + (int64_t)blockIdx.x * work_elems;
+    for (int64_t g = blockIdx.x; g < G; g += gridDim.x) {
+        if (!(flags_out[g] & DX_FLAG_RANK_OVERFLOW)) continue;
+        const int novf = ovf_count[g];
+        const int m = novf + DX_HIST_BINS + 1;
+        int64_t mp = TGB_TILE;
+        while (mp < m) mp <<= 1;
+        if (mp > work_elems) continue;            // workspace too small for this gene: the flag stays set
+        const uint32_t* tail_g = tail_all + g * (int64_t)K * DX_HIST_BINS;
+        const float* oval = ovf_val + indptr[g];
+        const uint8_t* ogrp = ovf_group + indptr[g];
+        __syncthreads();
+        if (tid < 2 * DX_HIST_BINS) {
+            const int k = tid / DX_HIST_BINS, j = tid % DX_HIST_BINS;
+            unsigned c = 0;
+            if (k == 0) c = tail_g[ga * DX_HIST_BINS + j];
+            else if (gb >= 0) c = tail_g[gb * DX_HIST_BINS + j];
+            else { for (int kk = 0; kk < K; ++kk) if (kk != ga) c += tail_g[kk * DX_HIST_BINS + j]; }
+            s_tail[k][j] = c;
+        }
+        if (tid < 2) s_tail[tid][DX_HIST_BINS] = 0u;
+        __syncthreads();
+        if (tid < 2 * DX_HIST_BINS) {
+            const int k = tid / DX_HIST_BINS, j = tid % DX_HIST_BINS;
+            s_cnt[k][j + 1] = s_tail[k][j] - s_tail[k][j + 1];
+        }
+        auto member = [&](int t) -> int {
+            const int og = ogrp[t];
+            if (og == ga) return 0;
+            if (gb >= 0) return (og == gb) ? 1 : -1;
+            return (og < K) ? 1 : -1;
+        };
+        // overflow members per sample -> the zero block
+        long long c0 = 0, c1 = 0;
+        for (int t = tid; t < novf; t += TGB_T) {
+            const int mb = member(t);
+            c0 += mb == 0; c1 += mb == 1;
+        }
+        c0 = __reduce_add_sync(DX_FULL_MASK, (unsigned)c0); c1 = __reduce_add_sync(DX_FULL_MASK, (unsigned)c1);
+        if (lane == 0) { s_part[warp][0] = c0; s_part[warp][1] = c1; }
+        __syncthreads();
+        if (tid == 0) {
+            long long a = 0, b = 0;
+            for (int w = 0; w < TGB_T / 32; ++w) { a += s_part[w][0]; b += s_part[w][1]; }
+            s_cnt[0][0] = (unsigned)(n0 - (double)s_tail[0][0] - (double)a);
+            s_cnt[1][0] = (unsigned)(n1 - (double)s_tail[1][0] - (double)b);
+        }
+        // ---- elements: id 0..64 = count block, 65 + t = overflow entry t; everything else sorts to the end ----
+        for (int64_t i = tid; i < mp; i += TGB_T) {
+            unsigned long long e = ~0ull;
+            if (i <= DX_HIST_BINS) e = ((unsigned long long)dx_float_key((float)i) << 32) | (unsigned long long)i;
+            else if (i < m && member((int)i - DX_HIST_BINS - 1) >= 0)
+                e = ((unsigned long long)dx_float_key(oval[i - DX_HIST_BINS - 1]) << 32) | (unsigned long long)i;
+            E[i] = e;
+        }
+        __syncthreads();
+        // ---- bitonic sort, ascending --------------------------------------------------------------------------
+        for (int64_t base = 0; base < mp; base += TGB_TILE) {               // every tile: all stages up to TGB_TILE
+            for (int i = tid; i < TGB_TILE; i += TGB_T) tgb_tile[i] = E[base + i];
+            __syncthreads();
+            for (int k2 = 2; k2 <= TGB_TILE; k2 <<= 1) {
+                for (int j = k2 >> 1; j > 0; j >>= 1) {
+                    for (int i = tid; i < TGB_TILE; i += TGB_T) {
+                        const int l = i ^ j;
+                        if (l > i) {
+                            unsigned long long a = tgb_tile[i], b = tgb_tile[l];
+                            const bool up = (((base + i) & k2) == 0);
+                            if ((a > b) == up) { tgb_tile[i] = b; tgb_tile[l] = a; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            for (int i = tid; i < TGB_TILE; i += TGB_T) E[base + i] = tgb_tile[i];
+            __syncthreads();
+        }
+        for (int64_t k2 = 2 * (int64_t)TGB_TILE; k2 <= mp; k2 <<= 1) {
+            for (int64_t j = k2 >> 1; j >= TGB_TILE; j >>= 1) {             // strides wider than a tile: on the workspace
+                for (int64_t i = tid; i < mp; i += TGB_T) {
+                    const int64_t l = i ^ j;
+                    if (l > i) {
+                        unsigned long long a = E[i], b = E[l];
+                        const bool up = ((i & k2) == 0);
+                        if ((a > b) == up) { E[i] = b; E[l] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+            for (int64_t base = 0; base < mp; base += TGB_TILE) {           // the rest of the merge inside the tiles
+                for (int i = tid; i < TGB_TILE; i += TGB_T) tgb_tile[i] = E[base + i];
+                __syncthreads();
+                const bool up = ((base & k2) == 0);
+                for (int j = TGB_TILE >> 1; j > 0; j >>= 1) {
+                    for (int i = tid; i < TGB_TILE; i += TGB_T) {
+                        const int l = i ^ j;
+                        if (l > i) {
+                            unsigned long long a = tgb_tile[i], b = tgb_tile[l];
+                            if ((a > b) == up) { tgb_tile[i] = b; tgb_tile[l] = a; }
+                        }
+                    }
+                    __syncthreads();
+                }
+                for (int i = tid; i < TGB_TILE; i += TGB_T) E[base + i] = tgb_tile[i];
+                __syncthreads();
+            }
+        }
+        // ---- tie blocks, in parallel -------------------------------------------------------------------------
+        auto counts = [&](unsigned long long e, long long& ta, long long& tb) {
+            ta = tb = 0;
+            if (e == ~0ull) return;
+            const unsigned id = (unsigned)(e & 0xffffffffull);
+            if (id <= (unsigned)DX_HIST_BINS) { ta = s_cnt[0][id]; tb = s_cnt[1][id]; }
+            else { const int mb = member((int)id - DX_HIST_BINS - 1); ta = mb == 0; tb = mb == 1; }
+        };
+        const int64_t per = (m + TGB_T - 1) / TGB_T;
+        const int64_t lo = (int64_t)tid * per < m ? (int64_t)tid * per : m;
+        const int64_t hi = lo + per < m ? lo + per : m;
+        unsigned long long mine = 0;
+        for (int64_t i = lo; i < hi; ++i) { long long ta, tb; counts(E[i], ta, tb); mine += (unsigned long long)(ta + tb); }
+        // exclusive block scan of `mine` (thread order)
+        unsigned long long inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(DX_FULL_MASK, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_scan[warp] = inc;
+        __syncthreads();
+        unsigned long long before = 0;
+        for (int w = 0; w < warp; ++w) before += s_scan[w];
+        long long cum = (long long)(before + inc - mine);
+        long long r1x2 = 0, tie = 0;
+        {
+            int64_t i = lo;
+            // skip the tail of a run that started in an earlier piece
+            if (i > 0 && i < hi) {
+                const unsigned key_prev = (unsigned)(E[i - 1] >> 32);
+                while (i < hi && E[i] != ~0ull && (unsigned)(E[i] >> 32) == key_prev) {
+                    long long ta, tb; counts(E[i], ta, tb); cum += ta + tb; ++i;
+                }
+            }
+            while (i < hi) {
+                const unsigned long long e0 = E[i];
+                if (e0 == ~0ull) break;
+                const unsigned key = (unsigned)(e0 >> 32);
+                long long ta = 0, tb = 0;
+                int64_t e = i;
+                while (e < m) {                                   // the run may extend beyond this thread's piece
+                    const unsigned long long ee = E[e];
+                    if (ee == ~0ull || (unsigned)(ee >> 32) != key) break;
+                    long long a, b; counts(ee, a, b); ta += a; tb += b; ++e;
+                }
+                const long long t = ta + tb;
+                if (t > 0) {
+                    r1x2 += ta * (2 * cum + t + 1);
+                    tie += t * t * t - t;
+                    cum += t;
+                }
+                i = e;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { r1x2 += __shfl_xor_sync(DX_FULL_MASK, r1x2, o); tie += __shfl_xor_sync(DX_FULL_MASK, tie, o); }
+        __syncthreads();
+        if (lane == 0) { s_part[warp][0] = r1x2; s_part[warp][1] = tie; }
+        __syncthreads();
+        if (tid == 0) {
+            r1x2 = tie = 0;
+            for (int w = 0; w < TGB_T / 32; ++w) { r1x2 += s_part[w][0]; tie += s_part[w][1]; }
+            const double n = n0 + n1;
+            const double u1 = 0.5 * (double)r1x2 - n0 * (n0 + 1.0) * 0.5;
+            const double mu = n0 * n1 * 0.5;
+            const double sdev = sqrt(n0 * n1 / 12.0 * ((n + 1.0) - (double)tie / (n * (n - 1.0))));
+            double num = u1 - mu;
+            num -= 0.5 * (double)((num > 0.0) - (num < 0.0));
+            const double z = num / sdev;
+            double p_rank = dx_clip(erfc(fabs(z) * 0.70710678118654752440), 0.0, 1.0);
+            if (isnan(z)) p_rank = NAN;
+            out[g * DX_TG_NCOL + DX_TG_PVAL_RANK] = p_rank;
+            if (u1x2_out) u1x2_out[g] = r1x2 - (long long)(n0 * (n0 + 1.0));
+            if (tie_out) tie_out[g] = tie;
+            flags_out[g] &= ~DX_FLAG_RANK_OVERFLOW;
+        }
+        __syncthreads();
+    }
+}
+
 inline unsigned grid1d(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 
@@ -506,6 +718,25 @@ cudaError_t dx_launch_two_group(int64_t G, int K, int ga, int gb, double n0, dou
     if (G <= 0) return cudaSuccess;
     dx_two_group_kernel<<<(unsigned)G, TG_T, 0, s>>>(G, K, ga, gb, n0, n1, tail, ovf_count, indptr, ovf_val, ovf_group, do_rank,
                                                      out, u1x2, tie, flags);
+    return cudaGetLastError();
+}
+
+cudaError_t dx_launch_two_group_big(int64_t G, int K, int ga, int gb, double n0, double n1, const uint32_t* tail,
+                                    const int32_t* ovf_count, const int64_t* indptr, const float* ovf_val,
+                                    const uint8_t* ovf_group, double* out, int64_t* u1x2, int64_t* tie, int32_t* flags,
+                                    void* work, int64_t work_bytes, int64_t slice_bytes, int sm_count, cudaStream_t s) {
+    if (G <= 0) return cudaSuccess;
+    // one power-of-two slice of the workspace per CTA
+    int64_t pow2 = TGB_TILE;
+    while (pow2 * 2 * 8 <= slice_bytes) pow2 *= 2;
+    int64_t grid = G < 2 * sm_count ? G : 2 * sm_count;
+    if (grid > work_bytes / (pow2 * 8)) grid = work_bytes / (pow2 * 8);
+    if (grid < 1 || slice_bytes < TGB_TILE * 8) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(dx_two_group_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TGB_TILE * 8);
+    if (e != cudaSuccess) return e;
+    dx_two_group_big_kernel<<<(unsigned)grid, TGB_T, TGB_TILE * 8, s>>>(G, K, ga, gb, n0, n1, tail, ovf_count, indptr, ovf_val,
+                                                                       ovf_group, out, u1x2, tie, flags,
+                                                                       (unsigned long long*)work, pow2);
     return cudaGetLastError();
 }
 

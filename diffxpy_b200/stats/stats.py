@@ -139,7 +139,7 @@ def mann_whitney_u_test(x0: Union[np.ndarray, scipy.sparse.csr_matrix], x1: Unio
         raise ValueError('the first axis (number of tests) is not allowed to differ between x0 and x1')
     res = two_group_raw(x0, x1, do_rank=True)
     if np.any(res["flags"] & _lib.FLAG_RANK_OVERFLOW):
-        raise _lib.DxError("rank test: a gene has more non-count values than the on-chip sort holds (4031)")
+        raise _lib.DxError("rank test: a gene has more non-count values than the rank workspace holds (stats.RANK_WORK_MAX_BYTES)")
     return res["out"][:, _lib.TG_PVAL_RANK]
 
 
@@ -166,7 +166,32 @@ def two_group_device(shard, cell_group, n0, n1, do_rank=True):
         _lib.call("dx_two_group_tests", g, float(n0), float(n1), ptr(suff.tail), ptr(suff.ovf_count), ptr(shard.indptr),
                   ptr(suff.ovf_val), ptr(suff.ovf_group), int(bool(do_rank)), ptr(out), ptr(u1x2), ptr(tie), ptr(flags),
                   stream_ptr())
+        if do_rank:
+            _rank_long_lists(suff, 0, 1, n0, n1, out, u1x2, tie, flags)
         return dict(out=out.cpu().numpy(), u1x2=u1x2.cpu().numpy(), tie=tie.cpu().numpy(), flags=flags.cpu().numpy())
+
+
+RANK_WORK_MAX_BYTES = 4 << 30      # device workspace the rank test of long non-count lists may take
+
+
+def _rank_long_lists(suff, group_a, group_b, n_a, n_b, out, u1x2, tie, flags):
+    """Genes K_twogroup flagged FLAG_RANK_OVERFLOW (more non-count values than its on-chip sort holds: normalised /
+    log-transformed data, highly expressed genes) are ranked by dx_group_pair_tests_big in a device workspace."""
+    flagged = (flags & _lib.FLAG_RANK_OVERFLOW) != 0
+    n_flag = int(flagged.sum().item())
+    if n_flag == 0:
+        return
+    shard = suff.shard
+    longest = int(suff.ovf_count[flagged].max().item()) + _lib.DX_HIST_BINS + 1
+    slice_elems = 8192
+    while slice_elems < longest:
+        slice_elems *= 2
+    sm = torch.cuda.get_device_properties(shard.device).multi_processor_count
+    n_cta = max(1, min(n_flag, 2 * sm, RANK_WORK_MAX_BYTES // (8 * slice_elems)))
+    work = torch.empty(n_cta * slice_elems, dtype=torch.int64, device=shard.device)
+    _lib.call("dx_group_pair_tests_big", shard.n_genes, int(suff.n_groups), int(group_a), int(group_b), float(n_a),
+              float(n_b), ptr(suff.tail), ptr(suff.ovf_count), ptr(shard.indptr), ptr(suff.ovf_val), ptr(suff.ovf_group),
+              ptr(out), ptr(u1x2), ptr(tie), ptr(flags), ptr(work), work.numel() * 8, slice_elems * 8, stream_ptr())
 
 
 def group_pair_device(suff, group_a, group_b, n_a, n_b, do_rank=True):
@@ -185,6 +210,8 @@ def group_pair_device(suff, group_a, group_b, n_a, n_b, do_rank=True):
         _lib.call("dx_group_pair_tests", g, int(suff.n_groups), int(group_a), int(group_b), float(n_a), float(n_b),
                   ptr(suff.tail), ptr(suff.ovf_count), ptr(shard.indptr), ptr(suff.ovf_val), ptr(suff.ovf_group),
                   int(bool(do_rank)), ptr(out), ptr(u1x2), ptr(tie), ptr(flags), stream_ptr())
+        if do_rank:
+            _rank_long_lists(suff, group_a, group_b, n_a, n_b, out, u1x2, tie, flags)
         return dict(out=out.cpu().numpy(), u1x2=u1x2.cpu().numpy(), tie=tie.cpu().numpy(), flags=flags.cpu().numpy())
 
 

@@ -362,7 +362,7 @@ def two_group_postprocess(out, flags, n0, n1, do_rank, is_logged=False, is_sig_z
     pval = np.zeros([out.shape[0]]) + np.nan
     col = _lib.TG_PVAL_RANK if do_rank else _lib.TG_PVAL_T
     if do_rank and np.any(flags[idx_run] & _lib.FLAG_RANK_OVERFLOW):
-        raise _lib.DxError("rank test: a gene has more non-count values than the on-chip sort holds (4031)")
+        raise _lib.DxError("rank test: a gene has more non-count values than the rank workspace holds (stats.RANK_WORK_MAX_BYTES)")
     pval[idx_run] = out[idx_run, col]
     pval[np.where(np.logical_and(np.logical_and(mean_x0 == mean_x1, mean > 0), np.logical_not(var_geq_zero)))[0]] = 1.0
     if is_sig_zerovar:

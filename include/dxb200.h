@@ -216,6 +216,20 @@ int dx_group_pair_tests(int64_t n_genes, int32_t n_groups, int32_t group_a, int3
                         const float* ovf_val, const uint8_t* ovf_group,
                         int32_t do_rank, double* out, int64_t* u1x2, int64_t* tie, int32_t* flags, void* stream);
 
+/* Rank test of the genes dx_group_pair_tests / dx_two_group_tests flagged DX_FLAG_RANK_OVERFLOW (more than 4031 values
+ * outside the count bins: normalised or log-transformed data, highly expressed genes).  Same arguments (the arrays of the
+ * first call, its out / u1x2 / tie / flags are updated in place and the flag cleared) plus a device workspace: every
+ * CTA sorts one gene in a slice of slice_bytes (rounded down to a power of two) of it, so a gene with n_ovf such values
+ * needs slice_bytes >= 8 * max(8192, next_pow2(n_ovf + 65)); the launch uses min(n_genes, 2 per SM,
+ * work_bytes / slice_bytes) CTAs.  A gene whose list does not fit a slice keeps its flag.
+ * Replaces the same reference lines as dx_group_pair_tests (stats.py:42-75 via det.py:1672-1743). */
+#define DX_RANK_WORK_MIN_BYTES 65536
+int dx_group_pair_tests_big(int64_t n_genes, int32_t n_groups, int32_t group_a, int32_t group_b, double n_a, double n_b,
+                            const uint32_t* hist, const int32_t* ovf_count, const int64_t* indptr,
+                            const float* ovf_val, const uint8_t* ovf_group,
+                            double* out, int64_t* u1x2, int64_t* tie, int32_t* flags, void* work, int64_t work_bytes,
+                            int64_t slice_bytes, void* stream);
+
 /* ---- host-buffer entry point (what bench.py's e2e leg and a foreign-language binding call) ---------
  * Full Wald test of one coefficient on a HOST CSC matrix with a grouped design: copies the inputs to
  * the device, runs ingest + fit + Wald, copies the per-gene rows back.  Pointers are host memory

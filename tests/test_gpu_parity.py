@@ -647,6 +647,44 @@ def test_rank_and_t_against_scipy(de):
     np.testing.assert_allclose(rk.pval, np.array([m.pvalue for m in mw]), rtol=1e-12, atol=1e-300)
 
 
+def test_rank_test_long_non_count_lists(de):
+    """Log-normalised data and highly expressed genes: every non-zero is a non-count value, far more of them than the
+    on-chip sort of K_twogroup holds -> dx_group_pair_tests_big (sort in a device workspace, parallel tie merge).
+    U is bit exact against scipy, p to rounding; heavy ties (log1p of small counts), several sort tiles, padding."""
+    rng = np.random.default_rng(7)
+    n, g = 40_000, 10
+    cond = (rng.uniform(size=n) < 0.4).astype(int)
+    mu = np.exp(rng.uniform(np.log(0.05), np.log(200), g))
+    mu[0], mu[1], mu[2] = 0.02, 3.0, 400.0
+    cnt = rng.poisson(rng.gamma(1.5, mu[None] / 1.5, size=(n, g))).astype(np.float64)
+    cnt[:, 3] *= np.exp(0.2 * cond)                          # a shifted gene
+    sf = rng.uniform(0.5, 2.0, n)
+    x = np.log1p(cnt / sf[:, None])                          # (almost) all non-zeros distinct
+    x[:, 4] = np.log1p(cnt[:, 4])                            # heavy ties among non-count values
+    x[:, 5] = cnt[:, 5]                                      # plain counts, many above 64
+    x[:, 6] = -x[:, 6]                                       # negative values sort below the zero block
+    x = x.astype(np.float32).astype(np.float64)              # the shard stores float32: compare on what it holds
+    names = ["g%d" % i for i in range(g)]
+    sd = pd.DataFrame({"condition": cond})
+    a, b = x[cond == 0], x[cond == 1]
+    assert ((x != 0).sum(axis=0) > 20_000).sum() >= 5
+    for data in (x, scipy.sparse.csr_matrix(x)):
+        rk = de.test.rank_test(data=data, grouping="condition", sample_description=sd, gene_names=names)
+        mw = [scipy.stats.mannwhitneyu(a[:, i], b[:, i], use_continuity=True, alternative="two-sided", method="asymptotic")
+              for i in range(g)]
+        np.testing.assert_array_equal(rk.u_statistic, np.array([m.statistic for m in mw]))
+        np.testing.assert_allclose(rk.pval, np.array([m.pvalue for m in mw]), rtol=1e-11, atol=1e-300)
+    # several groups from one ingest pass: pairwise and versus-rest take the same path
+    grp3 = rng.integers(0, 3, n)
+    sd3 = pd.DataFrame({"g": grp3.astype(str)})
+    pw = de.test.pairwise(data=x, grouping="g", test="rank", lazy=False, sample_description=sd3, gene_names=names)
+    p01 = np.array([scipy.stats.mannwhitneyu(x[grp3 == 0][:, i], x[grp3 == 1][:, i], use_continuity=True,
+                                             alternative="two-sided", method="asymptotic").pvalue for i in range(g)])
+    groups = [str(v) for v in pw.groups]
+    i0, i1 = groups.index("0"), groups.index("1")
+    np.testing.assert_allclose(pw.pval[i0, i1], p01, rtol=1e-11, atol=1e-300)
+
+
 def test_extreme_values_rules(de):
     # unit_test/test_extreme_values.py:11-73
     rng = np.random.default_rng(1)

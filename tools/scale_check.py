@@ -61,6 +61,35 @@ def cfg5(n_cells=1_000_000, n_genes=2500):
             "flags_nonzero": int(np.count_nonzero(res["flags"]))}
 
 
+def ranklog(n_cells=100_000, n_genes=2_000):
+    """rank test on log-normalised data (every non-zero is a non-count value): K_ingest + K_twogroup + the workspace sort."""
+    import scipy.stats
+    from diffxpy_b200.device import CountShard
+    bench.MU_HI = 3.0
+    shard, cond, _ = bench.make_shard(torch, dev, seed=6, n_genes=n_genes, n_cells=n_cells, chunk=200)
+    bench.MU_HI = 1.0
+    sf = torch.rand(n_cells, device=dev) + 0.5
+    vals = torch.log1p(shard.vals / sf[shard.rows.long()])
+    shard = CountShard(shard.indptr, shard.rows, vals.contiguous(), n_cells)
+    n0, n1 = int((cond == 0).sum()), int((cond == 1).sum())
+    res, sec = timed(lambda: two_group_device(shard, cond.astype(np.uint8), n0, n1, do_rank=True))
+    u1 = res["u1x2"] / 2.0
+    indptr = shard.indptr.cpu().numpy()
+    nnz_g = np.diff(indptr)
+    worst_p = 0.0
+    for g in (int(np.argmax(nnz_g)), n_genes // 2, int(np.argmin(nnz_g))):
+        sl = slice(indptr[g], indptr[g + 1])
+        col = np.zeros(n_cells, dtype=np.float64)
+        col[shard.rows[sl].cpu().numpy()] = shard.vals[sl].cpu().numpy()
+        ref = scipy.stats.mannwhitneyu(col[cond == 0], col[cond == 1], use_continuity=True, alternative="two-sided")
+        assert ref.statistic == u1[g], "U1 differs from scipy at gene %d" % g
+        worst_p = max(worst_p, abs(ref.pvalue - res["out"][g, _lib.TG_PVAL_RANK]) / max(ref.pvalue, 1e-300))
+    return {"config": "rank_test on log1p(count / size factor), %d cells x %d genes, two groups" % (n_cells, n_genes),
+            "nnz": shard.nnz, "max_nnz_per_gene": int(nnz_g.max()), "median_nnz_per_gene": float(np.median(nnz_g)),
+            "seconds": sec, "genes_per_s": n_genes / sec, "u1_matches_scipy_exactly": True,
+            "max_rel_dp_vs_scipy": worst_p, "flags_nonzero": int(np.count_nonzero(res["flags"]))}
+
+
 def cfg3(n_cells=100_000, n_genes=20_000):
     """LRT: full '~1+condition+batch' vs reduced '~1+batch', scale model '~1+batch' (8 dispersion coefficients)."""
     shard, cond, batch = bench.make_shard(torch, dev, seed=3, n_genes=n_genes, n_cells=n_cells)
@@ -143,6 +172,6 @@ def api(n_cells=100_000, n_genes=20_000):
 if __name__ == "__main__":
     which = sys.argv[1:] or ["cfg5", "cfg3", "cfg4"]
     for w in which:
-        out = {"cfg5": cfg5, "cfg3": cfg3, "cfg4": cfg4, "api": api}[w]()
+        out = {"cfg5": cfg5, "cfg3": cfg3, "cfg4": cfg4, "api": api, "ranklog": ranklog}[w]()
         print(json.dumps(out), flush=True)
         torch.cuda.empty_cache()
