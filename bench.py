@@ -406,9 +406,9 @@ def main_cuda(args):
                          "one process per core)" % (gps, N_CELLS)}
 
     from diffxpy_b200.testing import correction as _corr
-    # own kernels per step: ingest, pack, fit, wald + BH (all-pairs path: rank, scatter, chunk-min, suffix, gather; sort path
-    # for the gathered vector of several GPUs: chunk-min, suffix after torch.sort)
-    launches_per_step = 4 + (5 if world * g <= _corr.BH_KERNEL_MAX else 2)
+    # own kernels per step: ingest, pack, fit, wald + BH (bucket histogram, bucket scan, place, rank, chunk-min, suffix,
+    # gather; the same kernels for the gathered vector of several GPUs)
+    launches_per_step = 4 + (7 if world * g <= _corr.BH_KERNEL_MAX else 2)
     if rank == 0:
         conv = float((flags & 1).to(torch.float64).mean().item())
         line = {

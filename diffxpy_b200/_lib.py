@@ -60,6 +60,7 @@ SIGNATURES = {
     "dx_lrt": [_I64, _P, _P, _I32, _P, _P, _P],
     "dx_two_coef_z": [_I64, _P, _P, _P, _P, _P, _P],
     "dx_t_test_moments": [_I64, _P, _P, _P, _P, _F64, _F64, _P, _P],
+    "dx_bh_work_bytes": [_I64, C.POINTER(C.c_int64)],
     "dx_bh_qvalues": [_I64, _P, _P, _P, _P],
     "dx_bh_qvalues_sorted": [_I64, _P, _P, _P, _P, _P],
     "dx_two_group_tests": [_I64, _F64, _F64, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P],

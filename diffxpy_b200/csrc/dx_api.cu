@@ -197,6 +197,12 @@ int dx_t_test_moments(int64_t n, const double* mu0, const double* mu1, const dou
     return DX_OK;
 }
 
+int dx_bh_work_bytes(int64_t n, int64_t* bytes) {
+    DX_CHECK(n >= 0 && bytes, "dx_bh_work_bytes: bad arguments");
+    *bytes = (int64_t)dx_bh_work_bytes_impl(n);
+    return DX_OK;
+}
+
 int dx_bh_qvalues(int64_t n, const double* pval, double* qval, double* work, void* stream) {
     DX_CHECK(n >= 0 && pval && qval && work, "dx_bh_qvalues: bad arguments");
     DX_CUDA(dx_launch_bh(n, pval, qval, work, (cudaStream_t)stream), "dx_bh_qvalues");

@@ -49,6 +49,7 @@ cudaError_t dx_launch_two_group_big(int64_t G, int K, int ga, int gb, double n0,
                                     const int32_t* ovf_count, const int64_t* indptr, const float* ovf_val,
                                     const uint8_t* ovf_group, double* out, int64_t* u1x2, int64_t* tie, int32_t* flags,
                                     void* work, int64_t work_bytes, int64_t slice_bytes, int sm_count, cudaStream_t s);
+size_t dx_bh_work_bytes_impl(int64_t n);
 cudaError_t dx_launch_bh(int64_t n, const double* pval, double* qval, double* work, cudaStream_t s);
 cudaError_t dx_launch_bh_sorted(int64_t n, const double* p_sorted, const int64_t* order, double* qval, double* work,
                                 cudaStream_t s);

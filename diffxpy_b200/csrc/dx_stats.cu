@@ -292,10 +292,6 @@ dx_two_group_kernel(int64_t G, int K, int ga, int gb, double n0, double n1, cons
 constexpr int TGB_T = 1024;
 constexpr int TGB_TILE = 8192;       // elements per shared-memory tile (64 KB)
 
-__device__ __forceinline__ void tgb_cmpx(unsigned long long& a, unsigned long long& b, bool up) {
-    if ((a > b) == up) { const unsigned long long t = a; a = b; b = t; }
-}
-
 __global__ void __launch_bounds__(TGB_T, 1)
 dx_two_group_big_kernel(int64_t G, int K, int ga, int gb, double n0, double n1, const uint32_t* __restrict__ tail_all,
                         const int32_t* __restrict__ ovf_count, const int64_t* __restrict__ indptr,
@@ -572,6 +568,94 @@ dx_bh_scatter_kernel(int64_t G, const double* __restrict__ p, const int* __restr
     }
 }
 
+// ---- ranks without a sort and without all pairs: monotone buckets ------------------------------------------------
+// c_i = #{j : p_j <= p_i} = (elements in lower buckets) + (elements of the own bucket that are <= p_i).  The bucket map
+// is monotone in p: p >= 2^-14 falls into one of 16384 linear buckets (uniform p-values: n / 16384 per bucket), smaller
+// p into 4 buckets per binade (the exponent and two mantissa bits), so neither a null-dominated nor a
+// signal-dominated vector piles up; p == 1 (diffxpy's zero-variance rule) has the last bucket to itself.  Counting is
+// exact, the result is the same integer the all-pairs kernel returns.  The 20k bucket counters fit in shared memory for
+// the single-CTA scan.
+constexpr int BH_LIN = 16384;
+constexpr int BH_LB = 4036;                        // log buckets: (bits of p) >> 50 for p < 2^-14  (1009 binades x 4)
+constexpr int BH_NB = BH_LB + BH_LIN + 1;          // + linear buckets floor(p * 16384) in 1..16384
+
+__device__ __forceinline__ int dx_bh_bucket(double p) {        // p >= 0, not NaN
+    int b;
+    if (p >= 0x1p-14) {
+        const double sc = p * (double)BH_LIN;
+        b = BH_LB + (sc >= (double)BH_LIN ? BH_LIN : (int)sc);
+    } else {
+        b = (int)(__double_as_longlong(p + 0.0) >> 50);
+    }
+    return b < 0 ? 0 : (b >= BH_NB ? BH_NB - 1 : b);
+}
+
+__global__ void __launch_bounds__(256)
+dx_bh_hist_kernel(int64_t G, const double* __restrict__ p, int* __restrict__ hist, double* __restrict__ tsorted) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= G) return;
+    tsorted[i] = INFINITY;
+    const double pi = p[i];
+    if (pi == pi) atomicAdd(hist + dx_bh_bucket(pi), 1);
+}
+
+// exclusive scan of the bucket counts (single CTA); offs[BH_NB] = number of non-NaN p-values; clears the cursors
+__global__ void __launch_bounds__(1024)
+dx_bh_bucket_scan_kernel(int* __restrict__ hist_offs, int* __restrict__ cursor) {
+    extern __shared__ int s_h[];             // [BH_NB + 1]
+    __shared__ int s_w[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int b = tid; b < BH_NB; b += 1024) { s_h[b] = hist_offs[b]; cursor[b] = 0; }
+    __syncthreads();
+    constexpr int PER = (BH_NB + 1023) / 1024;
+    const int lo = tid * PER < BH_NB ? tid * PER : BH_NB, hi = (lo + PER < BH_NB) ? lo + PER : BH_NB;
+    int sum = 0;
+    for (int b = lo; b < hi; ++b) sum += s_h[b];
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(DX_FULL_MASK, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += s_w[w];
+    int run = before + inc - sum;
+    for (int b = lo; b < hi; ++b) { const int c = s_h[b]; s_h[b] = run; run += c; }
+    if (tid == 1023) s_h[BH_NB] = run;
+    __syncthreads();
+    for (int b = tid; b <= BH_NB; b += 1024) hist_offs[b] = s_h[b];
+}
+
+__global__ void __launch_bounds__(256)
+dx_bh_place_kernel(int64_t G, const double* __restrict__ p, const int* __restrict__ offs, int* __restrict__ cursor,
+                   long long* __restrict__ skey) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= G) return;
+    const double pi = p[i];
+    if (pi != pi) return;
+    const int b = dx_bh_bucket(pi);
+    skey[offs[b] + atomicAdd(cursor + b, 1)] = dx_p_key(pi);
+}
+
+// cnt_i, and t_i = p_i / (cnt_i / n) into slot cnt_i - 1 of the table sorted by p (a tie block shares its last slot and
+// one value; the other slots of the block stay +inf)
+__global__ void __launch_bounds__(256)
+dx_bh_bucket_rank_kernel(int64_t G, const double* __restrict__ p, const int* __restrict__ offs,
+                         const long long* __restrict__ skey, int* __restrict__ cnt, double* __restrict__ tsorted) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= G) return;
+    const double pi = p[i];
+    if (pi != pi) { cnt[i] = 0; return; }
+    const int b = dx_bh_bucket(pi);
+    const long long ki = dx_p_key(pi);
+    const int lo = offs[b], hi = offs[b + 1];
+    int c = lo;
+    if (b == BH_NB - 1) c = hi;                              // p == 1: everything is <= p
+    else for (int j = lo; j < hi; ++j) c += (skey[j] <= ki) ? 1 : 0;
+    cnt[i] = c;
+    const int n = offs[BH_NB];
+    tsorted[c - 1] = pi / ((double)c / (double)n);          // statsmodels: p_sorted / (rank / n)
+}
+
 // ---- running minimum from the right, multi-CTA: chunk minima, then per-chunk suffix scan with the carry of the later
 // chunks.  SORTED: the values are p_sorted[j] / ((j + 1) / n) (n = number of non-NaN = index of the first NaN) and the
 // result is scattered through `order`; otherwise the values are the table of dx_bh_scatter_kernel, scanned in place.
@@ -740,20 +824,42 @@ cudaError_t dx_launch_two_group_big(int64_t G, int K, int ga, int gb, double n0,
     return cudaGetLastError();
 }
 
+size_t dx_bh_work_bytes_impl(int64_t n) {
+    const int64_t n_chunks = (n + BH_ST - 1) / BH_ST;
+    return (size_t)(8 * n + 8 * n_chunks + 8 * n + 4 * n + 4 * (2 * (int64_t)BH_NB + 2) + 16);
+}
+
 cudaError_t dx_launch_bh(int64_t n, const double* pval, double* qval, double* work, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
-    // work: n doubles (table sorted by p) + ceil(n / 1024) doubles (chunk minima) + n ints (cnt)
+    // work: table sorted by p [n] | chunk minima [ceil(n / 1024)] | bucket-ordered keys [n] | cnt [n] | bucket offsets
+    // [BH_NB + 1] | bucket cursors [BH_NB]
     const int n_chunks = (int)((n + BH_ST - 1) / BH_ST);
     double* chunk_min = work + n;
-    int* cnt = reinterpret_cast<int*>(chunk_min + n_chunks);
-    cudaError_t e = cudaMemsetAsync(cnt, 0, (size_t)n * sizeof(int), s);
-    if (e != cudaSuccess) return e;
-    const dim3 grid((unsigned)((n + BH_T * BH_R - 1) / (BH_T * BH_R)), BH_JS);
-    dx_bh_rank_kernel<<<grid, BH_T, 0, s>>>(n, pval, cnt, work);
-    dx_bh_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, pval, cnt, work);
+    long long* skey = reinterpret_cast<long long*>(chunk_min + n_chunks);
+    int* cnt = reinterpret_cast<int*>(skey + n);
+    int* offs = cnt + n;
+    int* cursor = offs + BH_NB + 1;
+    static const bool all_pairs = getenv("DXB200_BH_ALLPAIRS") != nullptr;      // development hook: the previous formulation
+    const unsigned g256 = (unsigned)((n + 255) / 256);
+    if (all_pairs) {
+        cudaError_t e = cudaMemsetAsync(cnt, 0, (size_t)n * sizeof(int), s);
+        if (e != cudaSuccess) return e;
+        const dim3 grid((unsigned)((n + BH_T * BH_R - 1) / (BH_T * BH_R)), BH_JS);
+        dx_bh_rank_kernel<<<grid, BH_T, 0, s>>>(n, pval, cnt, work);
+        dx_bh_scatter_kernel<<<g256, 256, 0, s>>>(n, pval, cnt, work);
+    } else {
+        cudaError_t e = cudaMemsetAsync(offs, 0, (size_t)(BH_NB + 1) * sizeof(int), s);
+        if (e != cudaSuccess) return e;
+        dx_bh_hist_kernel<<<g256, 256, 0, s>>>(n, pval, offs, work);
+        e = cudaFuncSetAttribute(dx_bh_bucket_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (BH_NB + 1) * 4);
+        if (e != cudaSuccess) return e;
+        dx_bh_bucket_scan_kernel<<<1, 1024, (BH_NB + 1) * 4, s>>>(offs, cursor);
+        dx_bh_place_kernel<<<g256, 256, 0, s>>>(n, pval, offs, cursor, skey);
+        dx_bh_bucket_rank_kernel<<<g256, 256, 0, s>>>(n, pval, offs, skey, cnt, work);
+    }
     dx_bh_chunkmin_kernel<false><<<n_chunks, BH_ST, 0, s>>>(n, work, chunk_min);
     dx_bh_suffix_kernel<false><<<n_chunks, BH_ST, 0, s>>>(n, work, chunk_min, n_chunks, nullptr, nullptr);
-    dx_bh_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, pval, cnt, work, qval);
+    dx_bh_gather_kernel<<<g256, 256, 0, s>>>(n, pval, cnt, work, qval);
     return cudaGetLastError();
 }
 

@@ -9,7 +9,9 @@ import torch
 from .. import _lib
 from ..device import cuda_device, ptr, stream_ptr
 
-BH_KERNEL_MAX = 32768     # above this the all-pairs kernel loses to a device sort
+import ctypes as _C
+
+BH_KERNEL_MAX = 1 << 24   # above this: device sort + dx_bh_qvalues_sorted
 
 
 def bh_device(p):
@@ -17,7 +19,9 @@ def bh_device(p):
     if p.shape[0] <= BH_KERNEL_MAX:
         p = p.contiguous()
         q = torch.empty_like(p)
-        work = torch.empty((p.shape[0] * 3 + 1) // 2 + p.shape[0] // 1024 + 2, dtype=torch.float64, device=p.device)
+        nbytes = _C.c_int64(0)
+        _lib.call("dx_bh_work_bytes", p.shape[0], _C.byref(nbytes))
+        work = torch.empty((nbytes.value + 7) // 8, dtype=torch.float64, device=p.device)
         _lib.call("dx_bh_qvalues", p.shape[0], ptr(p), ptr(q), ptr(work), stream_ptr())
         return q
     # large n: device sort (NaNs last) + one kernel for ranks, running minimum and the scatter back

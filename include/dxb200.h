@@ -185,8 +185,9 @@ int dx_t_test_moments(int64_t n, const double* mu0, const double* mu1, const dou
                       double n0, double n1, double* pval, void* stream);
 
 /* Benjamini-Hochberg q-values of the non-NaN p-values (correction.py:5-24 -> statsmodels fdr_bh arithmetic,
- * bit-identical values; all-pairs formulation without a sort, meant for n up to ~1e5).
- * work: 8 * (n + ceil(n / 1024)) + 4 * n bytes, 8-byte aligned. */
+ * bit-identical values), without a sort: ranks by counting over monotone buckets of p, then a running minimum from
+ * the right.  work: dx_bh_work_bytes(n) bytes of device memory (20 n + 8 ceil(n / 1024) + 0.17 MB), 8-byte aligned. */
+int dx_bh_work_bytes(int64_t n, int64_t* bytes);
 int dx_bh_qvalues(int64_t n, const double* pval, double* qval, double* work, void* stream);
 /* Same q-values for large n, after a device sort done by the caller: p_sorted ascending with NaNs last, order[j] =
  * position of p_sorted[j] in the unsorted vector (what torch.sort / cub return); qval is written unsorted.

@@ -97,6 +97,13 @@ def test_bh_on_device(de, gold):
     finally:
         correction.BH_KERNEL_MAX = old
     assert np.all(np.isnan(correction.correct(np.full(7, np.nan))))
+    # the bucketed rank count: p-values over 300 decades, denormals, exact 0 / 1, one value repeated thousands of times
+    rng = np.random.default_rng(6)
+    p = np.concatenate([rng.uniform(size=30000), 10.0 ** rng.uniform(-320, 0, 20000), np.full(3000, 1.0), np.zeros(50),
+                        np.full(2500, 0.25), np.full(40, np.nan), [2.0 ** -16, np.nextafter(2.0 ** -16, 0), 5e-324]])
+    rng.shuffle(p)
+    np.testing.assert_array_equal(correction.correct(p), ost.bh_correct(p))
+    np.testing.assert_array_equal(correction.correct(p[:1]), ost.bh_correct(p[:1]))
 
 
 # ---------------------------------------------------------------------------------------------------
