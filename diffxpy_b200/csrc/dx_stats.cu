@@ -572,11 +572,12 @@ dx_bh_scatter_kernel(int64_t G, const double* __restrict__ p, const int* __restr
 // c_i = #{j : p_j <= p_i} = (elements in lower buckets) + (elements of the own bucket that are <= p_i).  The bucket map
 // is monotone in p: p >= 2^-14 falls into one of 16384 linear buckets (uniform p-values: n / 16384 per bucket), smaller
 // p into 4 buckets per binade (the exponent and two mantissa bits), so neither a null-dominated nor a
-// signal-dominated vector piles up; p == 1 (diffxpy's zero-variance rule) has the last bucket to itself.  Counting is
+// signal-dominated vector piles up; p == 0 (underflow of strongly significant genes) and p == 1 (diffxpy's zero-variance
+// rule) have the first and the last bucket to themselves, where the count is the bucket size.  Counting is
 // exact, the result is the same integer the all-pairs kernel returns.  The 20k bucket counters fit in shared memory for
 // the single-CTA scan.
 constexpr int BH_LIN = 16384;
-constexpr int BH_LB = 4036;                        // log buckets: (bits of p) >> 50 for p < 2^-14  (1009 binades x 4)
+constexpr int BH_LB = 4037;                        // bucket 0: p == 0; log buckets 1 + ((bits of p) >> 50) for p < 2^-14  (1009 binades x 4)
 constexpr int BH_NB = BH_LB + BH_LIN + 1;          // + linear buckets floor(p * 16384) in 1..16384
 
 __device__ __forceinline__ int dx_bh_bucket(double p) {        // p >= 0, not NaN
@@ -585,7 +586,7 @@ __device__ __forceinline__ int dx_bh_bucket(double p) {        // p >= 0, not Na
         const double sc = p * (double)BH_LIN;
         b = BH_LB + (sc >= (double)BH_LIN ? BH_LIN : (int)sc);
     } else {
-        b = (int)(__double_as_longlong(p + 0.0) >> 50);
+        b = (p == 0.0) ? 0 : 1 + (int)(__double_as_longlong(p) >> 50);
     }
     return b < 0 ? 0 : (b >= BH_NB ? BH_NB - 1 : b);
 }
@@ -649,8 +650,18 @@ dx_bh_bucket_rank_kernel(int64_t G, const double* __restrict__ p, const int* __r
     const long long ki = dx_p_key(pi);
     const int lo = offs[b], hi = offs[b + 1];
     int c = lo;
-    if (b == BH_NB - 1) c = hi;                              // p == 1: everything is <= p
-    else for (int j = lo; j < hi; ++j) c += (skey[j] <= ki) ? 1 : 0;
+    if (pi >= 1.0 || pi == 0.0) {      // (tested on p, not on the bucket index: ptxas 12.9 folds "b == 0 || b == BH_NB - 1"
+                                       // into the predicate output of the clamping VIMNMX.RELU and takes this branch for every bucket)
+        c = hi;                                              // p == 1 or p == 0: the whole bucket is one tie block
+    } else {
+        int c1 = 0, c2 = 0, c3 = 0, j = lo;
+        for (; j + 4 <= hi; j += 4) {                        // independent loads: long tie blocks stay latency-tolerant
+            const long long k0 = skey[j], k1 = skey[j + 1], k2 = skey[j + 2], k3 = skey[j + 3];
+            c += (k0 <= ki) ? 1 : 0; c1 += (k1 <= ki) ? 1 : 0; c2 += (k2 <= ki) ? 1 : 0; c3 += (k3 <= ki) ? 1 : 0;
+        }
+        for (; j < hi; ++j) c += (skey[j] <= ki) ? 1 : 0;
+        c += c1 + c2 + c3;
+    }
     cnt[i] = c;
     const int n = offs[BH_NB];
     tsorted[c - 1] = pi / ((double)c / (double)n);          // statsmodels: p_sorted / (rank / n)

@@ -136,8 +136,9 @@ def main():
         res = {"tail": tail, "ovf_count": ovf_count, "a": a_var, "b": b_var, "fim": fim_inv, "ll": ll, "niter": niter, "flags": flags}
         if not ref:
             ref = {kk: v.clone() for kk, v in res.items()}
-            out.append("mean niter %.3f conv %.4f packed genes %d" % (niter.double().mean().item(), (flags & 1).double().mean().item(),
-                                                                       int((packed[:, 0] > 0).sum().item())))
+            out.append("mean niter %.3f max %d conv %.4f packed genes %d max ovf %d" % (
+                niter.double().mean().item(), int(niter.max().item()), (flags & 1).double().mean().item(),
+                int((packed[:, 0] > 0).sum().item()), int(ovf_count.max().item())))
         else:
             ok_int = all(torch.equal(ref[kk], res[kk]) for kk in ("tail", "ovf_count"))
             out.append("suffstats_equal=%s" % ok_int)
