@@ -138,9 +138,11 @@ def main_reference(args):
 class ClockSampler(threading.Thread):
     """Polls NVML for SM clock and throttle reasons while the timed region runs."""
 
-    def __init__(self, index):
+    def __init__(self, index, active=True):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.active = active        # only the rank that prints the line polls: concurrent NVML queries of 8 processes
+        #                             serialise in the driver and stall the other ranks' launches
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -151,7 +153,7 @@ class ClockSampler(threading.Thread):
             self.nv = None
 
     def run(self):
-        if self.nv is None:
+        if self.nv is None or not self.active:
             return
         nv = self.nv
         names = {
@@ -269,11 +271,27 @@ def main_cuda(args):
     niter, flags = torch.empty(g, dtype=torch.int32, device=dev), torch.empty(g, dtype=torch.int32, device=dev)
     rows_out = torch.empty((4, g), **f64)          # theta, sd, pval, log pval
     pv_all = torch.empty(world * g, **f64) if world > 1 else None
+    exchange, gather_kind = None, "none"
+    if world > 1:
+        gather_kind = "nccl"
+        if os.environ.get("DXB200_GATHER", "peer") == "peer":
+            try:          # the product's own gather over NVLink peer memory; NCCL when CUDA IPC is not available
+                from diffxpy_b200.dist import PeerExchange
+                exchange = PeerExchange(g)
+                gather_kind = "peer"
+            except Exception as exc:          # noqa: BLE001
+                if rank == 0:
+                    print("bench: peer exchange unavailable (%s), using NCCL" % exc, file=sys.stderr)
+                exchange = None
+        ok = torch.tensor([1 if exchange is not None else 0], device=dev)
+        td.all_reduce(ok, op=td.ReduceOp.MIN)          # all ranks take the same path
+        if int(ok.item()) == 0:
+            exchange, gather_kind = None, "nccl"
     ev = lambda: torch.cuda.Event(enable_timing=True)
     kern_events = []
 
     def step(record=False):
-        e = [ev() for _ in range(5)] if record else None
+        e = [ev() for _ in range(7)] if record else None
         if record:
             e[0].record()
         _lib.call("dx_group_suffstats_ex", g, ptr(shard.indptr), ptr(shard.rows), ptr(shard.vals), ptr(cell_group), k,
@@ -297,9 +315,17 @@ def main_cuda(args):
             kern_events.append(e)
         pv = rows_out[2]
         if world > 1:      # the one collective of the path: the per-gene p-values of every rank (q-values couple all genes)
-            td.all_gather_into_tensor(pv_all, pv)
+            if exchange is not None:
+                exchange.allgather(pv, pv_all)
+            else:
+                td.all_gather_into_tensor(pv_all, pv)
             pv = pv_all
-        return bh_device(pv)
+        if record:
+            e[5].record()
+        q = bh_device(pv)
+        if record:
+            e[6].record()
+        return q
 
     def barrier():
         if world > 1:
@@ -309,7 +335,7 @@ def main_cuda(args):
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, active=(rank == 0))
     sampler.start()
     t_start, t_stop = ev(), ev()
     t_start.record()
@@ -328,6 +354,8 @@ def main_cuda(args):
     pack_ms = float(np.mean([e[1].elapsed_time(e[4]) for e in kern_events]))
     fit_ms = float(np.mean([e[4].elapsed_time(e[2]) for e in kern_events]))
     wald_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in kern_events]))
+    gather_ms = float(np.mean([e[3].elapsed_time(e[5]) for e in kern_events]))       # includes waiting for the slowest rank
+    bh_ms = float(np.mean([e[5].elapsed_time(e[6]) for e in kern_events]))
     value = world * g * args.steps / (elapsed_ms * 1e-3)
 
     # ---- e2e: C-ABI host entry point from pinned host buffers (H2D + compute + D2H per step) -------------
@@ -376,7 +404,13 @@ def main_cuda(args):
     kern = {"dx_ingest_tma_kernel": {"ms": ingest_ms, "algorithmic_bytes": ingest_bytes},
             "dx_pack_overflow_kernel": {"ms": pack_ms},
             "dx_fit_grouped_kernel": {"ms": fit_ms, "algorithmic_bytes": fit_bytes},
-            "dx_wald_from_fit_kernel": {"ms": wald_ms}}
+            "dx_wald_from_fit_kernel": {"ms": wald_ms},
+            "dx_bh_kernels": {"ms": bh_ms}}
+    if world > 1:
+        kern["all_gather_pvalues"] = {"ms": gather_ms, "kind": gather_kind,
+                                      "note": "rank 0's view; includes waiting for the slowest rank"}
+        if exchange is not None:
+            exchange.check()
     # the roofline object describes the kernel of the step that streams HBM (K_ingest reads the whole shard once);
     # K_fit / Wald / BH work on 4 KB of statistics per gene and are bounded by fp64 issue, not by HBM
     dom = "dx_ingest_tma_kernel"       # K <= 32 groups and a 16-byte aligned shard: the TMA variant of K_ingest runs
@@ -408,7 +442,7 @@ def main_cuda(args):
     from diffxpy_b200.testing import correction as _corr
     # own kernels per step: ingest, pack, fit, wald + BH (bucket histogram, bucket scan, place, rank, chunk-min, suffix,
     # gather; the same kernels for the gathered vector of several GPUs)
-    launches_per_step = 4 + (7 if world * g <= _corr.BH_KERNEL_MAX else 2)
+    launches_per_step = 4 + (7 if world * g <= _corr.BH_KERNEL_MAX else 2) + (1 if gather_kind == "peer" else 0)
     if rank == 0:
         conv = float((flags & 1).to(torch.float64).mean().item())
         line = {
@@ -431,6 +465,8 @@ def main_cuda(args):
         }
         print(json.dumps(line))
     if world > 1:
+        if exchange is not None:
+            exchange.close()
         td.destroy_process_group()
     return 0
 

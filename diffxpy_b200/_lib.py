@@ -18,6 +18,7 @@ DX_MAX_COEF = 32
 DX_SHARD_INTEGER_COUNTS = 1
 DX_GROUPS_FIT_U16 = 2
 DX_OPT_SCALE_CONST = 1
+DX_IPC_HANDLE_BYTES = 64
 DX_INIT_GIVEN, DX_INIT_STANDARD, DX_INIT_CLOSED_FORM, DX_INIT_ALL_ZERO = 0, 1, 2, 3
 
 FLAG_CONVERGED, FLAG_SINGULAR_FIM, FLAG_SCALE_FROZEN, FLAG_NONFINITE, FLAG_ALL_ZERO, FLAG_RANK_OVERFLOW = 1, 2, 4, 8, 16, 32
@@ -66,6 +67,12 @@ SIGNATURES = {
     "dx_two_group_tests": [_I64, _F64, _F64, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P],
     "dx_group_pair_tests": [_I64, _I32, _I32, _I32, _F64, _F64, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P],
     "dx_group_pair_tests_big": [_I64, _I32, _I32, _I32, _F64, _F64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P],
+    "dx_exchange_create": [_I64, C.POINTER(C.c_void_p), _P],
+    "dx_exchange_open": [_P, C.POINTER(C.c_void_p)],
+    "dx_exchange_close": [_P],
+    "dx_exchange_destroy": [_P],
+    "dx_exchange_status": [_P, C.POINTER(C.c_int32)],
+    "dx_peer_allgather_f64": [_I64, _P, _P, _I32, _I32, _I64, C.c_uint32, _P, _P],
     "dx_wald_grouped_host": [_I64, _I64, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, C.POINTER(DxFitOpts),
                              _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
 }

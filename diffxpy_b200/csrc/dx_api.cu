@@ -261,6 +261,62 @@ int dx_group_pair_tests_big(int64_t n_genes, int32_t n_groups, int32_t group_a, 
     return DX_OK;
 }
 
+// ---- exchange buffers in peer memory (multi-GPU gather of result rows) ---------------------------------------------
+int dx_exchange_create(int64_t slot_bytes, void** local_buf, void* ipc_handle_out) {
+    DX_CHECK(slot_bytes > 0 && local_buf && ipc_handle_out, "dx_exchange_create: bad arguments");
+    void* p = nullptr;
+    const size_t total = 512 + 2 * (size_t)slot_bytes;
+    DX_CUDA(cudaMalloc(&p, total), "dx_exchange_create: cudaMalloc");
+    cudaError_t e = cudaMemset(p, 0, total);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); DX_CUDA(e, "dx_exchange_create: IPC handle"); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == DX_IPC_HANDLE_BYTES, "IPC handle size");
+    memcpy(ipc_handle_out, &h, sizeof(h));
+    *local_buf = p;
+    return DX_OK;
+}
+
+int dx_exchange_open(const void* ipc_handle, void** peer_buf) {
+    DX_CHECK(ipc_handle && peer_buf, "dx_exchange_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof(h));
+    DX_CUDA(cudaIpcOpenMemHandle(peer_buf, h, cudaIpcMemLazyEnablePeerAccess), "dx_exchange_open");
+    return DX_OK;
+}
+
+int dx_exchange_close(void* peer_buf) {
+    DX_CHECK(peer_buf, "dx_exchange_close: null pointer");
+    DX_CUDA(cudaIpcCloseMemHandle(peer_buf), "dx_exchange_close");
+    return DX_OK;
+}
+
+int dx_exchange_destroy(void* local_buf) {
+    DX_CHECK(local_buf, "dx_exchange_destroy: null pointer");
+    DX_CUDA(cudaFree(local_buf), "dx_exchange_destroy");
+    return DX_OK;
+}
+
+int dx_exchange_status(const void* local_buf, int32_t* failed_rank_plus_one) {
+    DX_CHECK(local_buf && failed_rank_plus_one, "dx_exchange_status: bad arguments");
+    uint32_t w = 0;
+    DX_CUDA(cudaMemcpy(&w, static_cast<const unsigned char*>(local_buf) + 256, 4, cudaMemcpyDeviceToHost), "dx_exchange_status");
+    *failed_rank_plus_one = (int32_t)w;
+    return DX_OK;
+}
+
+int dx_peer_allgather_f64(int64_t n, const double* src, void* const* peer_bufs, int32_t world, int32_t rank,
+                          int64_t slot_bytes, uint32_t seq, double* dst, void* stream) {
+    DX_CHECK(n >= 0 && (src || n == 0) && peer_bufs, "dx_peer_allgather_f64: bad arguments");
+    DX_CHECK(world >= 1 && world <= 16 && rank >= 0 && rank < world, "dx_peer_allgather_f64: world must be 1..16, rank inside it");
+    DX_CHECK((int64_t)world * n * 8 <= slot_bytes, "dx_peer_allgather_f64: slot too small for world * n doubles");
+    DX_CHECK(seq != 0, "dx_peer_allgather_f64: sequence numbers start at 1");
+    DX_CUDA(dx_launch_peer_allgather(n, src, peer_bufs, world, rank, slot_bytes, seq, dst, sm_count_cached(), (cudaStream_t)stream),
+            "dx_peer_allgather_f64");
+    return DX_OK;
+}
+
 // ---- host-buffer entry point ------------------------------------------------------------------------
 // The host shard is cut into chunks of genes with about equal non-zero counts; chunk c+1 crosses PCIe on the copy
 // stream while chunk c is ingested, fitted and tested on the compute stream, so the call costs about one

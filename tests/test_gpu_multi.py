@@ -217,4 +217,5 @@ def test_gene_sharded_estimator_over_nccl_matches_single_process():
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                           "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.join(root, "tools", "dist_check.py")],
                          capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0 and "dist_check OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.returncode == 0 and "dist_check OK" in out.stdout and "peer exchange OK" in out.stdout, \
+        out.stdout[-2000:] + out.stderr[-2000:]

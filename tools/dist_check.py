@@ -64,6 +64,24 @@ def main():
         np.testing.assert_array_equal(single.niter, out["dense"][1])
         print("dist_check OK: world %d, gene ranges cover %d genes, sharded == single-process (bit-identical), "
               "lrt median p %.3f" % (world, g, float(np.nanmedian(lrt.pval))))
+    # the gather over NVLink peer memory against NCCL: several rounds (both slots, growing sequence numbers), ragged tail
+    from diffxpy_b200.dist import PeerExchange
+    px = PeerExchange(5000)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(100 + rank)
+    for it, n_rows in enumerate((5000, 5000, 1, 4097, 0, 256, 5000)):
+        src = torch.rand(n_rows, dtype=torch.float64, device="cuda", generator=gen) + it
+        got = torch.full((world * n_rows,), -1.0, dtype=torch.float64, device="cuda")
+        want = torch.empty(world * n_rows, dtype=torch.float64, device="cuda")
+        px.allgather(src, got)
+        if n_rows:
+            td.all_gather_into_tensor(want, src)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), "peer all-gather differs from NCCL in round %d" % it
+    px.check()
+    px.close()
+    if rank == 0:
+        print("peer exchange OK: 7 rounds identical to NCCL all_gather")
     td.barrier()
     td.destroy_process_group()
 
