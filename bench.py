@@ -8,7 +8,7 @@ bench.py -- headline benchmark of the NB-GLM Wald path (BASELINE.json: "genes/se
 
 One "step" = one full ``de.test.wald`` pass over one shard of synthetic counts that is already resident in HBM
 as a gene-major CSC shard: K_ingest (the only kernel that streams the count matrix) -> K_fit (complete batchglm
-training schedule per gene) -> Wald statistics -> (N > 1: NCCL all-gather of the per-gene rows) -> BH q-values.
+training schedule per gene) -> Wald statistics -> (N > 1: all-gather of the per-gene p-values over NVLink peer memory) -> BH q-values.
 Workload = BASELINE.json configs[1]: 100 000 cells x 20 000 genes PER GPU (weak scaling: genes are independent,
 every rank owns its own 20k-gene shard; no collective on the data path), sparse, '~ 1 + condition + batch'
 (2 x 8 -> 16 design groups, 9 location coefficients), constant dispersion model, no size factors.
@@ -332,15 +332,43 @@ def main_cuda(args):
             td.barrier()
         torch.cuda.synchronize()
 
+    # One CUDA graph per step: the 11-12 launches of a step cost the host 0.1-0.3 ms of Python / driver time, which on an
+    # 8-GPU box (8 interpreters sharing the host) shows up as idle gaps on the slowest rank (1.32 -> see profiles/).  Used
+    # for N > 1 only: at N = 1 the host keeps up, and plain launches let the per-kernel CUDA events sit inside the timed
+    # region.  DXB200_BENCH_GRAPH=0 / 1 forces plain launches / the graph.
+    graph, launch_kind = None, "eager"
+    step()
+    barrier()
+    want_graph = os.environ.get("DXB200_BENCH_GRAPH", "1" if world > 1 else "0") == "1"
+    if want_graph:
+        try:
+            cap_stream = torch.cuda.Stream()
+            cap_stream.wait_stream(torch.cuda.current_stream())
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=cap_stream, capture_error_mode="thread_local"):
+                q = step()
+            launch_kind = "cuda graph replay (one graph per step)"
+        except Exception as exc:          # noqa: BLE001
+            graph = None
+            if rank == 0:
+                print("bench: graph capture failed (%s), timing plain launches" % str(exc).splitlines()[0], file=sys.stderr)
+        if world > 1:
+            ok = torch.tensor([1 if graph is not None else 0], device=dev)
+            td.all_reduce(ok, op=td.ReduceOp.MIN)          # all ranks launch the same way
+            if int(ok.item()) == 0:
+                graph, launch_kind = None, "eager"
+    run_step = (lambda: graph.replay()) if graph is not None else (lambda: step(record=False))
+    timed_step = (lambda: graph.replay()) if graph is not None else (lambda: step(record=True))
+
     for _ in range(args.warmup):
-        step()
+        run_step()
     barrier()
     sampler = ClockSampler(local_rank, active=(rank == 0))
     sampler.start()
     t_start, t_stop = ev(), ev()
     t_start.record()
     for _ in range(args.steps):
-        q = step(record=True)
+        timed_step()
     t_stop.record()
     barrier()
     elapsed_ms = t_start.elapsed_time(t_stop)
@@ -350,6 +378,11 @@ def main_cuda(args):
     if world > 1:
         td.all_reduce(t, op=td.ReduceOp.MAX)
     elapsed_ms = float(t.item())
+    if graph is not None:
+        # per-kernel times: events cannot sit inside a replayed graph, so a few more steps with plain launches follow
+        for _ in range(min(args.steps, 5)):
+            q = step(record=True)
+        barrier()
     ingest_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in kern_events]))
     pack_ms = float(np.mean([e[1].elapsed_time(e[4]) for e in kern_events]))
     fit_ms = float(np.mean([e[4].elapsed_time(e[2]) for e in kern_events]))
@@ -357,6 +390,12 @@ def main_cuda(args):
     gather_ms = float(np.mean([e[3].elapsed_time(e[5]) for e in kern_events]))       # includes waiting for the slowest rank
     bh_ms = float(np.mean([e[5].elapsed_time(e[6]) for e in kern_events]))
     value = world * g * args.steps / (elapsed_ms * 1e-3)
+    per_rank = None
+    if world > 1:          # every rank's own view of the step (the printed kernel times are rank 0's)
+        mine = {"ingest": round(ingest_ms, 4), "pack": round(pack_ms, 4), "fit": round(fit_ms, 4), "wald": round(wald_ms, 4),
+                "gather_incl_wait": round(gather_ms, 4), "bh": round(bh_ms, 4)}
+        per_rank = [None] * world
+        td.all_gather_object(per_rank, mine)
 
     # ---- e2e: C-ABI host entry point from pinned host buffers (H2D + compute + D2H per step) -------------
     pin = lambda tns: tns.cpu().pin_memory()
@@ -409,6 +448,7 @@ def main_cuda(args):
     if world > 1:
         kern["all_gather_pvalues"] = {"ms": gather_ms, "kind": gather_kind,
                                       "note": "rank 0's view; includes waiting for the slowest rank"}
+        kern["per_rank_ms"] = per_rank
         if exchange is not None:
             exchange.check()
     # the roofline object describes the kernel of the step that streams HBM (K_ingest reads the whole shard once);
@@ -453,7 +493,7 @@ def main_cuda(args):
                        "density": nnz / (n_cells * g), "design_groups": k, "p_loc": p, "p_scale": ps,
                        "l2": "inputs (%.2f GB per pass) larger than L2; no explicit flush" % (8 * nnz / 1e9),
                        "frac_converged": conv, "mean_niter": mean_iter, "max_niter": int(niter.max().item()),
-                       "equivalent_iter_stream_gbs": equiv_gbs},
+                       "equivalent_iter_stream_gbs": equiv_gbs, "launch": launch_kind, "gather": gather_kind},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "genes/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "api": "dx_wald_grouped_host (C ABI, pinned host CSC in, per-gene rows out)",

@@ -72,7 +72,7 @@ SIGNATURES = {
     "dx_exchange_close": [_P],
     "dx_exchange_destroy": [_P],
     "dx_exchange_status": [_P, C.POINTER(C.c_int32)],
-    "dx_peer_allgather_f64": [_I64, _P, _P, _I32, _I32, _I64, C.c_uint32, _P, _P],
+    "dx_peer_allgather_f64": [_I64, _P, _P, _I32, _I32, _I64, _P, _P],
     "dx_wald_grouped_host": [_I64, _I64, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, C.POINTER(DxFitOpts),
                              _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
 }

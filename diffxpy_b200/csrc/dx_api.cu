@@ -307,12 +307,11 @@ int dx_exchange_status(const void* local_buf, int32_t* failed_rank_plus_one) {
 }
 
 int dx_peer_allgather_f64(int64_t n, const double* src, void* const* peer_bufs, int32_t world, int32_t rank,
-                          int64_t slot_bytes, uint32_t seq, double* dst, void* stream) {
+                          int64_t slot_bytes, double* dst, void* stream) {
     DX_CHECK(n >= 0 && (src || n == 0) && peer_bufs, "dx_peer_allgather_f64: bad arguments");
     DX_CHECK(world >= 1 && world <= 16 && rank >= 0 && rank < world, "dx_peer_allgather_f64: world must be 1..16, rank inside it");
     DX_CHECK((int64_t)world * n * 8 <= slot_bytes, "dx_peer_allgather_f64: slot too small for world * n doubles");
-    DX_CHECK(seq != 0, "dx_peer_allgather_f64: sequence numbers start at 1");
-    DX_CUDA(dx_launch_peer_allgather(n, src, peer_bufs, world, rank, slot_bytes, seq, dst, sm_count_cached(), (cudaStream_t)stream),
+    DX_CUDA(dx_launch_peer_allgather(n, src, peer_bufs, world, rank, slot_bytes, dst, sm_count_cached(), (cudaStream_t)stream),
             "dx_peer_allgather_f64");
     return DX_OK;
 }

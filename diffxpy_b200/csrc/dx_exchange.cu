@@ -10,7 +10,8 @@
 // written in exchange s + 1 is never the one a peer still reads in exchange s.
 //
 // Buffer layout (every rank allocates the same):  [0, 256): uint32 flags[64] (flag[r] = last sequence number rank r
-// published here);  [256, 260): error word;  [260, 264): CTA ticket of the local store kernel;  [512, ...): two data
+// published here);  [256, 260): error word;  [260, 264): CTA ticket (stores fenced);  [264, 268): number of finished
+// exchanges;  [268, 272): CTA ticket (leaving);  [512, ...): two data
 // slots of slot_bytes each.  The buffers are cudaMalloc allocations shared through CUDA IPC handles, which the host
 // side exchanges with its own plumbing (torch.distributed all_gather_object in diffxpy_b200/dist.py).
 #include <cuda_runtime.h>
@@ -42,8 +43,12 @@ __device__ __forceinline__ unsigned long long ex_globaltimer() {
 // One launch: store to every peer, publish, wait for every peer, copy the gathered slot out.  The grid never exceeds
 // the SM count, so every CTA is resident while it spins on the flags.
 __global__ void __launch_bounds__(256)
-dx_peer_gather_kernel(int64_t n, const double* __restrict__ src, PeerPtrs peers, int world, int rank, int64_t slot_off,
-                      uint32_t seq, double* __restrict__ dst, unsigned long long timeout_ns) {
+dx_peer_gather_kernel(int64_t n, const double* __restrict__ src, PeerPtrs peers, int world, int rank, int64_t slot_bytes,
+                      double* __restrict__ dst, unsigned long long timeout_ns) {
+    // the sequence number lives in the buffer header (so a captured CUDA graph can be replayed): this exchange is
+    // number `done + 1`; the last CTA to leave the kernel stores it back
+    const uint32_t seq = *reinterpret_cast<volatile uint32_t*>(peers.p[rank] + 264) + 1u;
+    const int64_t slot_off = EX_HEADER + (int64_t)(seq & 1u) * slot_bytes;
     const int64_t stride = (int64_t)gridDim.x * 256;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
         const double v = src[i];
@@ -80,21 +85,28 @@ dx_peer_gather_kernel(int64_t n, const double* __restrict__ src, PeerPtrs peers,
         const int64_t total = (int64_t)world * n;
         for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += stride) dst[i] = __ldcg(slot + i);   // not through L1
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t* leave = reinterpret_cast<uint32_t*>(local + 268);
+        if (atomicAdd(leave, 1u) == gridDim.x - 1) {           // every CTA has read `done`
+            *leave = 0u;
+            *reinterpret_cast<volatile uint32_t*>(local + 264) = seq;
+        }
+    }
 }
 
 }  // namespace
 
 cudaError_t dx_launch_peer_allgather(int64_t n, const double* src, void* const* peer_bufs, int world, int rank,
-                                     int64_t slot_bytes, uint32_t seq, double* dst, int sm_count, cudaStream_t stream) {
+                                     int64_t slot_bytes, double* dst, int sm_count, cudaStream_t stream) {
     if (world < 1 || world > EX_MAX_WORLD || rank < 0 || rank >= world) return cudaErrorInvalidValue;
     if ((int64_t)world * n * 8 > slot_bytes) return cudaErrorInvalidValue;
     PeerPtrs pp;
     for (int r = 0; r < EX_MAX_WORLD; ++r) pp.p[r] = r < world ? static_cast<unsigned char*>(peer_bufs[r]) : nullptr;
-    const int64_t slot_off = EX_HEADER + (int64_t)(seq & 1u) * slot_bytes;
     int64_t grid = (n + 255) / 256;          // an empty shard still publishes its flag
     if (grid < 1) grid = 1;
     if (grid > sm_count) grid = sm_count;
-    dx_peer_gather_kernel<<<(unsigned)grid, 256, 0, stream>>>(n, src, pp, world, rank, slot_off, seq, dst, 5000000000ull);
+    dx_peer_gather_kernel<<<(unsigned)grid, 256, 0, stream>>>(n, src, pp, world, rank, slot_bytes, dst, 5000000000ull);
     cudaError_t e = cudaGetLastError();
     return e;
 }

@@ -54,4 +54,4 @@ cudaError_t dx_launch_bh(int64_t n, const double* pval, double* qval, double* wo
 cudaError_t dx_launch_bh_sorted(int64_t n, const double* p_sorted, const int64_t* order, double* qval, double* work,
                                 cudaStream_t s);
 cudaError_t dx_launch_peer_allgather(int64_t n, const double* src, void* const* peer_bufs, int world, int rank,
-                                     int64_t slot_bytes, uint32_t seq, double* dst, int sm_count, cudaStream_t stream);
+                                     int64_t slot_bytes, double* dst, int sm_count, cudaStream_t stream);

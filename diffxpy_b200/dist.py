@@ -104,7 +104,6 @@ class PeerExchange:
                 _lib.call("dx_exchange_open", handles[r], C.byref(p))
                 ptrs.append(p.value)
         self._ptrs = (C.c_void_p * self.size)(*ptrs)
-        self.seq = 0
         td.barrier()          # every buffer is mapped everywhere before the first store
 
     def allgather(self, src, dst):
@@ -112,9 +111,8 @@ class PeerExchange:
         from .device import ptr, stream_ptr
         n = int(src.shape[0])
         assert dst.shape[0] == self.size * n and src.dtype == torch.float64 and dst.dtype == torch.float64
-        self.seq += 1
         self._lib.call("dx_peer_allgather_f64", n, ptr(src), self._ptrs, self.size, self.rank, self.slot_bytes,
-                       self.seq, ptr(dst), stream_ptr())
+                       ptr(dst), stream_ptr())
         return dst
 
     def check(self):

@@ -153,10 +153,11 @@ int dx_nb_fit_grouped_packed(int64_t n_genes, int32_t n_groups, int32_t p_loc, i
  *   dx_exchange_create  allocates this rank's exchange buffer (512 + 2 * slot_bytes) and returns a CUDA IPC handle
  *                       (DX_IPC_HANDLE_BYTES bytes) that the host side sends to the other ranks with its own plumbing;
  *   dx_exchange_open    maps a peer's buffer;  dx_exchange_close / dx_exchange_destroy undo the two;
- *   dx_peer_allgather_f64  stores src[0..n) into slot (seq & 1) of EVERY rank's buffer at row `rank`, publishes seq in the
- *                       peers' flag rows, waits (on the stream) for the flags of all ranks and copies the world * n
- *                       gathered doubles to dst.  peer_bufs: HOST array of `world` device pointers, own buffer at
- *                       [rank].  Every rank calls it with the same n and seq = 1, 2, 3, ... ; one exchange in flight.
+ *   dx_peer_allgather_f64  stores src[0..n) into the current slot of EVERY rank's buffer at row `rank`, publishes the
+ *                       exchange's sequence number in the peers' flag rows, waits (on the stream) for the flags of all
+ *                       ranks and copies the world * n gathered doubles to dst.  peer_bufs: HOST array of `world`
+ *                       device pointers, own buffer at [rank].  Every rank makes the same sequence of calls with the
+ *                       same n; the sequence number is kept in the buffer, so the call can sit in a replayed CUDA graph.
  *   dx_exchange_status  (synchronous) 0, or 1 + the rank whose flag did not arrive within 5 s. */
 #define DX_IPC_HANDLE_BYTES 64
 int dx_exchange_create(int64_t slot_bytes, void** local_buf, void* ipc_handle_out);
@@ -165,7 +166,7 @@ int dx_exchange_close(void* peer_buf);
 int dx_exchange_destroy(void* local_buf);
 int dx_exchange_status(const void* local_buf, int32_t* failed_rank_plus_one);
 int dx_peer_allgather_f64(int64_t n, const double* src, void* const* peer_bufs, int32_t world, int32_t rank,
-                          int64_t slot_bytes, uint32_t seq, double* dst, void* stream);
+                          int64_t slot_bytes, double* dst, void* stream);
 
 /* ---- K_fit (per cell): same schedule, one CTA per gene, streams all cells every step --------------
  * General path: arbitrary numeric design, per-cell size factors (tests.py:177-191 arguments).

@@ -51,13 +51,14 @@ def main():
     ap.add_argument("--plain", action="store_true", help="use dx_group_suffstats (no gene order / integer flag)")
     ap.add_argument("--scale-batch", action="store_true", help="scale model '~1+batch' (8 dispersion coefficients, configs[2])")
     ap.add_argument("--pack", action="store_true", help="dx_pack_overflow after the ingest + dx_nb_fit_grouped_packed")
+    ap.add_argument("--seed", type=int, default=1000, help="shard seed (bench.py uses 1000 + rank)")
     ap.add_argument("--mu-hi", type=float, default=1.0, help="upper end of the log-uniform gene means (default: the bench workload)")
     ap.add_argument("names", nargs="+")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     bench.MU_HI = a.mu_hi
-    shard, cond, batch = bench.make_shard(torch, dev, seed=1000, n_genes=a.genes, n_cells=a.cells)
+    shard, cond, batch = bench.make_shard(torch, dev, seed=a.seed, n_genes=a.genes, n_cells=a.cells)
     nnz = shard.nnz
     g = a.genes
     xd = bench.design_for(cond, batch)
