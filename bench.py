@@ -138,9 +138,11 @@ def main_reference(args):
 class ClockSampler(threading.Thread):
     """Polls NVML for SM clock and throttle reasons while the timed region runs."""
 
-    def __init__(self, index, active=True):
+    def __init__(self, index, active=True, period_s=0.002):
         super().__init__(daemon=True)
+        self.period_s = period_s
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.armed = False          # samples are kept from the start of the timed region on
         self.active = active        # only the rank that prints the line polls: concurrent NVML queries of 8 processes
         #                             serialise in the driver and stall the other ranks' launches
         try:
@@ -164,7 +166,11 @@ class ClockSampler(threading.Thread):
         }
         while not self.stop_flag:
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                clock = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                if not self.armed:
+                    time.sleep(self.period_s)
+                    continue
+                self.samples.append(clock)
                 try:
                     mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
@@ -174,7 +180,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period_s)
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
@@ -360,13 +366,17 @@ def main_cuda(args):
     run_step = (lambda: graph.replay()) if graph is not None else (lambda: step(record=False))
     timed_step = (lambda: graph.replay()) if graph is not None else (lambda: step(record=True))
 
+    # NVML is initialised and the polling thread started BEFORE the barrier (nvmlInit takes milliseconds: done after it,
+    # rank 0 would enter the timed region late and every other rank would wait for it in the first gather)
+    # (several processes per node: NVML queries take a driver-wide lock that delays the other ranks' launches -> poll less often)
+    sampler = ClockSampler(local_rank, active=(rank == 0), period_s=0.002 if world == 1 else 0.005)
+    sampler.start()
     for _ in range(args.warmup):
         run_step()
     barrier()
-    sampler = ClockSampler(local_rank, active=(rank == 0))
-    sampler.start()
     t_start, t_stop = ev(), ev()
     t_start.record()
+    sampler.armed = True
     for _ in range(args.steps):
         timed_step()
     t_stop.record()
