@@ -828,15 +828,6 @@ dx_fit_grouped_kernel(const FitArgs P) {
     double dinv_f;
     const bool okf = ldl_factor<SW>(smem_d + s.A, p, sl, mask, dinv_f);
     double* Ainv = smem_d + s.Ainv;                         // aliases w1 | w2 | Cj: none of them is needed any more
-#ifdef DX_FIT_OLDINV
-    if (okf) {
-#pragma unroll 1
-        for (int c = 0; c < p; ++c) {
-            const double x = ldl_solve<SW>(smem_d + s.A, p, sl, mask, dinv_f, (sl == c) ? 1.0 : 0.0);
-            if (sl < p) Ainv[c * p + sl] = x;
-        }
-    }
-#else
     {   // inverse: lane c solves (L D L^T) x = e_c serially into its own column (all columns in parallel)
         double* dv = smem_d + s.vec;
         if (sl < p) dv[sl] = dinv_f;
@@ -860,7 +851,6 @@ dx_fit_grouped_kernel(const FitArgs P) {
             }
         }
     }
-#endif
     __syncwarp(mask);
     double* fo = P.fim_inv + g * (int64_t)p * p;
 #pragma unroll 1

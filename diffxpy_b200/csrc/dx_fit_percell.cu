@@ -137,13 +137,6 @@ struct Pass {
                 double x[PMAX];
                 double eta = log_sf ? log_sf[i] : 0.0;
                 {
-#ifdef DX_PC_OLDLOAD
-#pragma unroll
-                    for (int j = 0; j < PMAX; ++j) {
-                        x[j] = (j < p) ? dl[(int64_t)j * N + i] : 0.0;
-                        eta += x[j] * av[j];
-                    }
-#else
                     const double* px = dl + i;           // coefficient-major design: column j of cell i at px + j * N
 #pragma unroll
                     for (int j = 0; j < PMAX; ++j) {
@@ -151,7 +144,6 @@ struct Pass {
                         px += N;
                         eta += x[j] * av[j];
                     }
-#endif
                 }
                 eta = dx_clip(eta, DX_ETA_MIN, DX_ETA_MAX);
                 double z[PSMAX];
