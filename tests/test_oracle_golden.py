@@ -151,3 +151,47 @@ def test_rank_deficient_design_raises():
     bad = np.concatenate([xd, xd[:, [1]]], axis=1)
     with pytest.raises(ValueError):
         onb.fit_nb(y, bad, zd, method_b="newton")
+
+
+def test_oracle_fit_reaches_an_independent_maximum_likelihood_estimate():
+    """The NB-GLM oracle restates batchglm's schedule, which cannot be run here.  What can be pinned
+    independently is WHERE the schedule ends: a generic quasi-Newton maximiser of the NB log-likelihood (scipy, analytic
+    gradient written from the model definition only) must arrive at the same coefficients, dispersion and likelihood, and
+    the reported Fisher inverse must equal (X' W X)^-1 with W = mu r / (r + mu) evaluated there."""
+    import scipy.optimize
+    from scipy.special import gammaln, digamma
+    rng = np.random.default_rng(42)
+    n, g = 600, 8
+    cond = rng.integers(0, 2, n)
+    batch = rng.integers(0, 3, n)
+    xd = np.concatenate([np.ones((n, 1)), cond[:, None], (batch[:, None] == np.arange(1, 3)[None])], axis=1).astype(float)
+    mu_true = np.exp(rng.uniform(np.log(0.3), np.log(40.0), g))[None] * np.exp(0.4 * cond)[:, None] * np.exp(0.2 * batch)[:, None]
+    r_true = rng.uniform(0.7, 5.0, g)
+    y = rng.poisson(rng.gamma(r_true[None], mu_true / r_true[None])).astype(np.float64)
+    fit = onb.fit_nb(y, xd, np.ones((n, 1)), method_b="newton")
+    p = xd.shape[1]
+    for j in range(g):
+        yj = y[:, j]
+
+        def negll(theta):
+            a, b = theta[:p], theta[p]
+            eta = xd @ a
+            mu, r = np.exp(eta), np.exp(b)
+            ll = np.sum(gammaln(yj + r) - gammaln(r) - gammaln(yj + 1.0) + r * (b - np.log(r + mu)) + yj * (eta - np.log(r + mu)))
+            d_eta = yj - (yj + r) * mu / (r + mu)                               # d ll / d eta_i
+            d_b = r * np.sum(digamma(yj + r) - digamma(r) + b - np.log(r + mu) + 1.0 - (yj + r) / (r + mu))
+            return -ll, -np.concatenate([xd.T @ d_eta, [d_b]])
+
+        start = np.concatenate([[np.log(yj.mean() + 1e-3)], np.zeros(p - 1), [0.0]])
+        opt = scipy.optimize.minimize(negll, start, jac=True, method="BFGS", options={"gtol": 1e-7, "maxiter": 2000})
+        ll_opt = -opt.fun
+        a_hat, b_hat = fit["a_var"][:, j], fit["b_var"][0, j]
+        # same maximum: the schedule stops on a relative likelihood change of 1e-10, BFGS on the gradient norm
+        assert abs(fit["log_likelihood"][j] - ll_opt) <= 1e-7 * abs(ll_opt), (j, fit["log_likelihood"][j], ll_opt)
+        mu_hat, r_hat = np.exp(xd @ a_hat), np.exp(b_hat)
+        w = mu_hat * r_hat / (r_hat + mu_hat)
+        cov = np.linalg.inv(xd.T @ (w[:, None] * xd))
+        sd = np.sqrt(np.diag(cov))
+        assert np.all(np.abs(a_hat - opt.x[:p]) <= 2e-3 * sd + 1e-6), (j, a_hat, opt.x[:p])
+        assert abs(b_hat - opt.x[p]) <= 2e-3
+        np.testing.assert_allclose(fit["fisher_inv"][j], cov, rtol=1e-8, atol=1e-12)
