@@ -1,6 +1,9 @@
 """
 CPU oracle for the per-gene negative-binomial GLM fit.  TEST INFRASTRUCTURE ONLY
-(see oracle/__init__.py).  **PARITY UNPINNED** against real batchglm.
+(see oracle/__init__.py).  **PARITY UNPINNED** against real batchglm (not installable offline, and the reference's
+tests hold no fitted number); the END POINT of the schedule is pinned independently: tests/test_oracle_golden.py
+maximises the same likelihood with scipy BFGS and requires likelihood, coefficients, dispersion and Fisher inverse
+to coincide.
 
 What is restated (numpy, float64, dense cells x genes like the reference's numpy backend):
 
