@@ -289,10 +289,6 @@ def main_cuda(args):
                 if rank == 0:
                     print("bench: peer exchange unavailable (%s), using NCCL" % exc, file=sys.stderr)
                 exchange = None
-        ok = torch.tensor([1 if exchange is not None else 0], device=dev)
-        td.all_reduce(ok, op=td.ReduceOp.MIN)          # all ranks take the same path
-        if int(ok.item()) == 0:
-            exchange, gather_kind = None, "nccl"
     ev = lambda: torch.cuda.Event(enable_timing=True)
     kern_events = []
 

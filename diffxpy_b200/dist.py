@@ -89,20 +89,46 @@ class PeerExchange:
             raise ValueError("PeerExchange: at most 16 ranks (one node)")
         self._lib, self._C = _lib, C
         self.slot_bytes = int(self.size * max_rows_per_rank * 8)
-        local = C.c_void_p()
+        # Every rank runs the same sequence of collectives whatever fails locally (a rank that raised early would leave
+        # the others in a collective it never joins): create, exchange handles, map, agree, then raise everywhere.
+        self._local, self._ptrs, err = None, None, None
         handle = C.create_string_buffer(_lib.DX_IPC_HANDLE_BYTES)
-        _lib.call("dx_exchange_create", self.slot_bytes, C.byref(local), handle)
-        self._local = local.value
+        try:
+            local = C.c_void_p()
+            _lib.call("dx_exchange_create", self.slot_bytes, C.byref(local), handle)
+            self._local = local.value
+        except Exception as exc:          # noqa: BLE001
+            err = exc
         handles = [None] * self.size
-        td.all_gather_object(handles, handle.raw)
-        ptrs = []
-        for r in range(self.size):
-            if r == self.rank:
-                ptrs.append(self._local)
-            else:
-                p = C.c_void_p()
-                _lib.call("dx_exchange_open", handles[r], C.byref(p))
-                ptrs.append(p.value)
+        td.all_gather_object(handles, handle.raw if self._local is not None else None)
+        ptrs = [None] * self.size
+        if err is None and all(h is not None for h in handles):
+            try:
+                for r in range(self.size):
+                    if r == self.rank:
+                        ptrs[r] = self._local
+                    else:
+                        p = C.c_void_p()
+                        _lib.call("dx_exchange_open", handles[r], C.byref(p))
+                        ptrs[r] = p.value
+            except Exception as exc:          # noqa: BLE001
+                err = exc
+        elif err is None:
+            err = RuntimeError("a peer could not create its exchange buffer")
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device="cuda")
+        td.all_reduce(ok, op=td.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            for r in range(self.size):      # undo what this rank did map
+                if r != self.rank and ptrs[r] is not None:
+                    try:
+                        _lib.call("dx_exchange_close", ptrs[r])
+                    except Exception:          # noqa: BLE001
+                        pass
+            td.barrier()
+            if self._local is not None:
+                _lib.call("dx_exchange_destroy", self._local)
+                self._local = None
+            raise RuntimeError("PeerExchange: CUDA IPC set-up failed on at least one rank (%s)" % (err or "a peer failed"))
         self._ptrs = (C.c_void_p * self.size)(*ptrs)
         td.barrier()          # every buffer is mapped everywhere before the first store
 
