@@ -7,8 +7,11 @@ bench.py -- headline benchmark of the NB-GLM Wald path (BASELINE.json: "genes/se
     python bench.py --impl reference --steps K --warmup W    # the reference path on the host CPU (oracle port)
 
 One "step" = one full ``de.test.wald`` pass over one shard of synthetic counts that is already resident in HBM
-as a gene-major CSC shard: K_ingest (the only kernel that streams the count matrix) -> K_fit (complete batchglm
-training schedule per gene) -> Wald statistics -> (N > 1: all-gather of the per-gene p-values over NVLink peer memory) -> BH q-values.
+as a gene-major CSC shard: K_ingest (the only kernel that streams the count matrix) -> K_pack (compresses long
+overflow lists; nothing to do on this workload) -> K_fit (complete batchglm training schedule per gene) -> Wald
+statistics -> (N > 1: all-gather of the per-gene p-values over NVLink peer memory) -> BH q-values.  With N > 1 the step
+is replayed as one CUDA graph; at N = 1 it is launched plainly so that the per-kernel CUDA events sit inside the timed
+region.
 Workload = BASELINE.json configs[1]: 100 000 cells x 20 000 genes PER GPU (weak scaling: genes are independent,
 every rank owns its own 20k-gene shard; no collective on the data path), sparse, '~ 1 + condition + batch'
 (2 x 8 -> 16 design groups, 9 location coefficients), constant dispersion model, no size factors.
