@@ -635,12 +635,12 @@ def continuous_1d(data, continuous: str, factor_loc_totest: Union[str, List[str]
                   constraints_scale=None, noise_model: str = 'nb', size_factors=None, batch_size=None, backend: str = "numpy",
                   train_args: dict = {}, training_strategy="AUTO", quick_scale: bool = None, dtype="float64", **kwargs):
     """Differential expression along a continuous covariate, modelled by a spline basis with ``df`` degrees of freedom
-    (tests.py:1971-2370).  ``spline_basis="bs"`` (cubic B-splines, the reference default) is built without patsy
-    (diffxpy_b200.data.splines); the natural / cyclic cubic bases "cr" / "cc" are not available.
+    (tests.py:1971-2370).  ``spline_basis``: "bs" (cubic B-splines, the reference default), "cr" / "cc" (natural / cyclic
+    cubic regression splines, centred), all built without patsy (diffxpy_b200.data.splines).
 
     LRT: the reduced location model is the location formula without the tested factors.  (The reference derives it
     from ``formula_scale`` at tests.py:2311, an evident slip that silently drops every untested location term.)"""
-    from ..data.splines import bs
+    from ..data.splines import bs, crs
     from .det_cont import DifferentialExpressionTestWaldCont, DifferentialExpressionTestLRTCont
     if isinstance(factor_loc_totest, str):
         factor_loc_totest = [factor_loc_totest]
@@ -663,7 +663,8 @@ def continuous_1d(data, continuous: str, factor_loc_totest: Union[str, List[str]
     if spline_basis.lower() == "bs":
         basis = bs(coords, df=df, degree=3, include_intercept=False)
     elif spline_basis.lower() in ("cr", "cc"):
-        raise ValueError("spline basis %s is not available in diffxpy_b200 (only 'bs')" % spline_basis)
+        # patsy cr / cc with constraints='center' (tests.py:2201-2210), restated in data/splines.py
+        basis, _, _ = crs(coords, df=df, cyclic=(spline_basis.lower() == "cc"), center=True)
     else:
         raise ValueError("spline basis %s not recognized" % spline_basis)
     new_coefs = [continuous + str(i) for i in range(basis.shape[1])]

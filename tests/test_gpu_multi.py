@@ -201,8 +201,27 @@ def test_continuous_1d_lrt_and_errors(de):
         de.test.continuous_1d(data=x, continuous="batch", df=4, formula_loc="~ 1 + batch", factor_loc_totest="batch",
                               sample_description=sd, gene_names=names)
     with pytest.raises(ValueError):
-        de.test.continuous_1d(data=x, continuous="pseudotime", df=4, spline_basis="cr", formula_loc="~ 1 + pseudotime",
+        de.test.continuous_1d(data=x, continuous="pseudotime", df=4, spline_basis="xx", formula_loc="~ 1 + pseudotime",
                               factor_loc_totest="pseudotime", sample_description=sd, gene_names=names)
+
+
+@pytest.mark.parametrize("basis", ["cr", "cc"])
+def test_continuous_1d_cubic_regression_splines(de, basis):
+    """Natural / cyclic cubic regression spline bases (tests.py:2201-2210): df centred columns, calibrated under the null,
+    powered on genes that change along the covariate."""
+    x, sd, is_de = _continuous_data(21, n=1500, g=60, de_frac=0.0)
+    names = ["g%d" % i for i in range(x.shape[1])]
+    res = de.test.continuous_1d(data=x, continuous="pseudotime", df=4, spline_basis=basis, formula_loc="~ 1 + pseudotime",
+                                formula_scale="~ 1", factor_loc_totest="pseudotime", test="wald",
+                                sample_description=sd, gene_names=names)
+    assert res._de_test.model_estim.a_var.shape[0] == 5                      # intercept + df spline coefficients
+    assert scipy.stats.kstest(res.pval, "uniform").pvalue > 0.01
+    x, sd, is_de = _continuous_data(22, n=1500, g=60, de_frac=0.5)
+    res = de.test.continuous_1d(data=x, continuous="pseudotime", df=4, spline_basis=basis, formula_loc="~ 1 + pseudotime + batch",
+                                formula_scale="~ 1", factor_loc_totest="pseudotime", test="lrt",
+                                sample_description=sd, gene_names=names)
+    assert np.mean(res.qval[is_de] < 0.05) >= 0.5          # one full sine period: inside both spaces
+    assert np.mean(res.qval[~is_de] < 0.05) <= 0.15
 
 
 def test_gene_sharded_estimator_over_nccl_matches_single_process():

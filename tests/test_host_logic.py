@@ -117,3 +117,64 @@ def test_bs_basis_matches_splev_recipe_and_formula_rewrite():
     assert _replace_continuous("~ 1 + pt + batch + pt:cond", "pt", ["pt0", "pt1"]) == \
         "~ 1 + pt0 + pt1 + batch + pt0:cond + pt1:cond"
     assert _replace_continuous("~ 1", "pt", ["pt0"]) == "~ 1"
+
+
+@pytest.mark.parametrize("cyclic", [False, True])
+def test_cubic_regression_spline_bases_have_the_defining_properties(cyclic):
+    """cr / cc of continuous_1d (reference: patsy cr / cc with constraints='center', tests.py:2201-2210).  patsy cannot be
+    imported here, so the restatement is pinned by what defines the construction: knots at quantiles of the unique sample
+    values, a cardinal basis of C2 piecewise cubics with natural (cr) or periodic (cc) boundary behaviour, and the
+    absorbed centering constraint.  These properties fix the spanned space, hence the fit and every test statistic of a
+    model with an intercept."""
+    from diffxpy_b200.data.splines import crs, crs_knots, crs_free_basis
+    rng = np.random.default_rng(3)
+    x = np.round(rng.uniform(-2.0, 7.0, 400), 2)              # repeated values: knots come from the unique ones
+    df = 5
+    knots = crs_knots(x, df, cyclic=cyclic)
+    ux = np.unique(x)
+    n_inner = df - (1 if cyclic else 2) + 1
+    assert knots.size == n_inner + 2 and knots[0] == ux[0] and knots[-1] == ux[-1]
+    np.testing.assert_allclose(knots[1:-1], np.percentile(ux, np.linspace(0, 100, n_inner + 2)[1:-1]))
+    # cardinal: value 1 at the own knot, 0 at the others
+    at_knots = crs_free_basis(knots[:-1] if cyclic else knots, knots, cyclic)
+    np.testing.assert_allclose(at_knots, np.eye(at_knots.shape[0]), atol=1e-12)
+    # C2 piecewise cubic: third differences of each piece vanish, value / first / second derivative continuous at the knots
+    eps = 1e-4
+    for t in knots[1:-1]:
+        left = crs_free_basis(np.array([t - 2 * eps, t - eps, t]), knots, cyclic)
+        right = crs_free_basis(np.array([t, t + eps, t + 2 * eps]), knots, cyclic)
+        d1l, d1r = (left[2] - left[1]) / eps, (right[1] - right[0]) / eps
+        d2l, d2r = (left[2] - 2 * left[1] + left[0]) / eps ** 2, (right[2] - 2 * right[1] + right[0]) / eps ** 2
+        np.testing.assert_allclose(d1l, d1r, atol=5e-3)
+        np.testing.assert_allclose(d2l, d2r, atol=5e-2)
+    mid = 0.5 * (knots[2] + knots[3])
+    pts = crs_free_basis(mid + eps * np.arange(5), knots, cyclic)
+    np.testing.assert_allclose(np.diff(pts, n=4, axis=0), 0.0, atol=1e-9)      # cubic inside an interval
+    if cyclic:
+        # periodic: value, first and second derivative agree across the seam; points outside are wrapped
+        span = knots[-1] - knots[0]
+        a = crs_free_basis(np.array([knots[0], knots[0] + eps, knots[0] + 2 * eps]), knots, True)
+        b = crs_free_basis(np.array([knots[-1] - 2 * eps, knots[-1] - eps, knots[-1] - 1e-12]), knots, True)
+        np.testing.assert_allclose(a[0], b[2], atol=1e-6)
+        np.testing.assert_allclose((a[1] - a[0]) / eps, (b[2] - b[1]) / eps, atol=5e-3)
+        np.testing.assert_allclose((a[2] - 2 * a[1] + a[0]) / eps ** 2, (b[2] - 2 * b[1] + b[0]) / eps ** 2, atol=5e-2)
+        np.testing.assert_allclose(crs_free_basis(np.array([1.3 + span]), knots, True), crs_free_basis(np.array([1.3]), knots, True), atol=1e-12)
+    else:
+        # natural: second derivative zero at the boundary knots, linear continuation beyond them
+        for t, sgn in ((knots[0], 1.0), (knots[-1], -1.0)):
+            q = crs_free_basis(np.array([t, t + sgn * eps, t + 2 * sgn * eps]), knots, False)
+            np.testing.assert_allclose((q[2] - 2 * q[1] + q[0]) / eps ** 2, 0.0, atol=5e-2)
+        out = crs_free_basis(knots[-1] + np.array([0.5, 1.0, 1.5]), knots, False)
+        np.testing.assert_allclose(np.diff(out, n=2, axis=0), 0.0, atol=1e-10)
+    # centred basis: df columns, zero column means over the sample, full rank together with the intercept,
+    # and the same transform re-applied to new points spans the same functions
+    basis, k2, constraint = crs(x, df, cyclic=cyclic)
+    assert basis.shape == (x.size, df)
+    np.testing.assert_allclose(basis.mean(axis=0), 0.0, atol=1e-12)
+    full = np.hstack([np.ones((x.size, 1)), basis])
+    assert np.linalg.matrix_rank(full) == df + 1
+    free = crs_free_basis(x, knots, cyclic)
+    resid = free - full @ np.linalg.lstsq(full, free, rcond=None)[0]
+    np.testing.assert_allclose(resid, 0.0, atol=1e-9)         # span{1, centred basis} == span{free basis}
+    again, _, _ = crs(x[:50], df, cyclic=cyclic, knots=k2, constraint=constraint)
+    np.testing.assert_allclose(again, basis[:50], atol=1e-12)
