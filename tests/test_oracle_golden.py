@@ -195,3 +195,46 @@ def test_oracle_fit_reaches_an_independent_maximum_likelihood_estimate():
         assert np.all(np.abs(a_hat - opt.x[:p]) <= 2e-3 * sd + 1e-6), (j, a_hat, opt.x[:p])
         assert abs(b_hat - opt.x[p]) <= 2e-3
         np.testing.assert_allclose(fit["fisher_inv"][j], cov, rtol=1e-8, atol=1e-12)
+
+
+def test_oracle_fit_with_size_factors_and_scale_model_reaches_the_independent_mle():
+    """Same independent pin for the general model: per-cell size factors as offsets and a dispersion model with two
+    coefficients ('~ 1 + condition')."""
+    import scipy.optimize
+    from scipy.special import gammaln, digamma
+    rng = np.random.default_rng(7)
+    n, g = 500, 5
+    cond = rng.integers(0, 2, n)
+    xd = np.stack([np.ones(n), cond.astype(float), rng.normal(size=n)], axis=1)
+    zd = np.stack([np.ones(n), cond.astype(float)], axis=1)
+    sf = rng.uniform(0.5, 2.0, n)
+    mu_true = np.exp(rng.uniform(np.log(2.0), np.log(30.0), g))[None] * np.exp(0.5 * cond + 0.2 * xd[:, 2])[:, None] * sf[:, None]
+    r_true = np.exp(rng.uniform(0.0, 1.5, g))[None] * np.exp(0.6 * cond)[:, None]
+    y = rng.poisson(rng.gamma(r_true, mu_true / r_true)).astype(np.float64)
+    fit = onb.fit_nb(y, xd, zd, size_factors=sf, method_b="newton")
+    p, ps = xd.shape[1], zd.shape[1]
+    for j in range(g):
+        yj = y[:, j]
+
+        def negll(theta):
+            a, b = theta[:p], theta[p:]
+            eta = xd @ a + np.log(sf)
+            zeta = zd @ b
+            mu, r = np.exp(eta), np.exp(zeta)
+            ll = np.sum(gammaln(yj + r) - gammaln(r) - gammaln(yj + 1.0) + r * (zeta - np.log(r + mu)) + yj * (eta - np.log(r + mu)))
+            d_eta = yj - (yj + r) * mu / (r + mu)
+            d_zeta = r * (digamma(yj + r) - digamma(r) + zeta - np.log(r + mu) + 1.0 - (yj + r) / (r + mu))
+            return -ll, -np.concatenate([xd.T @ d_eta, zd.T @ d_zeta])
+
+        start = np.concatenate([[np.log(np.mean(yj / sf) + 1e-3)], np.zeros(p - 1), np.zeros(ps)])
+        opt = scipy.optimize.minimize(negll, start, jac=True, method="BFGS", options={"gtol": 1e-7, "maxiter": 3000})
+        ll_opt = -opt.fun
+        assert abs(fit["log_likelihood"][j] - ll_opt) <= 1e-7 * abs(ll_opt), (j, fit["log_likelihood"][j], ll_opt)
+        a_hat, b_hat = fit["a_var"][:, j], fit["b_var"][:, j]
+        mu_hat, r_hat = np.exp(xd @ a_hat + np.log(sf)), np.exp(zd @ b_hat)
+        w = mu_hat * r_hat / (r_hat + mu_hat)
+        cov = np.linalg.inv(xd.T @ (w[:, None] * xd))
+        sd = np.sqrt(np.diag(cov))
+        assert np.all(np.abs(a_hat - opt.x[:p]) <= 3e-3 * sd + 1e-6), (j, a_hat, opt.x[:p])
+        assert np.all(np.abs(b_hat - opt.x[p:]) <= 5e-3), (j, b_hat, opt.x[p:])
+        np.testing.assert_allclose(fit["fisher_inv"][j], cov, rtol=1e-8, atol=1e-12)
