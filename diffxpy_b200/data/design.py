@@ -11,6 +11,8 @@ language is the additive subset the reference's tests use:
 Categorical terms are treatment coded with sorted levels (first level absorbed when an intercept or an earlier
 categorical term spans it), columns are named like patsy: ``Intercept``, ``condition[T.1]``, ``group[a]``.
 """
+import itertools
+
 import numpy as np
 import pandas as pd
 
@@ -106,10 +108,22 @@ def _levels(series):
         return sorted(vals, key=str)
 
 
-def _factor_columns(sample_description, col, as_categorical, full_rank):
+def _resolve_factor(sample_description, term):
+    """'x' -> ('x', False); patsy's categorical marker 'C(x)' -> ('x', True).  Raises for unknown columns."""
+    col, forced = term, False
+    if term.startswith("C(") and term.endswith(")"):
+        col, forced = term[2:-1], True
+    if col not in sample_description.columns:
+        raise ValueError("term %r not found in sample description columns %s" % (term, list(sample_description.columns)))
+    return col, forced
+
+
+def _factor_columns(sample_description, term, as_categorical, full_rank):
     """Columns of one main-effect term -> (matrix n x k, names)."""
+    col, forced = _resolve_factor(sample_description, term)
     s = sample_description[col]
-    if _is_categorical(sample_description, col, as_categorical):
+    if forced or _is_categorical(sample_description, col, as_categorical):
+        col = term                      # patsy names the columns after the term as written: C(x)[T.level]
         levels = _levels(s)
         vals = s.values
         if full_rank:
@@ -153,22 +167,85 @@ def design_matrix(sample_description=None, formula=None, as_categorical=True, dm
             tnames.append("Intercept")
             tslices.append(slice(0, 1))
             pos = 1
-        spanned = intercept   # has the constant vector already been spanned?
+        # patsy's coding rule (patsy/build.py, "redundancy"): a term with categorical factors c1..ck stands for the sum of
+        # the sub-terms over all subsets of them, each factor reduced-rank (treatment) coded; sub-terms that an earlier term
+        # (or the intercept) already covers are dropped, and a remaining pair "S" and "S + f" folds into one sub-term in
+        # which f is full-rank coded.  Numeric factors define separate buckets: 'a:x' is only redundant with terms that
+        # carry the same numeric factors.
+        used = set()
+        if intercept:
+            used.add((frozenset(), frozenset()))
+
+        def _numeric_factors(term):
+            out_ = []
+            for f in [x.strip() for x in term.split(":")]:
+                col_f, forced_f = _resolve_factor(sample_description, f)
+                if not (forced_f or _is_categorical(sample_description, col_f, as_categorical)):
+                    out_.append(f)
+            return frozenset(out_)
+
+        # patsy's column order: terms without numeric factors first, then one group per set of numeric factors in order
+        # of first appearance; inside a group by interaction order, ties in formula order
+        buckets = [frozenset()]
         for t in terms:
-            if ":" in t:
-                f1, f2 = [x.strip() for x in t.split(":")]
-                m1, n1 = _factor_columns(sample_description, f1, as_categorical, full_rank=False)
-                m2, n2 = _factor_columns(sample_description, f2, as_categorical, full_rank=False)
-                mat = np.stack([m1[:, i] * m2[:, j] for i in range(m1.shape[1]) for j in range(m2.shape[1])], axis=1)
-                cn = ["%s:%s" % (a, b) for a in n1 for b in n2]
-            else:
-                if t not in sample_description.columns:
-                    raise ValueError("term %r not found in sample description columns %s"
-                                     % (t, list(sample_description.columns)))
-                cat = _is_categorical(sample_description, t, as_categorical)
-                mat, cn = _factor_columns(sample_description, t, as_categorical, full_rank=cat and not spanned)
-                if cat:
-                    spanned = True
+            b = _numeric_factors(t)
+            if b not in buckets:
+                buckets.append(b)
+        terms = sorted(terms, key=lambda t: (buckets.index(_numeric_factors(t)), t.count(":"), terms.index(t)))
+        for t in terms:
+            factors = [x.strip() for x in t.split(":")]
+            cats, nums = [], []
+            for f in factors:
+                col_f, forced_f = _resolve_factor(sample_description, f)
+                (cats if (forced_f or _is_categorical(sample_description, col_f, as_categorical)) else nums).append(f)
+            bucket = frozenset(nums)
+            subsets = [frozenset(c for c, keep in zip(cats, bits) if keep)
+                       for bits in itertools.product([False, True], repeat=len(cats))]
+            subsets.sort(key=lambda st: (len(st), [cats.index(c) for c in cats if c in st]))
+            fresh = [st for st in subsets if (st, bucket) not in used]
+            used.update((st, bucket) for st in fresh)
+            subterms = [{c: False for c in cats if c in st} for st in fresh]        # factor -> full-rank coded?
+            merged = True
+            while merged:
+                merged = False
+                for a_i, short in enumerate(subterms):
+                    for b_i in range(a_i + 1, len(subterms)):
+                        long_ = subterms[b_i]
+                        extra = [c for c in long_ if c not in short]
+                        if len(long_) == len(short) + 1 and len(extra) == 1 and not long_[extra[0]] \
+                                and all(long_[c] == short[c] for c in short):
+                            folded = dict(short)
+                            folded[extra[0]] = True
+                            subterms[b_i] = folded          # (patsy keeps the folded sub-term where the longer one stood)
+                            subterms.pop(a_i)
+                            merged = True
+                            break
+                    if merged:
+                        break
+            num_mat = np.ones((n, 1))
+            for f in nums:
+                num_mat = num_mat * np.asarray(sample_description[_resolve_factor(sample_description, f)[0]].values,
+                                               dtype=np.float64)[:, None]
+            t_blocks, t_names = [], []
+            for st in subterms:
+                mats, nms = [np.ones((n, 1))], [""]
+                for f in factors:                     # factor order of the term; the first factor varies fastest
+                    if f in nums:
+                        continue
+                    if f not in st:
+                        continue
+                    m_f, n_f = _factor_columns(sample_description, f, True, full_rank=st[f])
+                    mats = [np.concatenate([mats[0][:, [a_]] * m_f[:, [b_]] for b_ in range(m_f.shape[1])
+                                            for a_ in range(mats[0].shape[1])], axis=1)]
+                    nms = [(x + ":" if x else "") + y for y in n_f for x in nms]
+                mat_st, names_st = mats[0] * num_mat, nms
+                if nums:
+                    names_st = [(x + ":" if x else "") + ":".join(nums) for x in names_st]
+                if mat_st.shape[1]:
+                    t_blocks.append(mat_st)
+                    t_names.extend(names_st)
+            mat = np.concatenate(t_blocks, axis=1) if t_blocks else np.zeros((n, 0))
+            cn = t_names
             blocks.append(mat)
             names.extend(cn)
             tnames.append(t)

@@ -178,3 +178,43 @@ def test_cubic_regression_spline_bases_have_the_defining_properties(cyclic):
     np.testing.assert_allclose(resid, 0.0, atol=1e-9)         # span{1, centred basis} == span{free basis}
     again, _, _ = crs(x[:50], df, cyclic=cyclic, knots=k2, constraint=constraint)
     np.testing.assert_allclose(again, basis[:50], atol=1e-12)
+
+
+def test_formula_coding_follows_patsy_redundancy_rules():
+    """Interaction terms, 'C(x)' and term order as patsy builds them (the reference hands its formulas to patsy through
+    batchglm's design_matrix, utils.py:127-176).  The expected column names are patsy's documented results for these
+    formulas ("Redundancy and categorical factors" in its formula documentation); every design must have full rank."""
+    rng = np.random.default_rng(0)
+    n = 80
+    sd = pd.DataFrame({"a": rng.choice(["a1", "a2"], n), "b": rng.choice(["b1", "b2"], n), "c": rng.integers(0, 3, n),
+                       "x": rng.normal(size=n), "z": rng.normal(size=n)})
+    cat = [True, True, False, False, False]
+    want = {
+        "~ 1 + a + b": ["Intercept", "a[T.a2]", "b[T.b2]"],
+        "~ 0 + a + b": ["a[a1]", "a[a2]", "b[T.b2]"],
+        "~ 1 + a:b": ["Intercept", "b[T.b2]", "a[T.a2]:b[b1]", "a[T.a2]:b[b2]"],
+        "~ 0 + a:b": ["a[a1]:b[b1]", "a[a2]:b[b1]", "a[a1]:b[b2]", "a[a2]:b[b2]"],
+        "~ 1 + a + a:b": ["Intercept", "a[T.a2]", "a[a1]:b[T.b2]", "a[a2]:b[T.b2]"],
+        "~ 1 + a*b": ["Intercept", "a[T.a2]", "b[T.b2]", "a[T.a2]:b[T.b2]"],
+        "~ 1 + a:b + a": ["Intercept", "a[T.a2]", "a[a1]:b[T.b2]", "a[a2]:b[T.b2]"],          # main effects before interactions
+        "~ 1 + a:x": ["Intercept", "a[a1]:x", "a[a2]:x"],
+        "~ 1 + x + a:x": ["Intercept", "x", "a[T.a2]:x"],
+        "~ 1 + x + a": ["Intercept", "a[T.a2]", "x"],                                          # categorical terms first
+        "~ 1 + x + a + a:x + z": ["Intercept", "a[T.a2]", "x", "a[T.a2]:x", "z"],
+        "~ 1 + C(c)": ["Intercept", "C(c)[T.1]", "C(c)[T.2]"],
+        "~ 1 + c": ["Intercept", "c"],
+    }
+    for formula, names in want.items():
+        dm = design.design_matrix(sd, formula, as_categorical=cat)
+        assert list(dm.design_info.column_names) == names, formula
+        arr = np.asarray(dm)
+        assert np.linalg.matrix_rank(arr) == arr.shape[1], formula
+        sl = dm.design_info.term_name_slices
+        assert sum(s.stop - s.start for s in sl.values()) == arr.shape[1]
+    # the interaction columns are products of the factor codings
+    dm = design.design_matrix(sd, "~ 1 + a + a:b", as_categorical=cat)
+    arr = np.asarray(dm)
+    np.testing.assert_array_equal(arr[:, 2], ((sd["a"] == "a1") & (sd["b"] == "b2")).values.astype(float))
+    np.testing.assert_array_equal(arr[:, 3], ((sd["a"] == "a2") & (sd["b"] == "b2")).values.astype(float))
+    dm = design.design_matrix(sd, "~ 1 + a:x", as_categorical=cat)
+    np.testing.assert_allclose(np.asarray(dm)[:, 1], (sd["a"] == "a1").values * sd["x"].values)
