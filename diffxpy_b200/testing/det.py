@@ -247,6 +247,33 @@ class DifferentialExpressionTestLRT(_DifferentialExpressionTestSingle):
             return dists[1, 0]
         return self._log_fold_change(factors=factors, base=base)
 
+    def _per_category(self, dmat, coefficients, inverse_link):
+        """Fitted parameter for every distinct combination of the factors of the full location model (det.py:606-648)."""
+        di = self.full_design_loc_info
+        factors = []
+        for t in di.term_names:
+            for f in t.split(":"):
+                f = f[2:-1] if f.startswith("C(") and f.endswith(")") else f
+                if f in self.sample_description.columns and f not in factors:
+                    factors.append(f)
+        sample_description = self.sample_description[factors]
+        dmat, sample_description = dmat_unique(np.array(dmat), sample_description)
+        retval = pd.DataFrame(inverse_link(np.matmul(dmat, coefficients)), columns=self.full_estim.input_data.features)
+        for col in sample_description:
+            retval[col] = sample_description[col].values
+        return retval.set_index(list(sample_description.columns))
+
+    def locations(self):
+        """det.py:606-626: pandas.DataFrame of the fitted means for the different categories of the factors."""
+        return self._per_category(self.full_estim.input_data.design_loc, self.full_estim.model.a,
+                                  self.full_estim.model.inverse_link_loc)
+
+    def scales(self):
+        """det.py:628-648: the same for the dispersion model.  (The reference's body cannot run -- ``dmat.doc``,
+        ``par_link_scale`` -- this is what it evidently means.)"""
+        return self._per_category(self.full_estim.input_data.design_scale, self.full_estim.model.b,
+                                  self.full_estim.model.inverse_link_scale)
+
     def summary(self, qval_thres=None, fc_upper_thres=None, fc_lower_thres=None, mean_thres=None, **kwargs) -> pd.DataFrame:
         """det.py:650-679"""
         res = super().summary(**kwargs)
@@ -450,3 +477,12 @@ class DifferentialExpressionTestRank(_DifferentialExpressionTestTwoGroup):
         if base == np.e:
             return self._logfc
         return self._logfc / np.log(base)
+
+
+def __getattr__(name):
+    """The reference defines the multi-test classes in det.py (det.py:1819-2084); here they live next to the pairwise
+    classes in det_pair.py and are resolved lazily to keep the two modules free of a circular import."""
+    if name in ("_DifferentialExpressionTestMulti", "DifferentialExpressionTestVsRest", "DifferentialExpressionTestByPartition"):
+        from . import det_pair
+        return getattr(det_pair, name)
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))

@@ -215,6 +215,7 @@ class DifferentialExpressionTestZTest(_DifferentialExpressionTestPairwiseBase):
 
 
 DifferentialExpressionTestZTestLazy = DifferentialExpressionTestZTest
+_DifferentialExpressionTestPairwiseLazyBase = _DifferentialExpressionTestPairwiseBase
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -218,3 +218,28 @@ def test_formula_coding_follows_patsy_redundancy_rules():
     np.testing.assert_array_equal(arr[:, 3], ((sd["a"] == "a2") & (sd["b"] == "b2")).values.astype(float))
     dm = design.design_matrix(sd, "~ 1 + a:x", as_categorical=cat)
     np.testing.assert_allclose(np.asarray(dm)[:, 1], (sd["a"] == "a1").values * sd["x"].values)
+
+
+def test_lrt_locations_and_scales_tables():
+    """det.py:606-648 on stub estimators (no GPU): fitted mean / dispersion for every distinct factor combination."""
+    from types import SimpleNamespace
+    from diffxpy_b200.testing.det import DifferentialExpressionTestLRT
+    rng = np.random.default_rng(1)
+    sd = pd.DataFrame({"condition": rng.choice(["c0", "c1"], 40), "batch": rng.choice(["b0", "b1", "b2"], 40)})
+    dm = design.design_matrix(sd, "~ 1 + condition + batch")
+    ds = design.design_matrix(sd, "~ 1 + condition")
+    a = rng.normal(size=(dm.shape[1], 3))
+    b = rng.normal(size=(ds.shape[1], 3))
+    model = SimpleNamespace(a=a, b=b, inverse_link_loc=np.exp, inverse_link_scale=np.exp)
+    est = SimpleNamespace(model=model, input_data=SimpleNamespace(design_loc=np.asarray(dm), design_scale=np.asarray(ds),
+                                                                   features=["g0", "g1", "g2"]))
+    red = design.design_matrix(sd, "~ 1 + batch")
+    test = DifferentialExpressionTestLRT(sample_description=sd, full_design_loc_info=dm.design_info, full_estim=est,
+                                         reduced_design_loc_info=red.design_info, reduced_estim=est)
+    loc = test.locations()
+    assert loc.shape == (6, 3) and list(loc.index.names) == ["condition", "batch"] and list(loc.columns) == ["g0", "g1", "g2"]
+    row = np.asarray(dm)[(sd["condition"] == "c1").values & (sd["batch"] == "b2").values][0]
+    np.testing.assert_allclose(loc.loc[("c1", "b2")].values, np.exp(row @ a))
+    sc = test.scales()
+    assert sc.shape == (2, 3)
+    np.testing.assert_allclose(np.sort(sc["g1"].values), np.sort(np.exp(np.array([[1, 0], [1, 1]]) @ b)[:, 1]))
