@@ -7,6 +7,7 @@ from typing import Union
 
 import numpy as np
 import scipy.sparse
+import scipy.stats
 import torch
 
 from .. import _lib
@@ -215,6 +216,8 @@ def group_pair_device(suff, group_a, group_b, n_a, n_b, do_rank=True):
         return dict(out=out.cpu().numpy(), u1x2=u1x2.cpu().numpy(), tie=tie.cpu().numpy(), flags=flags.cpu().numpy())
 
 
-def hypergeom_test(*args, **kwargs):
-    """stats.py:329-355 belongs to gene-set enrichment, which is outside the accelerated hot path."""
-    raise NotImplementedError("hypergeom_test (enrichment) is out of scope of diffxpy_b200")
+def hypergeom_test(intersections: np.ndarray, enquiry: int, references: np.ndarray, background: int) -> np.ndarray:
+    """stats.py:329-355: hypergeometric (gene-set over-representation) test; a handful of scalars per gene set, evaluated
+    on the host with the arithmetic of the reference (1 - cdf(x - 1) of scipy.stats.hypergeom)."""
+    return np.array([1 - scipy.stats.hypergeom(M=background, n=references[i], N=enquiry).cdf(x - 1)
+                     for i, x in enumerate(intersections)])

@@ -243,3 +243,13 @@ def test_lrt_locations_and_scales_tables():
     sc = test.scales()
     assert sc.shape == (2, 3)
     np.testing.assert_allclose(np.sort(sc["g1"].values), np.sort(np.exp(np.array([[1, 0], [1, 1]]) @ b)[:, 1]))
+
+
+def test_hypergeom_test_matches_scipy_survival_function():
+    import scipy.stats
+    from diffxpy_b200.stats.stats import hypergeom_test      # stats.py:329-355
+    inter, refs = np.array([5, 1, 0, 12]), np.array([30, 40, 10, 25])
+    got = hypergeom_test(inter, 20, refs, 1000)
+    want = scipy.stats.hypergeom(M=1000, n=refs, N=20).sf(inter - 1)
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-15)
+    assert got[2] == 1.0
