@@ -101,6 +101,11 @@ def _is_categorical(sample_description, col, as_categorical):
 
 
 def _levels(series):
+    if isinstance(series.dtype, pd.CategoricalDtype):
+        # patsy keeps the order of an existing categorical (the first category is the reference level); levels that do
+        # not occur are left out here (patsy would add all-zero columns, which the rank check of de.test.* rejects)
+        present = set(pd.unique(series.astype(object)))
+        return [lv for lv in series.cat.categories if lv in present]
     vals = pd.unique(series)
     try:
         return sorted(vals)

@@ -253,3 +253,14 @@ def test_hypergeom_test_matches_scipy_survival_function():
     want = scipy.stats.hypergeom(M=1000, n=refs, N=20).sf(inter - 1)
     np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-15)
     assert got[2] == 1.0
+
+
+def test_existing_categorical_columns_keep_their_level_order():
+    sd = pd.DataFrame({"condition": pd.Categorical(["treated", "ctrl", "treated", "ctrl", "other"],
+                                                   categories=["treated", "other", "ctrl", "unused"])})
+    dm = design.design_matrix(sd, "~ 1 + condition")
+    assert list(dm.design_info.column_names) == ["Intercept", "condition[T.other]", "condition[T.ctrl]"]
+    np.testing.assert_array_equal(np.asarray(dm)[:, 2], [0, 1, 0, 1, 0])
+    sd2 = pd.DataFrame({"condition": ["treated", "ctrl", "treated", "ctrl", "other"]})
+    assert list(design.design_matrix(sd2, "~ 1 + condition").design_info.column_names) == \
+        ["Intercept", "condition[T.other]", "condition[T.treated]"]
