@@ -264,3 +264,27 @@ def test_existing_categorical_columns_keep_their_level_order():
     sd2 = pd.DataFrame({"condition": ["treated", "ctrl", "treated", "ctrl", "other"]})
     assert list(design.design_matrix(sd2, "~ 1 + condition").design_info.column_names) == \
         ["Intercept", "condition[T.other]", "condition[T.treated]"]
+
+
+def test_anndata_like_inputs_supply_gene_names_and_sample_description():
+    """unit_test/test_data_types.py:15-124 feed AnnData / AnnData.raw; anndata is not installed here, so the host logic
+    accepts anything that looks like it (X, obs, var_names)."""
+    from types import SimpleNamespace
+    from diffxpy_b200.testing import utils
+    x = np.arange(12.0).reshape(4, 3)
+    adata = SimpleNamespace(X=x, obs=pd.DataFrame({"condition": ["a", "b", "a", "b"]}), var_names=pd.Index(["g1", "g2", "g3"]))
+    assert list(utils.parse_gene_names(adata, None)) == ["g1", "g2", "g3"]
+    assert list(utils.parse_gene_names(x, ["u", "v", "w"])) == ["u", "v", "w"]
+    with pytest.raises(ValueError):
+        utils.parse_gene_names(x, None)
+    sd = utils.parse_sample_description(adata, None)
+    assert list(sd["condition"]) == ["a", "b", "a", "b"]
+    with pytest.raises(ValueError):
+        utils.parse_sample_description(x, None)
+    with pytest.raises(AssertionError):
+        utils.parse_sample_description(x, pd.DataFrame({"condition": ["a", "b"]}))
+    np.testing.assert_array_equal(utils.parse_grouping(adata, None, "condition"), ["a", "b", "a", "b"])
+    sf = utils.parse_size_factors(np.array([1.0, 2.0, 0.5, 1.5]), adata, sd)
+    assert sf.shape[0] == 4
+    with pytest.raises(AssertionError):
+        utils.parse_size_factors(np.array([1.0, 0.0, 0.5, 1.5]), adata, sd)
