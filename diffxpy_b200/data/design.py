@@ -130,14 +130,19 @@ def _factor_columns(sample_description, term, as_categorical, full_rank):
     if forced or _is_categorical(sample_description, col, as_categorical):
         col = term                      # patsy names the columns after the term as written: C(x)[T.level]
         levels = _levels(s)
-        vals = s.values
         if full_rank:
             use = levels
             names = ["%s[%s]" % (col, lv) for lv in use]
         else:
             use = levels[1:]
             names = ["%s[T.%s]" % (col, lv) for lv in use]
-        mat = np.stack([(vals == lv).astype(np.float64) for lv in use], axis=1) if len(use) else np.zeros((len(s), 0))
+        # one pass over the column: level codes, then a one-hot scatter (comparing the column with every level in turn
+        # costs a string comparison pass per level)
+        codes = pd.Categorical(s, categories=levels).codes.astype(np.int64)
+        onehot = np.zeros((len(s), len(levels)), dtype=np.float64)
+        ok = codes >= 0
+        onehot[np.nonzero(ok)[0], codes[ok]] = 1.0
+        mat = onehot if full_rank else onehot[:, 1:]
         return mat, names
     return np.asarray(s.values, dtype=np.float64)[:, None], [col]
 
@@ -240,10 +245,13 @@ def design_matrix(sample_description=None, formula=None, as_categorical=True, dm
                     if f not in st:
                         continue
                     m_f, n_f = _factor_columns(sample_description, f, True, full_rank=st[f])
+                    if nms == [""]:                   # first categorical factor of the sub-term: nothing to multiply yet
+                        mats, nms = [m_f], list(n_f)
+                        continue
                     mats = [np.concatenate([mats[0][:, [a_]] * m_f[:, [b_]] for b_ in range(m_f.shape[1])
                                             for a_ in range(mats[0].shape[1])], axis=1)]
                     nms = [(x + ":" if x else "") + y for y in n_f for x in nms]
-                mat_st, names_st = mats[0] * num_mat, nms
+                mat_st, names_st = (mats[0] * num_mat if nums else mats[0]), nms
                 if nums:
                     names_st = [(x + ":" if x else "") + ":".join(nums) for x in names_st]
                 if mat_st.shape[1]:
