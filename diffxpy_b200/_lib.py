@@ -53,6 +53,11 @@ SIGNATURES = {
     "dx_pack_overflow": [_I64, _I32, _I32, _P, _P, _P, _P, _P, _P],
     "dx_nb_fit_grouped_packed": [_I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P,
                                  C.POINTER(DxFitOpts), _P, _P, _P, _P, _P, _P, _P, _P],
+    "dx_nb_fit_wald_grouped": [_I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P,
+                               C.POINTER(DxFitOpts), _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P,
+                               _P, _I32, _I32, _I64, _I64, _P],
+    "dx_bh_qvalues_exchange": [_I64, _P, _I32, _I64, _P, _P, _P, _P],
+    "dx_host_release": [],
     "dx_nb_fit_percell": [_I64, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, C.POINTER(DxFitOpts),
                           _P, _P, _P, _P, _P, _P, _P, _P],
     "dx_wald_test": [_I64, _P, _P, _P, _P, _P],
@@ -74,7 +79,7 @@ SIGNATURES = {
     "dx_exchange_status": [_P, C.POINTER(C.c_int32)],
     "dx_peer_allgather_f64": [_I64, _P, _P, _I32, _I32, _I64, _P, _P],
     "dx_wald_grouped_host": [_I64, _I64, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, C.POINTER(DxFitOpts),
-                             _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+                             _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
 }
 OTHER_SYMBOLS = ["dx_version", "dx_last_error"]
 

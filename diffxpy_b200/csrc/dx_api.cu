@@ -94,7 +94,7 @@ int dx_nb_fit_grouped(int64_t n_genes, int32_t n_groups, int32_t p_loc, int32_t 
     DX_CHECK(opts->init_b != DX_INIT_CLOSED_FORM, "dx_nb_fit_grouped: closed-form init_b must be resolved by the host");
     DX_CUDA(dx_launch_fit_grouped(n_genes, n_groups, p_loc, p_scale, xu_loc, xu_scale, offset, n_k, pinv_loc, loc_group,
                                   n_loc_groups, hist, ovf_count, indptr, ovf_val, ovf_group, opts, a_var, b_var, fim_inv, ll, jac, niter,
-                                  flags, 0, nullptr, (cudaStream_t)stream), "dx_nb_fit_grouped");
+                                  flags, 0, nullptr, nullptr, (cudaStream_t)stream), "dx_nb_fit_grouped");
     return DX_OK;
 }
 
@@ -129,7 +129,51 @@ int dx_nb_fit_grouped_packed(int64_t n_genes, int32_t n_groups, int32_t p_loc, i
     DX_CHECK(opts->init_b != DX_INIT_CLOSED_FORM, "dx_nb_fit_grouped_packed: closed-form init_b must be resolved by the host");
     DX_CUDA(dx_launch_fit_grouped(n_genes, n_groups, p_loc, p_scale, xu_loc, xu_scale, offset, n_k, pinv_loc, loc_group,
                                   n_loc_groups, hist, ovf_count, indptr, ovf_val, ovf_group, opts, a_var, b_var, fim_inv, ll, jac, niter,
-                                  flags, 0, ovf_packed, (cudaStream_t)stream), "dx_nb_fit_grouped_packed");
+                                  flags, 0, ovf_packed, nullptr, (cudaStream_t)stream), "dx_nb_fit_grouped_packed");
+    return DX_OK;
+}
+
+int dx_nb_fit_wald_grouped(int64_t n_genes, int32_t n_groups, int32_t p_loc, int32_t p_scale,
+                           const double* xu_loc, const double* xu_scale, const double* offset, const double* n_k,
+                           const double* pinv_loc, const int32_t* loc_group, int32_t n_loc_groups,
+                           const uint32_t* hist, const int32_t* ovf_count, const int64_t* indptr,
+                           const float* ovf_val, const uint8_t* ovf_group, const int32_t* ovf_packed,
+                           const dx_fit_opts* opts,
+                           double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
+                           int32_t* niter, int32_t* flags,
+                           int32_t coef, double* theta, double* sd, double* pval, double* log_pval,
+                           void* const* peer_bufs, int32_t world, int32_t rank, int64_t slot_bytes, int64_t gene_offset,
+                           void* stream) {
+    DX_CHECK(n_genes >= 0, "dx_nb_fit_wald_grouped: n_genes < 0");
+    DX_CHECK(n_groups >= 1 && n_groups <= DX_MAX_GROUPS, "dx_nb_fit_wald_grouped: n_groups must be in 1..255");
+    DX_CHECK(p_loc >= 1 && p_loc <= DX_MAX_COEF && p_scale >= 1 && p_scale <= DX_MAX_COEF,
+             "dx_nb_fit_wald_grouped: coefficient counts must be in 1..32");
+    DX_CHECK(!bad_opts(opts), "dx_nb_fit_wald_grouped: bad options");
+    DX_CHECK(xu_loc && xu_scale && n_k && hist && ovf_count && indptr, "dx_nb_fit_wald_grouped: null input pointer");
+    DX_CHECK(a_var && b_var && fim_inv && ll && jac && niter && flags, "dx_nb_fit_wald_grouped: null output pointer");
+    DX_CHECK(opts->init_a != DX_INIT_CLOSED_FORM || (pinv_loc && n_loc_groups >= 1 && n_loc_groups <= n_groups),
+             "dx_nb_fit_wald_grouped: closed-form init needs pinv_loc and 1 <= n_loc_groups <= n_groups");
+    DX_CHECK(opts->init_b != DX_INIT_CLOSED_FORM, "dx_nb_fit_wald_grouped: closed-form init_b must be resolved by the host");
+    DX_CHECK(coef >= 0 && coef < p_loc, "dx_nb_fit_wald_grouped: coefficient index out of range");
+    DX_CHECK(world >= 1 && world <= 16 && rank >= 0 && rank < world, "dx_nb_fit_wald_grouped: world must be 1..16, rank inside it");
+    DX_CHECK(world == 1 || (peer_bufs && gene_offset >= 0 && (gene_offset + n_genes) * 8 <= slot_bytes),
+             "dx_nb_fit_wald_grouped: exchange needs peer_bufs and a slot that holds gene_offset + n_genes doubles");
+    DxFitEpilogueHost epi;
+    epi.wald_coef = coef; epi.theta = theta; epi.sd = sd; epi.pval = pval; epi.logp = log_pval;
+    epi.world = world; epi.rank = rank; epi.gene_offset = gene_offset; epi.slot_bytes = slot_bytes; epi.peer_bufs = peer_bufs;
+    DX_CUDA(dx_launch_fit_grouped(n_genes, n_groups, p_loc, p_scale, xu_loc, xu_scale, offset, n_k, pinv_loc, loc_group,
+                                  n_loc_groups, hist, ovf_count, indptr, ovf_val, ovf_group, opts, a_var, b_var, fim_inv, ll, jac, niter,
+                                  flags, 0, ovf_packed, &epi, (cudaStream_t)stream), "dx_nb_fit_wald_grouped");
+    return DX_OK;
+}
+
+int dx_bh_qvalues_exchange(int64_t n_total, void* local_buf, int32_t world, int64_t slot_bytes, double* pval_all,
+                           double* qval, double* work, void* stream) {
+    DX_CHECK(n_total >= 1 && local_buf && qval && work, "dx_bh_qvalues_exchange: bad arguments");
+    DX_CHECK(world >= 1 && world <= 16, "dx_bh_qvalues_exchange: world must be 1..16");
+    DX_CHECK(n_total * 8 <= slot_bytes, "dx_bh_qvalues_exchange: slot too small for n_total doubles");
+    DX_CUDA(dx_launch_bh_exchange(n_total, local_buf, world, slot_bytes, pval_all, qval, work, (cudaStream_t)stream),
+            "dx_bh_qvalues_exchange");
     return DX_OK;
 }
 
@@ -364,6 +408,25 @@ struct HostPipe {
 HostPipe g_pipe;
 }  // namespace
 
+// frees the device workspace, streams and events the *_host entry points cache between calls
+int dx_host_release(void) {
+    std::lock_guard<std::mutex> lock(g_pipe.mu);
+    if (g_pipe.device >= 0) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(g_pipe.device);
+        for (HostPipe::Buf& b : g_pipe.bufs) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+        for (cudaEvent_t e : g_pipe.ev) cudaEventDestroy(e);
+        g_pipe.ev.clear();
+        if (g_pipe.s_copy) cudaStreamDestroy(g_pipe.s_copy);
+        if (g_pipe.s_comp) cudaStreamDestroy(g_pipe.s_comp);
+        g_pipe.s_copy = g_pipe.s_comp = nullptr;
+        g_pipe.device = -1;
+        cudaSetDevice(cur);
+    }
+    return DX_OK;
+}
+
 int dx_wald_grouped_host(int64_t n_cells, int64_t n_genes, const int64_t* indptr, const int32_t* rows,
                          const float* vals, const uint8_t* cell_group, int32_t n_groups,
                          int32_t p_loc, int32_t p_scale, const double* xu_loc, const double* xu_scale,
@@ -371,7 +434,7 @@ int dx_wald_grouped_host(int64_t n_cells, int64_t n_genes, const int64_t* indptr
                          const int32_t* loc_group, int32_t n_loc_groups,
                          const dx_fit_opts* opts, int32_t coef,
                          double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
-                         int32_t* niter, int32_t* flags, double* pval, double* log_pval, double* sd) {
+                         int32_t* niter, int32_t* flags, double* pval, double* log_pval, double* sd, double* qval) {
     DX_CHECK(n_cells >= 1 && n_genes >= 0 && indptr && cell_group, "dx_wald_grouped_host: bad arguments");
     DX_CHECK(n_groups >= 1 && n_groups <= DX_MAX_GROUPS, "dx_wald_grouped_host: n_groups must be in 1..255");
     DX_CHECK(p_loc >= 1 && p_loc <= DX_MAX_COEF && p_scale >= 1 && p_scale <= DX_MAX_COEF,
@@ -406,7 +469,7 @@ int dx_wald_grouped_host(int64_t n_cells, int64_t n_genes, const int64_t* indptr
     cudaStream_t sc = g_pipe.s_copy, sx = g_pipe.s_comp;
     int rc = DX_OK;
     void *d_indptr, *d_rows, *d_vals, *d_grp, *d_hist, *d_oc, *d_ov, *d_og, *d_xl, *d_xs, *d_off, *d_nk, *d_pinv, *d_lg;
-    void *d_a, *d_b, *d_fi, *d_ll, *d_jac, *d_ni, *d_fl, *d_p, *d_lp, *d_sd, *d_pk;
+    void *d_a, *d_b, *d_fi, *d_ll, *d_jac, *d_ni, *d_fl, *d_p, *d_lp, *d_sd, *d_pk, *d_q, *d_bhw;
 #define HX(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail_cuda(e__, "dx_wald_grouped_host"); goto done; } } while (0)
     {
         int sl = 0;
@@ -422,6 +485,7 @@ int dx_wald_grouped_host(int64_t n_cells, int64_t n_genes, const int64_t* indptr
         HX(g_pipe.ensure(sl++, G * 8, &d_jac)); HX(g_pipe.ensure(sl++, G * 4, &d_ni)); HX(g_pipe.ensure(sl++, G * 4, &d_fl));
         HX(g_pipe.ensure(sl++, G * 8, &d_p)); HX(g_pipe.ensure(sl++, G * 8, &d_lp)); HX(g_pipe.ensure(sl++, G * 8, &d_sd));
         HX(g_pipe.ensure(sl++, G * 8, &d_pk));
+        HX(g_pipe.ensure(sl++, G * 8, &d_q)); HX(g_pipe.ensure(sl++, dx_bh_work_bytes_impl(G) + 16, &d_bhw));
         // small inputs first
         HX(cudaMemcpyAsync(d_indptr, indptr, (G + 1) * 8, cudaMemcpyHostToDevice, sc));
         HX(cudaMemcpyAsync(d_grp, cell_group, n_cells, cudaMemcpyHostToDevice, sc));
@@ -449,6 +513,9 @@ int dx_wald_grouped_host(int64_t n_cells, int64_t n_genes, const int64_t* indptr
                                 (int32_t*)d_oc + g0, (float*)d_ov, (uint8_t*)d_og, nullptr, 0, sm_count_cached(), sx));
             HX(dx_launch_pack_overflow(gc, K, DX_PACK_MIN_ENTRIES, (const int32_t*)d_oc + g0, (const int64_t*)d_indptr + g0,
                                        (float*)d_ov, (uint8_t*)d_og, (int32_t*)d_pk + 2 * g0, sm_count_cached(), sx));
+            DxFitEpilogueHost epi;            // Wald row of the tested coefficient straight from the fit kernel
+            epi.wald_coef = coef; epi.theta = nullptr; epi.sd = (double*)d_sd + g0; epi.pval = (double*)d_p + g0;
+            epi.logp = (double*)d_lp + g0; epi.world = 1; epi.rank = 0; epi.gene_offset = 0; epi.slot_bytes = 0; epi.peer_bufs = nullptr;
             HX(dx_launch_fit_grouped(gc, K, p, ps, (const double*)d_xl, (const double*)d_xs,
                                      offset ? (const double*)d_off : nullptr, (const double*)d_nk,
                                      pinv_loc ? (const double*)d_pinv : nullptr, loc_group ? (const int32_t*)d_lg : nullptr,
@@ -456,9 +523,11 @@ int dx_wald_grouped_host(int64_t n_cells, int64_t n_genes, const int64_t* indptr
                                      (const int32_t*)d_oc + g0, (const int64_t*)d_indptr + g0, (const float*)d_ov,
                                      (const uint8_t*)d_og, opts, (double*)d_a + g0, (double*)d_b + g0,
                                      (double*)d_fi + g0 * (int64_t)p * p, (double*)d_ll + g0, (double*)d_jac + g0,
-                                     (int32_t*)d_ni + g0, (int32_t*)d_fl + g0, G, (const int32_t*)d_pk + 2 * g0, sx));
-            HX(dx_launch_wald_from_fit(gc, p, coef, (const double*)d_a + g0, (const double*)d_fi + g0 * (int64_t)p * p, nullptr,
-                                       (double*)d_sd + g0, (double*)d_p + g0, (double*)d_lp + g0, G, sx));
+                                     (int32_t*)d_ni + g0, (int32_t*)d_fl + g0, G, (const int32_t*)d_pk + 2 * g0, &epi, sx));
+        }
+        if (qval) {      // Benjamini-Hochberg over all genes (correction.py:5-24), part of the Wald result (det.py:108-117)
+            HX(dx_launch_bh(G, (const double*)d_p, (double*)d_q, (double*)d_bhw, sx));
+            HX(cudaMemcpyAsync(qval, d_q, G * 8, cudaMemcpyDeviceToHost, sx));
         }
         HX(cudaMemcpyAsync(a_var, d_a, (size_t)G * p * 8, cudaMemcpyDeviceToHost, sx));
         HX(cudaMemcpyAsync(b_var, d_b, (size_t)G * ps * 8, cudaMemcpyDeviceToHost, sx));

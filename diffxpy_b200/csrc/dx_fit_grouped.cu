@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include "dx_common.cuh"
 #include "dx_internal.h"
+#include "dx_fit_args.cuh"
 
 namespace {
 
@@ -488,23 +489,6 @@ template <int SW> __device__ __noinline__ double scale_newton(Slot& s, double& b
     return f;
 }
 
-struct FitArgs {
-    int64_t n_genes, stride;          // stride: distance (in genes) between coefficient rows of a_var / b_var
-    int K, p, ps, KL;
-    const double *xu_loc, *xu_scale, *offset, *n_k, *pinv_loc;
-    const int32_t* loc_group;
-    const uint32_t* tail_all;
-    const int32_t* ovf_count;
-    const int64_t* indptr;
-    const float* ovf_val;
-    const uint8_t* ovf_group;
-    const int32_t* ovf_packed;        // [n_genes][2] record counts of dx_pack_overflow (0, 0 = plain list); may be null
-    dx_fit_opts opts;
-    double *a_var, *b_var, *fim_inv, *ll_out, *jac_out;
-    int32_t *niter_out, *flags_out;
-    int slot_doubles, table_doubles, nent, nz_max, ainv_extra;
-    unsigned int* queue;              // gene queue of this launch (dx_queue_acquire)
-};
 
 template <int SW>
 __global__ void __launch_bounds__(256)
@@ -866,8 +850,11 @@ dx_fit_grouped_kernel(const FitArgs P) {
         P.niter_out[g] = step;
         P.flags_out[g] = flags;
     }
+    if (P.epi.wald_coef >= 0 && sl == P.epi.wald_coef)
+        dx_fit_epilogue_row(P.epi, g, areg, okf ? Ainv[sl * p + sl] : NAN);
     __syncwarp(mask);
     }
+    dx_fit_epilogue_publish(P.epi);
 }
 
 template <int SW>
@@ -910,8 +897,13 @@ cudaError_t launch_sw(FitArgs& A, int sm_count, cudaStream_t stream) {
     }
     int64_t grid = (A.n_genes + slots_per_cta - 1) / slots_per_cta;        // never more CTAs than gene slots needed
     if (grid > (int64_t)per_sm * sm_count) grid = (int64_t)per_sm * sm_count;
+    if (grid < 1) grid = 1;                // an empty shard still publishes its exchange flag
     e = dx_queue_acquire(stream, &A.queue);
     if (e != cudaSuccess) return e;
+    if (A.epi.world > 1) {
+        e = dx_queue_acquire(stream, &A.epi.done_ctas);
+        if (e != cudaSuccess) return e;
+    }
     dx_fit_grouped_kernel<SW><<<(unsigned)grid, best_w * 32, smem, stream>>>(A);
     return cudaGetLastError();
 }
@@ -925,9 +917,23 @@ cudaError_t dx_launch_fit_grouped(int64_t n_genes, int K, int p, int ps,
                                   const float* ovf_val, const uint8_t* ovf_group, const dx_fit_opts* opts,
                                   double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
                                   int32_t* niter, int32_t* flags, int64_t coef_stride, const int32_t* ovf_packed,
-                                  cudaStream_t stream) {
-    if (n_genes <= 0) return cudaSuccess;
+                                  const DxFitEpilogueHost* epi, cudaStream_t stream) {
     FitArgs A;
+    A.epi.wald_coef = -1;
+    A.epi.theta = A.epi.sd = A.epi.pval = A.epi.logp = nullptr;
+    A.epi.world = 1; A.epi.rank = 0; A.epi.gene_offset = 0; A.epi.slot_bytes = 0; A.epi.done_ctas = nullptr;
+    for (int r = 0; r < DX_EX_MAX_WORLD; ++r) A.epi.peer[r] = nullptr;
+    if (epi) {
+        A.epi.wald_coef = epi->wald_coef;
+        A.epi.theta = epi->theta; A.epi.sd = epi->sd; A.epi.pval = epi->pval; A.epi.logp = epi->logp;
+        if (epi->world > 1) {
+            if (epi->world > DX_EX_MAX_WORLD || epi->rank < 0 || epi->rank >= epi->world || !epi->peer_bufs) return cudaErrorInvalidValue;
+            A.epi.world = epi->world; A.epi.rank = epi->rank;
+            A.epi.gene_offset = epi->gene_offset; A.epi.slot_bytes = epi->slot_bytes;
+            for (int r = 0; r < epi->world; ++r) A.epi.peer[r] = static_cast<unsigned char*>(epi->peer_bufs[r]);
+        }
+    }
+    if (n_genes <= 0 && A.epi.world <= 1) return cudaSuccess;
     A.ovf_packed = ovf_packed;
     A.stride = coef_stride > 0 ? coef_stride : n_genes;
     A.n_genes = n_genes; A.K = K; A.p = p; A.ps = ps; A.KL = n_loc_groups;
@@ -936,6 +942,9 @@ cudaError_t dx_launch_fit_grouped(int64_t n_genes, int K, int p, int ps,
     A.opts = *opts;
     A.a_var = a_var; A.b_var = b_var; A.fim_inv = fim_inv; A.ll_out = ll; A.jac_out = jac; A.niter_out = niter; A.flags_out = flags;
     A.nent = p * (p + 1) / 2;
+    static const char* fast_env = getenv("DXB200_FIT_IMPL");      // tuning hook (development only): "g" forces the general kernel
+    if (!(fast_env && fast_env[0] == 'g') && dx_fit_fast_eligible(K, p, ps, opts) && (reinterpret_cast<uintptr_t>(tail) & 15u) == 0)
+        return dx_launch_fit_fast(A, 0, stream);
     static const char* nz_env = getenv("DXB200_FIT_NZ");         // tuning hook (development only)
     A.nz_max = nz_env ? atoi(nz_env) : 96;   // capacity of the non-zero design-product list (0.9 KB); denser designs use the dense loop
     A.table_doubles = K * p + K * ps + 2 * K + A.nz_max + (2 * ((A.nent + 7) & ~7) + 2 * ((A.nent + 1 + 3) & ~3) + A.nz_max + 7) / 8 + 2;

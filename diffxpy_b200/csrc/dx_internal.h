@@ -15,6 +15,15 @@ cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32
                              cudaStream_t stream);
 cudaError_t dx_launch_gene_moments(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,
                                    const double* inv_sf, double* sum1, double* sum2, cudaStream_t stream);
+// what K_fit does for a gene after finalize (both nullable parts): the single-coefficient Wald row, and on several GPUs
+// the store of the p-value into every rank's exchange buffer (peer_bufs: host array of `world` device pointers)
+struct DxFitEpilogueHost {
+    int wald_coef;                        // < 0: none
+    double *theta, *sd, *pval, *logp;     // device, [n_genes], nullable
+    int world, rank;                      // world <= 1: no exchange
+    int64_t gene_offset, slot_bytes;
+    void* const* peer_bufs;
+};
 cudaError_t dx_launch_fit_grouped(int64_t n_genes, int K, int p, int ps,
                                   const double* xu_loc, const double* xu_scale, const double* offset,
                                   const double* n_k, const double* pinv_loc, const int32_t* loc_group, int n_loc_groups,
@@ -22,7 +31,7 @@ cudaError_t dx_launch_fit_grouped(int64_t n_genes, int K, int p, int ps,
                                   const float* ovf_val, const uint8_t* ovf_group, const dx_fit_opts* opts,
                                   double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
                                   int32_t* niter, int32_t* flags, int64_t coef_stride, const int32_t* ovf_packed,
-                                  cudaStream_t stream);
+                                  const DxFitEpilogueHost* epi, cudaStream_t stream);
 cudaError_t dx_launch_pack_overflow(int64_t n_genes, int K, int min_entries, const int32_t* ovf_count,
                                     const int64_t* indptr, float* ovf_val, uint8_t* ovf_group, int32_t* ovf_packed,
                                     int sm_count, cudaStream_t stream);
@@ -51,6 +60,8 @@ cudaError_t dx_launch_two_group_big(int64_t G, int K, int ga, int gb, double n0,
                                     void* work, int64_t work_bytes, int64_t slice_bytes, int sm_count, cudaStream_t s);
 size_t dx_bh_work_bytes_impl(int64_t n);
 cudaError_t dx_launch_bh(int64_t n, const double* pval, double* qval, double* work, cudaStream_t s);
+cudaError_t dx_launch_bh_exchange(int64_t n_total, void* local_buf, int world, int64_t slot_bytes, double* pval_all,
+                                  double* qval, double* work, cudaStream_t s);
 cudaError_t dx_launch_bh_sorted(int64_t n, const double* p_sorted, const int64_t* order, double* qval, double* work,
                                 cudaStream_t s);
 cudaError_t dx_launch_peer_allgather(int64_t n, const double* src, void* const* peer_bufs, int world, int rank,

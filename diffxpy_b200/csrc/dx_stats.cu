@@ -6,8 +6,10 @@
 //  * /root/reference/diffxpy/testing/det.py:1545-1620 / 1672-1743: per-gene group moments, Welch t and
 //    the Mann-Whitney U test (scipy.stats.mannwhitneyu asymptotic method, tie + continuity corrected)
 //    computed from the 2-group tail counts of K_ingest with exact integer rank sums.
+#include <cstdlib>
 #include "dx_common.cuh"
 #include "dx_internal.h"
+#include "dx_fit_args.cuh"
 
 namespace {
 
@@ -15,9 +17,14 @@ __global__ void dx_wald_kernel(int64_t n, const double* __restrict__ theta, cons
                                double* __restrict__ pval, double* __restrict__ logp) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double s = fmax(sd[i], DX_TINY);      // stats.py:215
+    // stats.py:215 floors sd at the smallest subnormal with np.nextafter(..., where=sd < tiny): a NaN sd (singular Fisher
+    // information) fails that comparison and stays NaN, so the gene gets p = NaN and is left out of the correction.
+    // (fmax would return the non-NaN operand and turn such a gene into p = 0.)
+    const double s0 = sd[i];
+    const double s = (s0 < DX_TINY) ? DX_TINY : s0;
     double p, lp;
     dx_two_sided_normal(theta[i] / s, &p, &lp);
+    if (isnan(s0) || isnan(theta[i])) { p = NAN; lp = NAN; }
     pval[i] = p;
     if (logp) logp[i] = lp;
 }
@@ -32,7 +39,8 @@ __global__ void dx_wald_from_fit_kernel(int64_t G, int64_t stride, int p, int co
     if (v < DX_TINY) v = DX_TINY;                // det.py:796 (NaN stays NaN)
     const double s = sqrt(v);
     double pv, lp;
-    dx_two_sided_normal(t / fmax(s, DX_TINY), &pv, &lp);
+    dx_two_sided_normal(t / ((s < DX_TINY) ? DX_TINY : s), &pv, &lp);
+    if (isnan(s) || isnan(t)) { pv = NAN; lp = NAN; }            // singular Fisher information: no test, not p = 0
     if (theta) theta[g] = t;
     if (sd) sd[g] = s;
     pval[g] = pv;
@@ -768,6 +776,156 @@ dx_bh_gather_kernel(int64_t G, const double* __restrict__ p, const int* __restri
     q[i] = (pi == pi) ? fmin(table[cnt[i] - 1], 1.0) : NAN;
 }
 
+// ---- the whole correction in ONE CTA (n up to BH_FUSED_MAX): bucket histogram and offsets live in shared memory, the
+// bucket-ordered keys / the table sorted by p / the ranks in the (L2-resident) workspace.  Same arithmetic and the same
+// values as the multi-kernel path; replaces 7 launches (~50 us of launch latency for 20k p-values) by one.
+// With an exchange buffer (several GPUs) the kernel first waits for the sequence flag of every rank -- the p-values
+// were stored into the slot by the fit kernels of all ranks (dx_fit_args.cuh) -- and finally marks the exchange done.
+constexpr int BH_FUSED_MAX = 32768;
+constexpr int BH_FT = 1024;
+
+struct BhExchange {
+    unsigned char* local;        // null: p is an ordinary device vector
+    int world;
+    int64_t slot_bytes;
+    double* pval_out;            // nullable: copy of the gathered p-values
+    unsigned long long timeout_ns;
+};
+
+__global__ void __launch_bounds__(BH_FT)
+dx_bh_fused_kernel(int n, const double* __restrict__ p_in, double* __restrict__ q, double* __restrict__ tsorted,
+                   long long* __restrict__ skey, int* __restrict__ cnt, BhExchange X) {
+    extern __shared__ int s_h[];             // [BH_NB + 1]
+    __shared__ int s_w[32];
+    __shared__ double s_m[32];
+    __shared__ int s_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* p = p_in;
+    uint32_t seq = 0;
+    if (X.local) {
+        seq = *reinterpret_cast<volatile uint32_t*>(X.local + 264) + 1u;
+        p = reinterpret_cast<const double*>(X.local + DX_EX_HEADER + (int64_t)(seq & 1u) * X.slot_bytes);
+        if (tid < X.world) {
+            const uint32_t* flag = reinterpret_cast<const uint32_t*>(X.local) + tid;
+            unsigned long long t0;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+            while ((int32_t)(dx_ex_ld_acquire_sys(flag) - seq) < 0) {
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+                if (t1 - t0 > X.timeout_ns) {          // a peer died: report instead of hanging the GPU
+                    atomicExch(reinterpret_cast<uint32_t*>(X.local + 256), 1u + tid);
+                    break;
+                }
+                __nanosleep(100);
+            }
+        }
+    }
+    for (int b = tid; b <= BH_NB; b += BH_FT) s_h[b] = 0;
+    __syncthreads();
+    // pass 1: bucket histogram; the table sorted by p starts at +inf
+    for (int i = tid; i < n; i += BH_FT) {
+        const double pi = __ldcg(p + i);
+        tsorted[i] = INFINITY;
+        if (X.pval_out) X.pval_out[i] = pi;
+        if (pi == pi) atomicAdd(&s_h[dx_bh_bucket(pi)], 1);
+    }
+    __syncthreads();
+    {   // exclusive scan of the bucket counts
+        constexpr int PER = (BH_NB + BH_FT - 1) / BH_FT;
+        const int lo = tid * PER < BH_NB ? tid * PER : BH_NB, hi = (lo + PER < BH_NB) ? lo + PER : BH_NB;
+        int sum = 0;
+        for (int b = lo; b < hi; ++b) sum += s_h[b];
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(DX_FULL_MASK, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        int before = 0;
+        for (int w = 0; w < warp; ++w) before += s_w[w];
+        int run = before + inc - sum;
+        for (int b = lo; b < hi; ++b) { const int c = s_h[b]; s_h[b] = run; run += c; }
+        if (tid == BH_FT - 1) s_total = run;
+    }
+    __syncthreads();
+    const int n_valid = s_total;
+    // pass 2: keys into their buckets; afterwards s_h[b] = end of bucket b (= start of bucket b + 1)
+    for (int i = tid; i < n; i += BH_FT) {
+        const double pi = __ldcg(p + i);
+        if (pi == pi) skey[atomicAdd(&s_h[dx_bh_bucket(pi)], 1)] = dx_p_key(pi);
+    }
+    __syncthreads();
+    // pass 3: c_i = #{p_j <= p_i}, t_i = p_i / (c_i / n) into slot c_i - 1 of the table sorted by p
+    for (int i = tid; i < n; i += BH_FT) {
+        const double pi = __ldcg(p + i);
+        if (pi != pi) { cnt[i] = 0; continue; }
+        const int b = dx_bh_bucket(pi);
+        const long long ki = dx_p_key(pi);
+        const int lo = b > 0 ? s_h[b - 1] : 0, hi = s_h[b];
+        int c = lo;
+        if (pi >= 1.0 || pi == 0.0) {
+            c = hi;                                  // p == 1 or p == 0: the whole bucket is one tie block
+        } else {
+            for (int j = lo; j < hi; ++j) c += (skey[j] <= ki) ? 1 : 0;
+        }
+        cnt[i] = c;
+        tsorted[c - 1] = pi / ((double)c / (double)n_valid);          // statsmodels: p_sorted / (rank / n)
+    }
+    __syncthreads();
+    {   // pass 4: running minimum from the right over the table, in place
+        const int per = (n + BH_FT - 1) / BH_FT;
+        const int lo = tid * per < n ? tid * per : n, hi = (lo + per < n) ? lo + per : n;
+        double m = INFINITY;
+        for (int j = lo; j < hi; ++j) m = fmin(m, tsorted[j]);
+        double sfx = m;                      // suffix minimum over the threads of the warp (this thread included)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_down_sync(DX_FULL_MASK, sfx, o);
+            if (lane + o < 32) sfx = fmin(sfx, t);
+        }
+        if (lane == 0) s_m[warp] = sfx;      // minimum of the whole warp
+        __syncthreads();
+        double later = INFINITY;             // everything to the right of this thread's piece
+        for (int w = warp + 1; w < BH_FT / 32; ++w) later = fmin(later, s_m[w]);
+        const double nxt = __shfl_down_sync(DX_FULL_MASK, sfx, 1);
+        if (lane < 31) later = fmin(later, nxt);
+        double run = later;
+        for (int j = hi - 1; j >= lo; --j) { run = fmin(run, tsorted[j]); tsorted[j] = run; }
+    }
+    __syncthreads();
+    // pass 5: q_i = min(1, table[c_i - 1])
+    for (int i = tid; i < n; i += BH_FT) {
+        const double pi = __ldcg(p + i);
+        q[i] = (pi == pi) ? fmin(tsorted[cnt[i] - 1], 1.0) : NAN;
+    }
+    if (X.local) {
+        __syncthreads();
+        if (tid == 0) *reinterpret_cast<volatile uint32_t*>(X.local + 264) = seq;
+    }
+}
+
+// several GPUs, more p-values than the fused kernel takes: wait for the flags, copy the slot out, mark the exchange done
+__global__ void __launch_bounds__(1024)
+dx_exchange_wait_kernel(int64_t n, BhExchange X) {
+    const int tid = threadIdx.x;
+    const uint32_t seq = *reinterpret_cast<volatile uint32_t*>(X.local + 264) + 1u;
+    const double* p = reinterpret_cast<const double*>(X.local + DX_EX_HEADER + (int64_t)(seq & 1u) * X.slot_bytes);
+    if (tid < X.world) {
+        const uint32_t* flag = reinterpret_cast<const uint32_t*>(X.local) + tid;
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+        while ((int32_t)(dx_ex_ld_acquire_sys(flag) - seq) < 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+            if (t1 - t0 > X.timeout_ns) { atomicExch(reinterpret_cast<uint32_t*>(X.local + 256), 1u + tid); break; }
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+    for (int64_t i = tid; i < n; i += 1024) X.pval_out[i] = __ldcg(p + i);
+    __syncthreads();
+    if (tid == 0) *reinterpret_cast<volatile uint32_t*>(X.local + 264) = seq;
+}
+
 }  // namespace
 
 cudaError_t dx_launch_wald(int64_t n, const double* theta, const double* sd, double* pval, double* logp, cudaStream_t s) {
@@ -851,7 +1009,16 @@ cudaError_t dx_launch_bh(int64_t n, const double* pval, double* qval, double* wo
     int* offs = cnt + n;
     int* cursor = offs + BH_NB + 1;
     static const bool all_pairs = getenv("DXB200_BH_ALLPAIRS") != nullptr;      // development hook: the previous formulation
+    static const bool multi = getenv("DXB200_BH_MULTI") != nullptr;              // development hook: force the multi-kernel path
     const unsigned g256 = (unsigned)((n + 255) / 256);
+    if (n <= BH_FUSED_MAX && !all_pairs && !multi) {
+        BhExchange X;
+        X.local = nullptr; X.world = 1; X.slot_bytes = 0; X.pval_out = nullptr; X.timeout_ns = 0;
+        cudaError_t e = cudaFuncSetAttribute(dx_bh_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (BH_NB + 1) * 4);
+        if (e != cudaSuccess) return e;
+        dx_bh_fused_kernel<<<1, BH_FT, (BH_NB + 1) * 4, s>>>((int)n, pval, qval, work, skey, cnt, X);
+        return cudaGetLastError();
+    }
     if (all_pairs) {
         cudaError_t e = cudaMemsetAsync(cnt, 0, (size_t)n * sizeof(int), s);
         if (e != cudaSuccess) return e;
@@ -881,4 +1048,28 @@ cudaError_t dx_launch_bh_sorted(int64_t n, const double* p_sorted, const int64_t
     dx_bh_chunkmin_kernel<true><<<n_chunks, BH_ST, 0, s>>>(n, p_sorted, work);
     dx_bh_suffix_kernel<true><<<n_chunks, BH_ST, 0, s>>>(n, const_cast<double*>(p_sorted), work, n_chunks, order, qval);
     return cudaGetLastError();
+}
+
+// q-values of the p-values that the fit kernels of all ranks stored into this rank's exchange buffer (dx_fit_args.cuh)
+cudaError_t dx_launch_bh_exchange(int64_t n_total, void* local_buf, int world, int64_t slot_bytes, double* pval_all,
+                                  double* qval, double* work, cudaStream_t s) {
+    if (n_total <= 0 || !local_buf || world < 1 || world > DX_EX_MAX_WORLD || n_total * 8 > slot_bytes) return cudaErrorInvalidValue;
+    BhExchange X;
+    X.local = static_cast<unsigned char*>(local_buf); X.world = world; X.slot_bytes = slot_bytes; X.pval_out = pval_all;
+    X.timeout_ns = 5000000000ull;
+    if (n_total <= BH_FUSED_MAX) {
+        const int n_chunks = (int)((n_total + BH_ST - 1) / BH_ST);
+        double* chunk_min = work + n_total;
+        long long* skey = reinterpret_cast<long long*>(chunk_min + n_chunks);
+        int* cnt = reinterpret_cast<int*>(skey + n_total);
+        cudaError_t e = cudaFuncSetAttribute(dx_bh_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (BH_NB + 1) * 4);
+        if (e != cudaSuccess) return e;
+        dx_bh_fused_kernel<<<1, BH_FT, (BH_NB + 1) * 4, s>>>((int)n_total, nullptr, qval, work, skey, cnt, X);
+        return cudaGetLastError();
+    }
+    if (!pval_all) return cudaErrorInvalidValue;
+    dx_exchange_wait_kernel<<<1, 1024, 0, s>>>(n_total, X);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return dx_launch_bh(n_total, pval_all, qval, work, s);
 }

@@ -79,7 +79,7 @@ class PeerExchange:
     carries the CUDA IPC handles at set-up.  One node, at most 16 ranks, every rank calls ``allgather`` in the same order
     with the same row count."""
 
-    def __init__(self, max_rows_per_rank):
+    def __init__(self, max_rows_per_rank, slot_rows=None):
         import ctypes as C
         from . import _lib
         if not (td.is_available() and td.is_initialized()):
@@ -88,7 +88,9 @@ class PeerExchange:
         if self.size > 16:
             raise ValueError("PeerExchange: at most 16 ranks (one node)")
         self._lib, self._C = _lib, C
-        self.slot_bytes = int(self.size * max_rows_per_rank * 8)
+        # one slot holds the rows of all ranks: size * max_rows_per_rank, or slot_rows when the ranks own ranges of
+        # different lengths of one vector of slot_rows entries (gene ranges cut by non-zero count)
+        self.slot_bytes = int((slot_rows if slot_rows is not None else self.size * max_rows_per_rank) * 8)
         # Every rank runs the same sequence of collectives whatever fails locally (a rank that raised early would leave
         # the others in a collective it never joins): create, exchange handles, map, agree, then raise everywhere.
         self._local, self._ptrs, err = None, None, None
@@ -140,6 +142,15 @@ class PeerExchange:
         self._lib.call("dx_peer_allgather_f64", n, ptr(src), self._ptrs, self.size, self.rank, self.slot_bytes,
                        ptr(dst), stream_ptr())
         return dst
+
+    @property
+    def peer_ptrs(self):
+        """ctypes array of the `size` exchange-buffer pointers (own buffer at [rank]) for the C ABI."""
+        return self._ptrs
+
+    @property
+    def local_ptr(self):
+        return self._C.c_void_p(self._local)
 
     def check(self):
         """Synchronous: raises if a peer's rows did not arrive within the kernel's 5 s limit."""

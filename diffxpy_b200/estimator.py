@@ -27,6 +27,7 @@ TRAINING_STRATEGIES = {
     "QUICK": [{"max_steps": 100, "method_b": "brent", "update_b_freq": 5, "ftol_b": 1e-4, "max_iter_b": 1000}],
 }
 LLTOL_BY_FEATURE = 1e-10
+_B_CLOSED_FORM = -1      # host-side marker: init_b="closed_form", turned into DX_INIT_GIVEN before the first launch
 
 
 def _dense_design(d):
@@ -297,11 +298,12 @@ class Estimator:
             mode_b = init_b.lower()
             if mode_b == "auto":
                 mode_b = "standard"
-            if mode_b == "closed_form":
-                raise ValueError("init_b='closed_form' is not supported by the CUDA estimator; use 'standard'")
-            if mode_b not in ("standard", "all_zero"):
+            if mode_b not in ("standard", "all_zero", "closed_form"):
                 raise ValueError("init_b string %s not recognized" % init_b)
-            b_mode = {"standard": _lib.DX_INIT_STANDARD, "all_zero": _lib.DX_INIT_ALL_ZERO}[mode_b]
+            # closed form (batchglm closedform_nb_glm_logphi; the reference's two-group wrappers pass it, tests.py:1067-1068,
+            # 1245-1246): resolved on the first train() call from group-wise moments into given start values
+            b_mode = {"standard": _lib.DX_INIT_STANDARD, "all_zero": _lib.DX_INIT_ALL_ZERO,
+                      "closed_form": _B_CLOSED_FORM}[mode_b]
         else:
             b_given = np.ascontiguousarray(np.asarray(init_b, dtype=np.float64))
             if b_given.shape != (idata.num_scale_params, g_total):
@@ -336,7 +338,8 @@ class Estimator:
                 # lstsq residuals are empty when the system is square / under-determined (saturated design)
                 saturated = loc_u.shape[0] <= p or np.linalg.matrix_rank(ud) < p
                 train_loc = (not saturated) or sf_nontrivial
-            plan.update(kind="grouped", k=k, kl=loc_u.shape[0],
+            plan.update(kind="grouped", k=k, kl=loc_u.shape[0], joint_rows=uniq,
+                        scale_const=bool(ps == 1 and np.all(xu_scale == xu_scale[0, 0])),
                         cell_group=torch.from_numpy(inv.astype(np.uint8)).to(dev),
                         xu_loc=torch.from_numpy(xu_loc).to(dev), xu_scale=torch.from_numpy(xu_scale).to(dev),
                         offset=None if offset is None else torch.from_numpy(offset).to(dev),
@@ -407,13 +410,20 @@ class Estimator:
             flags = torch.empty(g, dtype=torch.int32, device=dev)
             opts = _lib.DxFitOpts(max_steps=int(max_steps), update_b_freq=int(update_b_freq),
                                   train_loc=int(plan["train_loc"]), train_scale=int(plan["train_scale"]),
-                                  init_a=a_mode, init_b=b_mode, newton_max_iter=100, reserved=0,
+                                  init_a=a_mode, init_b=max(b_mode, 0), newton_max_iter=100, reserved=0,
                                   lltol=LLTOL_BY_FEATURE, newton_xtol=1e-8)
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
             if plan["kind"] == "grouped":
                 if "suff" not in plan:
-                    plan["suff"] = shard.group_suffstats(plan["cell_group"], plan["k"]).pack_overflow()
+                    suff = shard.group_suffstats(plan["cell_group"], plan["k"])
+                    if b_mode == _B_CLOSED_FORM:
+                        b_var.copy_(self._closed_form_b_grouped(suff))
+                    plan["suff"] = suff.pack_overflow()
+                if b_mode == _B_CLOSED_FORM:
+                    opts.init_b = b_mode = _lib.DX_INIT_GIVEN
+                if plan.get("scale_const"):
+                    opts.reserved |= _lib.DX_OPT_SCALE_CONST          # constant dispersion: register-resident K_fit
                 suff = plan["suff"]
                 _lib.call("dx_nb_fit_grouped_packed", g, plan["k"], p, ps, ptr(plan["xu_loc"]), ptr(plan["xu_scale"]),
                           ptr(plan["offset"]), ptr(plan["n_k"]), ptr(plan["pinv"]), ptr(plan["loc_group"]),
@@ -425,6 +435,7 @@ class Estimator:
                 if first:
                     self._percell_init(a_var, b_var, a_mode, b_mode)
                     opts.init_a = opts.init_b = _lib.DX_INIT_GIVEN
+                    b_mode = _lib.DX_INIT_GIVEN
                 if ps == 1 and np.all(idata.xh_scale == idata.xh_scale[0, 0]):
                     opts.reserved |= _lib.DX_OPT_SCALE_CONST          # constant dispersion model
                 _lib.call("dx_nb_fit_percell", g, shard.n_cells, p, ps, ptr(plan["design_loc"]),
@@ -478,6 +489,77 @@ class Estimator:
             b_var[0] = torch.clamp(torch.log(m * m / denom + np.nextafter(0.0, 1.0)), _ETA_MIN, _ETA_MAX)
         elif b_mode == _lib.DX_INIT_ALL_ZERO:
             b_var.zero_()
+        elif b_mode == _B_CLOSED_FORM:
+            scale_u, inv_cells = group_rows(idata.design_scale)
+            if scale_u.shape[0] > 500:
+                raise ValueError("large least-square problem in init, likely defined a numeric predictor as categorical")
+            ks = scale_u.shape[0]
+            m = torch.empty((ks, shard.n_genes), dtype=torch.float64, device=dev)
+            e2 = torch.empty_like(m)
+            for l in range(ks):
+                sel = torch.from_numpy((inv_cells == l).astype(np.float64)).to(dev)
+                cnt = float(sel.sum().item())
+                w = sel if inv_sf is None else sel * inv_sf
+                s1, s2 = shard.gene_moments(w.contiguous())          # sums of (x w) and (x w)^2: w is 0 outside the group
+                m[l], e2[l] = s1 / cnt, s2 / cnt
+            b_var.copy_(self._closed_form_b_solve(m, e2, scale_u))
+
+    def _closed_form_b_solve(self, m, e2, scale_u):
+        """batchglm closedform_nb_glm_logphi (oracle/nb_glm.py:init_par): log method-of-moments size of every distinct
+        dispersion-design row, pushed through the least-squares solution of those rows."""
+        v = e2 - m * m
+        denom = torch.clamp(v - m, min=float(np.sqrt(np.nextafter(0.0, 1.0))))
+        linked = torch.log(m * m / denom)
+        pinv = torch.from_numpy(np.linalg.pinv(scale_u @ self.input_data.constraints_scale)).to(m.device)
+        # lstsq of the reference = pseudo-inverse; -inf entries (all-zero groups) propagate like there and are clipped below
+        b0 = pinv @ torch.nan_to_num(linked, neginf=_ETA_MIN * 4)
+        return torch.clamp(b0, _ETA_MIN, _ETA_MAX)
+
+    def _closed_form_b_grouped(self, suff):
+        """Start values of the dispersion model from the sufficient statistics of K_ingest (before K_pack): per design
+        group sum(x) and sum(x^2) from the tail counts (+ overflow entries), pooled over the groups that share a
+        dispersion-design row, divided by the group's size factor."""
+        idata, plan = self.input_data, self._plan
+        dev = suff.tail.device
+        k, g = plan["k"], suff.tail.shape[0]
+        p, ps = idata.num_loc_params, idata.num_scale_params
+        tail = suff.tail.to(torch.float64)                                            # [G][K][64]
+        j = torch.arange(_lib.DX_HIST_BINS, dtype=torch.float64, device=dev)
+        s1 = tail.sum(dim=2)                                                          # sum_j c(j) = sum of counts
+        s2 = (tail * (2.0 * j + 1.0)).sum(dim=2)                                      # sum_j c(j) (2 j + 1) = sum of squares
+        n_ovf = suff.ovf_count.to(torch.int64)
+        if int(n_ovf.sum().item()) > 0:
+            genes = torch.nonzero(n_ovf).reshape(-1)
+            cnts = n_ovf[genes]
+            gene_of = torch.repeat_interleave(genes, cnts)
+            start = torch.repeat_interleave(suff.shard.indptr[genes], cnts)
+            first = torch.cumsum(cnts, 0) - cnts
+            pos = start + (torch.arange(gene_of.shape[0], device=dev) - torch.repeat_interleave(first, cnts))
+            val = suff.ovf_val[pos].to(torch.float64)
+            flat = gene_of * k + suff.ovf_group[pos].to(torch.int64)
+            s1.view(-1).index_add_(0, flat, val)
+            s2.view(-1).index_add_(0, flat, val * val)
+        # dispersion-design groups: distinct rows of design_scale, numbered through the joint design groups
+        joint = plan["joint_rows"]
+        scale_rows = joint[:, p:p + ps]
+        # design_scale itself (not the constrained one) defines the groups in batchglm; with constraints the distinct
+        # rows of the constrained design are a coarsening that spans the same space
+        scale_u, grp = group_rows(np.ascontiguousarray(scale_rows))
+        n_k = plan["n_k"].to(torch.float64)
+        if plan["offset"] is not None:
+            isf = torch.exp(-plan["offset"])
+            s1, s2 = s1 * isf[None, :], s2 * (isf * isf)[None, :]
+        sel = torch.zeros((k, scale_u.shape[0]), dtype=torch.float64, device=dev)
+        sel[torch.arange(k, device=dev), torch.from_numpy(grp).to(dev)] = 1.0
+        cnt = n_k @ sel                                                               # cells per dispersion group
+        m = (s1 @ sel / cnt[None, :]).t().contiguous()                                # [KS][G]
+        e2 = (s2 @ sel / cnt[None, :]).t().contiguous()
+        v = e2 - m * m
+        denom = torch.clamp(v - m, min=float(np.sqrt(np.nextafter(0.0, 1.0))))
+        linked = torch.log(m * m / denom)
+        pinv = torch.from_numpy(np.linalg.pinv(scale_u)).to(dev)
+        b0 = pinv @ torch.nan_to_num(linked, neginf=_ETA_MIN * 4)
+        return torch.clamp(b0, _ETA_MIN, _ETA_MAX)
 
     # ------------------------------------------------------------------------------------------
     def finalize(self):

@@ -378,7 +378,8 @@ def two_sample(data, grouping: Union[str, np.ndarray, list], as_numeric=(), test
         return lrt(data=data, full_formula_loc="~ 1 + grouping", full_formula_scale="~ 1",
                    reduced_formula_loc="~ 1", reduced_formula_scale="~ 1", as_numeric=as_numeric,
                    gene_names=gene_names, sample_description=sample_description, noise_model=noise_model,
-                   size_factors=size_factors, batch_size=batch_size, backend=backend, train_args=train_args,
+                   size_factors=size_factors, init_a="closed_form", init_b="closed_form",      # reference tests.py:1067-1068
+                   batch_size=batch_size, backend=backend, train_args=train_args,
                    training_strategy=training_strategy, quick_scale=bool(quick_scale), dtype=dtype, **kwargs)
     elif test.lower() == 't-test' or test.lower() == "t_test" or test.lower() == "ttest":
         return t_test(data=data, gene_names=gene_names, grouping=grouping, is_sig_zerovar=is_sig_zerovar)
@@ -440,10 +441,9 @@ def pairwise(data, grouping: Union[str, np.ndarray, list], as_numeric=(), test: 
     groups = np.unique(grouping)
     if is_z:
         dmat = _design_matrix(sample_description=sample_description, formula="~ 1 - 1 + grouping")
-        # init_b="closed_form" of the reference (tests.py:1245) needs batchglm's group-wise dispersion start;
-        # the standard method-of-moments start converges to the same optimum
+        # group-wise starts for both models, like the reference (tests.py:1245-1246)
         model = _fit(noise_model=noise_model, data=data, design_loc=dmat, design_scale=dmat, gene_names=gene_names,
-                     size_factors=size_factors, init_a="closed_form", init_b="standard", batch_size=batch_size,
+                     size_factors=size_factors, init_a="closed_form", init_b="closed_form", batch_size=batch_size,
                      backend=backend, train_args=train_args, training_strategy=training_strategy,
                      quick_scale=quick_scale, dtype=dtype, **kwargs)
         return DifferentialExpressionTestZTest(model_estim=model, grouping=grouping, groups=groups,

@@ -57,8 +57,9 @@ extern "C" {
 #define DX_INIT_ALL_ZERO 3
 
 /* dx_fit_opts.reserved bits */
-#define DX_OPT_SCALE_CONST 1   /* per-cell path: p_scale == 1 and design_scale is the same value in every cell (the caller
-                                  verified it): the dispersion is evaluated once per pass instead of once per cell */
+#define DX_OPT_SCALE_CONST 1   /* p_scale == 1 and design_scale is the same value in every cell / design group (the caller
+                                  verified it).  Per-cell path: the dispersion is evaluated once per pass instead of once per
+                                  cell.  Grouped path: selects the register-resident kernel when n_groups <= 32, p_loc <= 16 */
 
 typedef struct dx_fit_opts {
     int32_t max_steps;        /* train(): max_steps, DEFAULT strategy 1000 */
@@ -146,6 +147,34 @@ int dx_nb_fit_grouped_packed(int64_t n_genes, int32_t n_groups, int32_t p_loc, i
                              const dx_fit_opts* opts,
                              double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
                              int32_t* niter, int32_t* flags, void* stream);
+
+/* ---- K_fit + Wald in one launch (the product path of de.test.wald with one tested coefficient) ------------------------
+ * dx_nb_fit_grouped_packed followed, per gene and inside the same kernel, by the single-coefficient Wald row
+ * (det.py:783-802, stats.py:181-218): theta = a_var[coef], sd = sqrt(max(fim_inv[g][coef][coef], tiny)), pval, log_pval
+ * ([n_genes] each, nullable).  A NaN variance (singular Fisher information) gives NaN rows, as in the reference.
+ * Several GPUs (world > 1): the p-value of gene g is ALSO stored into the current slot of every rank's exchange buffer
+ * (dx_exchange_create below) at index gene_offset + g, and the last CTA publishes this rank's sequence flag;
+ * dx_bh_qvalues_exchange on every rank then waits for all flags and corrects the complete vector -- no separate gather
+ * launch.  peer_bufs: HOST array of `world` device pointers (own buffer at [rank]); world == 1: no exchange, peer_bufs
+ * may be null.
+ * opts->reserved & DX_OPT_SCALE_CONST (p_scale == 1 and the same dispersion design value in every group, verified by
+ * the caller) with n_groups <= 32 and p_loc <= 16 selects the register-resident kernel (dx_fit_fast.cu). */
+int dx_nb_fit_wald_grouped(int64_t n_genes, int32_t n_groups, int32_t p_loc, int32_t p_scale,
+                           const double* xu_loc, const double* xu_scale, const double* offset, const double* n_k,
+                           const double* pinv_loc, const int32_t* loc_group, int32_t n_loc_groups,
+                           const uint32_t* hist, const int32_t* ovf_count, const int64_t* indptr,
+                           const float* ovf_val, const uint8_t* ovf_group, const int32_t* ovf_packed,
+                           const dx_fit_opts* opts,
+                           double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
+                           int32_t* niter, int32_t* flags,
+                           int32_t coef, double* theta, double* sd, double* pval, double* log_pval,
+                           void* const* peer_bufs, int32_t world, int32_t rank, int64_t slot_bytes, int64_t gene_offset,
+                           void* stream);
+/* Benjamini-Hochberg q-values (correction.py:5-24) of the n_total p-values that dx_nb_fit_wald_grouped of ALL ranks
+ * stored into this rank's exchange buffer: waits (on the stream) for every rank's flag, corrects, marks the exchange
+ * done.  pval_all (nullable for n_total <= 32768): copy of the gathered p-values.  work: dx_bh_work_bytes(n_total). */
+int dx_bh_qvalues_exchange(int64_t n_total, void* local_buf, int32_t world, int64_t slot_bytes, double* pval_all,
+                           double* qval, double* work, void* stream);
 
 /* ---- multi-GPU: all-gather of per-gene result rows over NVLink peer memory (one node, one process per GPU) ----------
  * Replaces nothing in the reference (it is single-process); it is the one exchange of the sharded path:
@@ -254,8 +283,10 @@ int dx_group_pair_tests_big(int64_t n_genes, int32_t n_groups, int32_t group_a, 
 
 /* ---- host-buffer entry point (what bench.py's e2e leg and a foreign-language binding call) ---------
  * Full Wald test of one coefficient on a HOST CSC matrix with a grouped design: copies the inputs to
- * the device, runs ingest + fit + Wald, copies the per-gene rows back.  Pointers are host memory
- * (pinned for full PCIe rate).  out_* are [G] (a_var [p_loc][G], fim_inv [G][p_loc][p_loc]). */
+ * the device (chunk c + 1 crosses PCIe while chunk c is ingested and fitted), runs ingest + fit + Wald + the
+ * Benjamini-Hochberg correction over all genes (det.py:108-117, correction.py:5-24), copies the per-gene rows back.
+ * Pointers are host memory (pinned for full PCIe rate).  out_* are [G] (a_var [p_loc][G], fim_inv [G][p_loc][p_loc]);
+ * fim_inv .. qval are nullable.  The device workspace is cached between calls; dx_host_release() frees it. */
 int dx_wald_grouped_host(int64_t n_cells, int64_t n_genes, const int64_t* indptr, const int32_t* rows,
                          const float* vals, const uint8_t* cell_group, int32_t n_groups,
                          int32_t p_loc, int32_t p_scale, const double* xu_loc, const double* xu_scale,
@@ -263,7 +294,8 @@ int dx_wald_grouped_host(int64_t n_cells, int64_t n_genes, const int64_t* indptr
                          const int32_t* loc_group, int32_t n_loc_groups,
                          const dx_fit_opts* opts, int32_t coef,
                          double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
-                         int32_t* niter, int32_t* flags, double* pval, double* log_pval, double* sd);
+                         int32_t* niter, int32_t* flags, double* pval, double* log_pval, double* sd, double* qval);
+int dx_host_release(void);
 
 #ifdef __cplusplus
 }

@@ -47,6 +47,13 @@ def make_stats():
     sd[:4] = [0.3, 0.1, 0.5, 0.0]
     out["wald_theta"], out["wald_sd"] = theta.copy(), sd.copy()
     out["wald_p"] = ref.wald_test(theta_mle=theta.copy(), theta_sd=sd.copy(), theta0=0)
+    # NaN standard deviations (singular Fisher information) and NaN coefficients stay NaN in the reference: the
+    # np.nextafter(..., where=sd < tiny) floor does not touch them
+    th_n = np.array([0.7, -2.0, np.nan, 1.5, 0.0])
+    sd_n = np.array([np.nan, 0.4, 0.3, np.nan, 0.0])
+    out["waldnan_theta"], out["waldnan_sd"] = th_n.copy(), sd_n.copy()
+    with np.errstate(all="ignore"):
+        out["waldnan_p"] = ref.wald_test(theta_mle=th_n.copy(), theta_sd=sd_n.copy(), theta0=0)
     # --- wald_test_chisq (stats.py:221-282): k = 3 coefficients, one singular covariance
     k = 3
     th = rng.normal(0, 0.4, (k, g))
@@ -161,4 +168,5 @@ def make_nbglm():
 
 if __name__ == "__main__":
     make_stats()
-    make_nbglm()
+    if "--stats-only" not in sys.argv:
+        make_nbglm()

@@ -52,6 +52,30 @@ def test_wald_test_kernel(de, gold):
     np.testing.assert_allclose(lp[carries], np.log(gold["wald_p"][carries]), rtol=1e-4, atol=1e-12)
 
 
+def test_wald_nan_sd_is_nan_not_zero(de, gold):
+    """Singular Fisher information -> NaN sd -> p = NaN (not 0), excluded from the q-values (reference golden)."""
+    from diffxpy_b200.stats import stats as dstats
+    from diffxpy_b200.testing import correction
+    p, lp = dstats.wald_test_full(gold["waldnan_theta"], gold["waldnan_sd"])
+    np.testing.assert_allclose(p, gold["waldnan_p"], rtol=0, atol=4e-16, equal_nan=True)
+    assert np.isnan(p[0]) and np.isnan(p[2]) and np.isnan(p[3]) and np.isnan(lp[0])
+    q = correction.correct(p)
+    np.testing.assert_array_equal(q, ost.bh_correct(gold["waldnan_p"]))
+    # the same rule inside dx_wald_from_fit: a NaN diagonal of fisher_inv (failed final factorisation) -> NaN row
+    import torch
+    from diffxpy_b200 import _lib
+    from diffxpy_b200.device import ptr, stream_ptr
+    dev = torch.device("cuda")
+    a = torch.tensor([[0.1, 0.2, 0.3], [1.0, -2.0, 0.5]], dtype=torch.float64, device=dev)        # [p][G]
+    fi = torch.eye(2, dtype=torch.float64, device=dev).repeat(3, 1, 1).contiguous()
+    fi[1] = float("nan")
+    out = torch.empty((4, 3), dtype=torch.float64, device=dev)
+    _lib.call("dx_wald_from_fit", 3, 2, 1, ptr(a), ptr(fi), ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]), stream_ptr())
+    o = out.cpu().numpy()
+    assert np.isnan(o[2, 1]) and np.isnan(o[3, 1]) and np.isnan(o[1, 1])
+    assert np.all(np.isfinite(o[2, [0, 2]]))
+
+
 def test_wald_chisq_kernel(de, gold):
     p = de.stats.wald_test_chisq(gold["chisq_theta"], gold["chisq_cov"])
     assert np.isnan(p[7])
@@ -741,12 +765,13 @@ def test_host_entry_point_matches_device_path(de, golden_dir):
     nk = np.bincount(inv, minlength=k).astype(np.float64)
     pinv = np.ascontiguousarray(np.linalg.pinv(xu))
     opts = _lib.DxFitOpts(max_steps=1000, update_b_freq=5, train_loc=1, train_scale=1, init_a=_lib.DX_INIT_CLOSED_FORM,
-                          init_b=_lib.DX_INIT_STANDARD, newton_max_iter=100, reserved=0, lltol=1e-10, newton_xtol=1e-8)
+                          init_b=_lib.DX_INIT_STANDARD, newton_max_iter=100, reserved=_lib.DX_OPT_SCALE_CONST,      # as the estimator
+                          lltol=1e-10, newton_xtol=1e-8)
     a = np.zeros((p, g)); b = np.zeros((1, g)); fi = np.zeros((g, p, p)); ll = np.zeros(g); jac = np.zeros(g)
     ni = np.zeros(g, dtype=np.int32); fl = np.zeros(g, dtype=np.int32); pv = np.zeros(g); lp = np.zeros(g); sdv = np.zeros(g)
     P = lambda arr: arr.ctypes.data_as(C.c_void_p)
     _lib.call("dx_wald_grouped_host", n, g, P(indptr), P(rows), P(vals), P(grp), k, p, 1, P(xu), P(xs), None, P(nk),
-              P(pinv), None, k, C.byref(opts), 1, P(a), P(b), P(fi), P(ll), P(jac), P(ni), P(fl), P(pv), P(lp), P(sdv))
+              P(pinv), None, k, C.byref(opts), 1, P(a), P(b), P(fi), P(ll), P(jac), P(ni), P(fl), P(pv), P(lp), P(sdv), None)
     np.testing.assert_array_equal(a, est.a_var)
     np.testing.assert_array_equal(ni, est.niter)
     np.testing.assert_array_equal(fl, est.error_codes)
@@ -756,7 +781,7 @@ def test_host_entry_point_matches_device_path(de, golden_dir):
     try:
         a2 = np.zeros((p, g)); b2 = np.zeros((1, g)); fi2 = np.zeros((g, p, p)); pv2 = np.zeros(g)
         _lib.call("dx_wald_grouped_host", n, g, P(indptr), P(rows), P(vals), P(grp), k, p, 1, P(xu), P(xs), None, P(nk),
-                  P(pinv), None, k, C.byref(opts), 1, P(a2), P(b2), P(fi2), P(ll), P(jac), P(ni), P(fl), P(pv2), P(lp), P(sdv))
+                  P(pinv), None, k, C.byref(opts), 1, P(a2), P(b2), P(fi2), P(ll), P(jac), P(ni), P(fl), P(pv2), P(lp), P(sdv), None)
     finally:
         del os.environ["DXB200_HOST_CHUNKS"]
     np.testing.assert_array_equal(a2, a)

@@ -33,6 +33,18 @@ def test_lrt_matches_reference(gold):
     np.testing.assert_allclose(p, gold["lrt_p"], rtol=0, atol=0)
 
 
+def test_wald_nan_sd_stays_nan(gold):
+    """A NaN standard deviation (singular Fisher information) gives p = NaN in the reference (stats.py:215 floors only
+    sd < tiny), and such genes are left out of the BH correction (correction.py:15-22)."""
+    with np.errstate(all="ignore"):
+        p = ost.wald_test(gold["waldnan_theta"], gold["waldnan_sd"])
+    np.testing.assert_array_equal(p, gold["waldnan_p"])
+    assert np.isnan(p[0]) and np.isnan(p[2]) and np.isnan(p[3]) and p[4] == 1.0
+    q = ost.bh_correct(p)
+    assert np.isnan(q[0]) and np.isfinite(q[1])
+    np.testing.assert_allclose(q[[1, 4]], ost.bh_correct(p[[1, 4]]), rtol=0, atol=0)
+
+
 def test_t_test_moments_matches_reference(gold):
     p = ost.t_test_moments(gold["tt_mu0"], gold["tt_mu1"], gold["tt_var0"], gold["tt_var1"],
                            int(gold["tt_n"][0]), int(gold["tt_n"][1]))

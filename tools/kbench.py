@@ -51,6 +51,7 @@ def main():
     ap.add_argument("--plain", action="store_true", help="use dx_group_suffstats (no gene order / integer flag)")
     ap.add_argument("--scale-batch", action="store_true", help="scale model '~1+batch' (8 dispersion coefficients, configs[2])")
     ap.add_argument("--pack", action="store_true", help="dx_pack_overflow after the ingest + dx_nb_fit_grouped_packed")
+    ap.add_argument("--reserved", type=int, default=1, help="dx_fit_opts.reserved (1 = DX_OPT_SCALE_CONST: register-resident K_fit)")
     ap.add_argument("--seed", type=int, default=1000, help="shard seed (bench.py uses 1000 + rank)")
     ap.add_argument("--mu-hi", type=float, default=1.0, help="upper end of the log-uniform gene means (default: the bench workload)")
     ap.add_argument("names", nargs="+")
@@ -75,13 +76,15 @@ def main():
     d_nk, d_pinv = torch.from_numpy(n_k).to(dev), torch.from_numpy(pinv).to(dev)
     opts = _lib.DxFitOpts(max_steps=1000, update_b_freq=5, train_loc=1, train_scale=1,
                           init_a=_lib.DX_INIT_CLOSED_FORM, init_b=_lib.DX_INIT_STANDARD, newton_max_iter=100,
-                          reserved=0, lltol=1e-10, newton_xtol=1e-8)
+                          reserved=(0 if a.scale_batch else a.reserved), lltol=1e-10, newton_xtol=1e-8)
     f64 = dict(dtype=torch.float64, device=dev)
     ref = {}
     ev = lambda: torch.cuda.Event(enable_timing=True)
     print("nnz %d  genes %d  groups %d  p %d" % (nnz, g, k, p))
     for name in a.names:
-        lib = load_variant(name)
+        # "name@g": the same library with the general K_fit kernel (reserved = 0) -- a reference for the register-resident one
+        opts.reserved = 0 if (name.endswith("@g") or a.scale_batch) else a.reserved
+        lib = load_variant(name[:-2] if name.endswith("@g") else name)
         tail = torch.zeros((g, k, _lib.DX_HIST_BINS), dtype=torch.int32, device=dev)
         ovf_count = torch.zeros(g, dtype=torch.int32, device=dev)
         ovf_val = torch.zeros(nnz, dtype=torch.float32, device=dev)
