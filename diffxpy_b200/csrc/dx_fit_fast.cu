@@ -282,7 +282,8 @@ dx_fit_fast_kernel(const FitArgs P) {
     // ---- initialize (batchglm init_par); lane i holds a_i, b is the same in every lane ------------------------------
     double areg = 0.0, breg = 0.0;
     if (opts.init_a == DX_INIT_STANDARD) {
-        areg = (sl == 0) ? dx_clip(dx_log(sum_all / ff_sum<LANES>(nk, mask)), DX_ETA_MIN, DX_ETA_MAX) : 0.0;
+        const double n_total = ff_sum<LANES>(nk, mask);          // (every lane takes part in the shuffles)
+        areg = (sl == 0) ? dx_clip(dx_log(sum_all / n_total), DX_ETA_MIN, DX_ETA_MAX) : 0.0;
     } else if (closed_form) {
         // batchglm closedform_glm_mean: log of the mean of x / size_factor over every distinct LOCATION design row,
         // pushed through the pseudo-inverse of those rows (np.linalg.lstsq in the reference)
@@ -357,7 +358,7 @@ dx_fit_fast_kernel(const FitArgs P) {
     double nll = -eval_ll(eta, zeta, r, l1p, T_r);
 
     // gradient G and curvature H of ll wrt the linear predictor of the dispersion at the current state
-    // (scale_terms of the general kernel for a shared r): g = xs0 G, -Hessian = xs0^2 H
+    // (scale_terms of the general kernel for a shared r): gradient wrt b = xs0 G, Hessian wrt b = xs0^2 H
     auto scale_terms = [&](double& G, double& H) {
         double D = 0.0, E = 0.0;
 #pragma unroll 1
@@ -505,7 +506,7 @@ dx_fit_fast_kernel(const FitArgs P) {
                 for (int it = 0; it < opts.newton_max_iter; ++it) {
                     double G, H;
                     scale_terms(G, H);
-                    const double gb = xs0 * G, hb = xs0 * xs0 * H;
+                    const double gb = xs0 * G, hb = -(xs0 * xs0) * H;          // hb = -Hessian wrt b (positive near a maximum)
                     if (!(isfinite(hb) && isfinite(gb))) break;
                     const double sb = (hb > 0.0) ? gb / hb : (double)((gb > 0.0) - (gb < 0.0));
                     const double smax = fabs(sb);

@@ -262,6 +262,7 @@ constexpr int NS = DX_TMA_NS;     // ring stages per warp
 constexpr int TILE = DX_TMA_TILE; // elements per stage
 constexpr int TU = TILE / 32;     // elements per lane and tile
 constexpr int NG = 8;             // gene descriptors in flight per warp (>= NS + 2)
+constexpr int DX_INGEST_MODE_GENES = 0, DX_INGEST_MODE_SPLIT = 1, DX_INGEST_MODE_REDO = 2;
 
 __device__ __forceinline__ uint32_t dx_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void dx_mbar_init(uint32_t bar, uint32_t count) {
@@ -308,7 +309,7 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
                      const float* __restrict__ vals, const uint8_t* __restrict__ cell_group, int K, int ysh, int NW, int NWA,
                      uint32_t* __restrict__ hist_out, int32_t* __restrict__ ovf_count,
                      float* __restrict__ ovf_val, uint8_t* __restrict__ ovf_group, unsigned int* __restrict__ queue,
-                     const int32_t* __restrict__ gene_order, int warp_bytes) {
+                     const int32_t* __restrict__ gene_order, int warp_bytes, int mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* base = smem_raw + (size_t)warp * warp_bytes;
@@ -346,14 +347,61 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
     const float* i_pv = vals;         // next tile of the issue gene
     const int32_t* i_pr = rows;
     int i_left = 0;                   // elements (padded to 4) of the issue gene not yet issued
+    // MODE_SPLIT: the queue hands out fixed-size ranges of the shard instead of genes; a range is cut at the gene
+    // boundaries inside it into pieces, every piece is counted like a (short) gene and its tail counts are ADDED to the
+    // (zeroed) output.  Used when the shard has fewer genes than the GPU has warps (a gene range of a multi-GPU run).
+    long long sp_pos = 0, sp_end = 0, sp_lo = 0, sp_hi = 0;     // current range [sp_pos, sp_end) of the shard [sp_lo, sp_hi)
+    long long sp_seg = 0;
+    long long sp_gene = 0;
+    if (mode == DX_INGEST_MODE_SPLIT) {
+        sp_lo = __ldg(indptr);
+        sp_hi = __ldg(indptr + n_genes);
+        const long long span = sp_hi - sp_lo;
+        const long long want = span / ((long long)gridDim.x * (blockDim.x >> 5) * 6) + 1;      // ~6 ranges per warp
+        sp_seg = ((want + TILE - 1) / TILE) * TILE;
+        if (sp_seg < 4 * TILE) sp_seg = 4 * TILE;
+        if (sp_seg > 128 * TILE) sp_seg = 128 * TILE;
+    }
     auto issue_one = [&]() {
         if (i_tiles == 0) {
             unsigned gq = 0;
-            if (lane == 0) gq = atomicAdd(queue, 1u);
-            gq = __shfl_sync(DX_FULL_MASK, gq, 0);
-            if ((int64_t)gq >= n_genes) { done_issue = true; return; }
-            if (gene_order) gq = (unsigned)__ldg(gene_order + gq);
-            const long long st_ = __ldg(indptr + gq), en_ = __ldg(indptr + gq + 1);
+            long long st_ = 0, en_ = 0;
+            if (mode == DX_INGEST_MODE_SPLIT) {
+                for (;;) {
+                    if (sp_pos >= sp_end) {                      // next range of the shard
+                        unsigned q = 0;
+                        if (lane == 0) q = atomicAdd(queue, 1u);
+                        q = __shfl_sync(DX_FULL_MASK, q, 0);
+                        sp_pos = sp_lo + (long long)q * sp_seg;
+                        if (sp_pos >= sp_hi) { done_issue = true; return; }
+                        sp_end = sp_pos + sp_seg < sp_hi ? sp_pos + sp_seg : sp_hi;
+                        // the gene that holds position sp_pos: last g with indptr[g] <= sp_pos (pointers are cached in L1)
+                        long long lo = 0, hi = n_genes;          // invariant: indptr[lo] <= sp_pos < indptr[hi]
+                        while (hi - lo > 1) {
+                            const long long mid = (lo + hi) >> 1;
+                            if (__ldg(indptr + mid) <= sp_pos) lo = mid; else hi = mid;
+                        }
+                        sp_gene = lo;
+                    }
+                    const long long g_end = __ldg(indptr + sp_gene + 1);
+                    st_ = sp_pos;
+                    en_ = g_end < sp_end ? g_end : sp_end;
+                    gq = (unsigned)sp_gene;
+                    if (g_end <= sp_end) ++sp_gene;              // the gene ends inside this range: the next piece is the next gene's
+                    sp_pos = en_;
+                    if (en_ > st_) break;                        // (genes without entries yield no piece)
+                }
+            } else {
+                for (;;) {
+                    if (lane == 0) gq = atomicAdd(queue, 1u);
+                    gq = __shfl_sync(DX_FULL_MASK, gq, 0);
+                    if ((int64_t)gq >= n_genes) { done_issue = true; return; }
+                    if (gene_order) gq = (unsigned)__ldg(gene_order + gq);
+                    // MODE_REDO: second pass after a split launch, only the genes that reported overflow entries
+                    if (mode != DX_INGEST_MODE_REDO || ovf_count[gq] != 0) break;
+                }
+                st_ = __ldg(indptr + gq); en_ = __ldg(indptr + gq + 1);
+            }
             if (lane == 0) {
                 GeneDesc d;
                 d.start = st_; d.end = en_; d.gene = (int)gq; d.pad = 0;
@@ -509,7 +557,7 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
                 const bool isbin = ((unsigned)(y - 1) < (unsigned)DX_HIST_BINS) && (__int2float_rn(y) == v[u]);
                 const bool ovf = !isbin && v[u] != 0.0f && k[u] < (unsigned)K;
                 const unsigned bal = __ballot_sync(DX_FULL_MASK, ovf);
-                if (ovf) {
+                if (ovf && mode != DX_INGEST_MODE_SPLIT) {      // (split pieces only count: the redo pass writes the list)
                     const int64_t pos = obase + ovf_base + __popc(bal & ((1u << lane) - 1u));
                     ovf_val[pos] = v[u];
                     ovf_group[pos] = (uint8_t)k[u];
@@ -536,10 +584,20 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
                 if (lane >= o) { plo += a; phi += b; }
             }
             const unsigned tot_lo = __shfl_sync(DX_FULL_MASK, plo, 31), tot_hi = __shfl_sync(DX_FULL_MASK, phi, 31);
-            out[kk * DX_HIST_BINS + 32 + lane] = tot_hi - phi + hi;
-            out[kk * DX_HIST_BINS + lane] = tot_hi + (tot_lo - plo + lo);
+            const unsigned t_hi = tot_hi - phi + hi, t_lo = tot_hi + (tot_lo - plo + lo);
+            if (mode == DX_INGEST_MODE_SPLIT) {          // a piece of the gene: tail counts are additive
+                if (t_hi) atomicAdd(out + kk * DX_HIST_BINS + 32 + lane, t_hi);
+                if (t_lo) atomicAdd(out + kk * DX_HIST_BINS + lane, t_lo);
+            } else {
+                out[kk * DX_HIST_BINS + 32 + lane] = t_hi;
+                out[kk * DX_HIST_BINS + lane] = t_lo;
+            }
         }
-        if (lane == 0) ovf_count[g] = (int32_t)ovf_base;
+        if (mode == DX_INGEST_MODE_SPLIT) {
+            if (lane == 0 && ovf_base) atomicAdd(ovf_count + g, (int32_t)ovf_base);
+        } else if (lane == 0) {
+            ovf_count[g] = (int32_t)ovf_base;
+        }
         ovf_base = 0;
         __syncwarp();
     };
@@ -633,10 +691,43 @@ cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32
                        : (h16 ? dx_ingest_tma_kernel<false, true> : dx_ingest_tma_kernel<false, false>);
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        // few genes (a gene range of a multi-GPU run): one warp per gene leaves warps idle and the longest gene sets the
+        // duration, so the shard is cut into equal ranges of non-zeros instead (pieces of genes, tail counts added with
+        // atomics into a zeroed table); genes with overflow entries are then redone gene-wise, which writes their lists in
+        // the canonical order.  DXB200_INGEST_SPLIT=0 / 1 forces the mode (development hook).
+        const char* split_env = getenv("DXB200_INGEST_SPLIT");
+        bool split = n_genes < 2 * (int64_t)sm_count * warps;
+        if (split_env) split = split_env[0] == '1';
+        if (split) {
+            // a piece never holds more than 128 tiles: its counts always fit 16-bit on-chip bins (the shared-memory
+            // layout sized for 32-bit bins holds them as well)
+            auto kern_split = io ? dx_ingest_tma_kernel<true, true> : dx_ingest_tma_kernel<false, true>;
+            e = cudaFuncSetAttribute(kern_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            e = cudaMemsetAsync(hist, 0, (size_t)n_genes * K * DX_HIST_BINS * sizeof(uint32_t), stream);
+            if (e != cudaSuccess) return e;
+            e = cudaMemsetAsync(ovf_count, 0, (size_t)n_genes * sizeof(int32_t), stream);
+            if (e != cudaSuccess) return e;
+            kern_split<<<(unsigned)sm_count, warps * 32, smem, stream>>>(n_genes, indptr, rows, vals, cell_group, K, ysh, NW, NWA,
+                                                                         hist, ovf_count, ovf_val, ovf_group, queue, nullptr,
+                                                                         warp_bytes, DX_INGEST_MODE_SPLIT);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+            unsigned int* queue2 = nullptr;
+            e = dx_queue_acquire(stream, &queue2);
+            if (e != cudaSuccess) return e;
+            int64_t grid2 = sm_count < 16 ? sm_count : 16;          // usually nothing to redo: a small grid walks the counts
+            if (grid2 > n_genes) grid2 = n_genes;
+            kern<<<(unsigned)grid2, warps * 32, smem, stream>>>(n_genes, indptr, rows, vals, cell_group, K, ysh, NW, NWA, hist,
+                                                                ovf_count, ovf_val, ovf_group, queue2, nullptr, warp_bytes,
+                                                                DX_INGEST_MODE_REDO);
+            return cudaGetLastError();
+        }
         int64_t grid = sm_count;                    // persistent CTAs; the warps pull genes from the queue
         if (grid > n_genes) grid = n_genes;
         kern<<<(unsigned)grid, warps * 32, smem, stream>>>(n_genes, indptr, rows, vals, cell_group, K, ysh, NW, NWA, hist,
-                                                           ovf_count, ovf_val, ovf_group, queue, gene_order, warp_bytes);
+                                                           ovf_count, ovf_val, ovf_group, queue, gene_order, warp_bytes,
+                                                           DX_INGEST_MODE_GENES);
         return cudaGetLastError();
     }
     // ---- CTA-per-gene variant (any K, any alignment) -------------------------------------------------------------
