@@ -491,10 +491,11 @@ def main_cuda(args):
     api_s = api_steps = None
     api_same = None
     sample_description = pd.DataFrame({"condition": cond.astype(str), "batch": batch.astype(str)})
+    gene_names = np.array(["g%d" % i for i in range(args.genes)])
     if full_host is not None and not args.no_api_e2e:
         def api_step():
             res = de.test.wald(data=full_host, formula_loc="~ 1 + condition + batch", factor_loc_totest="condition",
-                               sample_description=sample_description, noise_model="nb")
+                               sample_description=sample_description, gene_names=gene_names, noise_model="nb")
             return res, res.summary()
         res, summ = api_step()
         barrier()

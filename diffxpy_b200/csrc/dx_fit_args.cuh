@@ -1,5 +1,5 @@
 // dx_fit_args.cuh -- launch arguments shared by the two grouped K_fit kernels (dx_fit_grouped.cu: any design /
-// dispersion model; dx_fit_fast.cu: register-resident variant for <= 32 groups, <= 16 coefficients, constant
+// dispersion model; dx_fit_lane.cu: lane-resident variant for <= 32 groups, <= 9 coefficients, constant
 // dispersion) and the per-gene epilogue both of them run after finalize: the single-coefficient Wald row
 // (/root/reference/diffxpy/testing/det.py:783-802 + stats.py:181-218) and, on several GPUs, the store of the p-value
 // into every rank's exchange buffer (the one exchange of the path), so that neither a separate Wald launch
@@ -87,6 +87,6 @@ __device__ __forceinline__ void dx_fit_epilogue_publish(const FitEpilogue& E) {
     }
 }
 
-// launcher of the register-resident variant (dx_fit_fast.cu); A.queue / A.epi.done_ctas are filled in by it
-bool dx_fit_fast_eligible(int K, int p, int ps, const dx_fit_opts* opts);
-cudaError_t dx_launch_fit_fast(FitArgs& A, int sm_count, cudaStream_t stream);
+// launcher of the lane-resident variant (dx_fit_lane.cu); A.queue / A.epi.done_ctas are filled in by it
+bool dx_fit_lane_eligible(int K, int p, int ps, const dx_fit_opts* opts);
+cudaError_t dx_launch_fit_lane(FitArgs& A, int sm_count, cudaStream_t stream);

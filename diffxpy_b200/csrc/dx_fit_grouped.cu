@@ -942,9 +942,9 @@ cudaError_t dx_launch_fit_grouped(int64_t n_genes, int K, int p, int ps,
     A.opts = *opts;
     A.a_var = a_var; A.b_var = b_var; A.fim_inv = fim_inv; A.ll_out = ll; A.jac_out = jac; A.niter_out = niter; A.flags_out = flags;
     A.nent = p * (p + 1) / 2;
-    static const char* fast_env = getenv("DXB200_FIT_IMPL");      // tuning hook (development only): "g" forces the general kernel
-    if (!(fast_env && fast_env[0] == 'g') && dx_fit_fast_eligible(K, p, ps, opts) && (reinterpret_cast<uintptr_t>(tail) & 15u) == 0)
-        return dx_launch_fit_fast(A, 0, stream);
+    const char* impl_env = getenv("DXB200_FIT_IMPL");      // test hook: "g" forces the general kernel (read at every launch)
+    if (!(impl_env && impl_env[0] == 'g') && dx_fit_lane_eligible(K, p, ps, opts) && (reinterpret_cast<uintptr_t>(tail) & 15u) == 0)
+        return dx_launch_fit_lane(A, 0, stream);
     static const char* nz_env = getenv("DXB200_FIT_NZ");         // tuning hook (development only)
     A.nz_max = nz_env ? atoi(nz_env) : 96;   // capacity of the non-zero design-product list (0.9 KB); denser designs use the dense loop
     A.table_doubles = K * p + K * ps + 2 * K + A.nz_max + (2 * ((A.nent + 7) & ~7) + 2 * ((A.nent + 1 + 3) & ~3) + A.nz_max + 7) / 8 + 2;
@@ -952,7 +952,11 @@ cudaError_t dx_launch_fit_grouped(int64_t n_genes, int K, int p, int ps,
     A.slot_doubles = 13 * K + 2 * K + DX_HIST_BINS + A.ainv_extra + p * p + (p > ps ? p : ps) + 2 * ps * ps;
     A.slot_doubles = (A.slot_doubles + 1) & ~1;
     A.table_doubles = (A.table_doubles + 1) & ~1;
-    if (K <= 8 && p <= 8 && ps <= 8) return launch_sw<8>(A, 0, stream);
-    if (K <= 16 && p <= 16 && ps <= 16) return launch_sw<16>(A, 0, stream);
+    const char* sw_env = getenv("DXB200_FIT_SW");          // test hook: sub-warp width of the general kernel (16 or 32)
+    const int sw_min = sw_env ? atoi(sw_env) : 0;
+    // the sub-warp width follows the coefficient counts (lane <-> matrix row in the factorisations); design groups beyond
+    // the width are strided over by the lanes
+    if (K <= 8 && p <= 8 && ps <= 8 && sw_min <= 8) return launch_sw<8>(A, 0, stream);
+    if (p <= 16 && ps <= 16 && sw_min <= 16) return launch_sw<16>(A, 0, stream);
     return launch_sw<32>(A, 0, stream);
 }

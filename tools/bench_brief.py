@@ -1,13 +1,27 @@
+"""One-paragraph summary of a bench.py JSON line (stdin or a file argument)."""
 import sys, json
-for l in sys.stdin:
+src = open(sys.argv[1]) if len(sys.argv) > 1 else sys.stdin
+for l in src:
     l = l.strip()
     if not l.startswith("{"):
         continue
     d = json.loads(l)
-    k = d.get("kernels", {})
-    print("value %.3g genes/s  ms/step %.3f | ingest %.3f ms (%.1f%% of HBM peak)  fit %.3f ms  wald %.4f ms | e2e %.3g genes/s | niter %.2f conv %.3f | clocks %s" % (
-        d["value"], d["ms_per_step"], k["dx_ingest_tma_kernel"]["ms"], 100 * d["roofline"]["frac"],
-        k["dx_fit_grouped_kernel"]["ms"], k["dx_wald_from_fit_kernel"]["ms"], d["e2e"]["value"],
-        d["config"]["mean_niter"], d["config"]["frac_converged"], d["clocks"]))
+    k = d.get("kernels", {}) or {}
+    r = d.get("roofline", {}) or {}
+    print("N=%s value %.4g %s  ms/step %.4f  scaling %s" % (d.get("n_gpus"), d["value"], d["unit"], d["ms_per_step"], d.get("scaling")))
+    print("  kernels: " + "  ".join("%s %.4f ms" % (kk.split("(")[0], vv["ms"]) for kk, vv in k.items()))
+    if r:
+        print("  roofline: %s frac %.3f (%.0f GB/s), whole step frac %.3f" % (r.get("kernel"), r.get("frac", 0), r.get("achieved", 0),
+                                                                             (r.get("whole_step") or {}).get("frac", 0)))
+    for key in ("e2e", "e2e_cabi"):
+        e = d.get(key)
+        if e:
+            print("  %s: %.4g genes/s, %.1f ms per call, matches %s" % (key, e["value"], e.get("ms_per_call", 0), e.get("matches_device_path")))
+    c = d.get("config", {})
+    print("  niter %.2f conv %.3f exchange_ok %s launch %s | clocks %s" % (c.get("mean_niter", 0), c.get("frac_converged", 0),
+                                                                        c.get("exchange_matches_nccl"), c.get("launch"), d.get("clocks")))
+    if d.get("per_rank_ms"):
+        for i, pr in enumerate(d["per_rank_ms"]):
+            print("  rank %d: %s" % (i, pr))
     if d.get("cpu_baseline"):
-        print("cpu_baseline", d["cpu_baseline"])
+        print("  cpu_baseline", d["cpu_baseline"])
