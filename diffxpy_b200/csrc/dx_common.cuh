@@ -97,7 +97,7 @@ static __device__ __noinline__ double dx_lgamma_ratio(double r, double y) {
 __device__ __forceinline__ double dx_ndtr(double a) {
     const double x = a * 0.70710678118654752440;
     const double z = fabs(x);
-    if (z < 0.70710678118654752440) return 0.5 + 0.5 * erf(x);
+    if (z < 0.70710678118654752440) return fma(0.5, erf(x), 0.5);
     double y = 0.5 * erfc(z);
     return x > 0 ? 1.0 - y : y;
 }
@@ -106,7 +106,8 @@ __device__ __forceinline__ void dx_two_sided_normal(double z, double* p_ref, dou
     z = fabs(z);
     *p_ref = 2.0 * (1.0 - dx_ndtr(z));
     const double x = z * 0.70710678118654752440;
-    *logp = isnan(z) ? z : (isinf(z) ? -INFINITY : log(erfcx(x)) - x * x);   // log(erfc(x)) = log(2 sf(z))
+    *logp = isnan(z) ? z : (isinf(z) ? -INFINITY : fma(-x, x, log(erfcx(x))));   // log(erfc(x)) = log(2 sf(z))
+    // (explicit fma: the same bits from translation units compiled with and without multiply-add contraction)
 }
 
 // regularized incomplete gamma: P (series) / Q (modified Lentz continued fraction)

@@ -10,6 +10,7 @@
 
 constexpr int DX_EX_HEADER = 512;          // exchange buffer header bytes (layout in dx_exchange.cu)
 constexpr int DX_EX_MAX_WORLD = 16;
+constexpr int DX_LANE_MAX_OVF = 0;
 
 struct FitEpilogue {
     int wald_coef;                        // < 0: no Wald row
@@ -17,6 +18,7 @@ struct FitEpilogue {
     // multi-GPU: p-values go straight into slot (seq & 1) of every rank's exchange buffer at global gene index
     // gene_offset + g; the last CTA of the launch publishes the sequence number in every rank's flag row
     int world, rank;
+    int publish;                          // 0: this launch only stores p-values, a later launch of the same fit publishes
     int64_t gene_offset, slot_bytes;
     unsigned char* peer[DX_EX_MAX_WORLD];
     unsigned int* done_ctas;              // device counter of the launch (zeroed by the launcher)
@@ -38,6 +40,11 @@ struct FitArgs {
     int32_t *niter_out, *flags_out;
     int slot_doubles, table_doubles, nent, nz_max, ainv_extra;
     unsigned int* queue;              // gene queue of this launch (dx_queue_acquire)
+    // Genes with overflow entries (counts above 64 or non-integer values: highly expressed genes, normalised data) are not
+    // fitted by the lane-resident kernel -- a single thread would walk the whole list at every likelihood evaluation -- but
+    // marked with niter = -1 and fitted by the general kernel, whose 16 lanes share the list, in a second launch
+    // (only_deferred = 1).
+    int only_deferred;
     FitEpilogue epi;
 };
 
@@ -74,7 +81,7 @@ __device__ __forceinline__ void dx_fit_epilogue_row(const FitEpilogue& E, int64_
 // End of the launch (every thread of the CTA calls it): the last CTA publishes this rank's sequence number in every
 // rank's flag row -- all p-value stores of the launch are fenced before it.
 __device__ __forceinline__ void dx_fit_epilogue_publish(const FitEpilogue& E) {
-    if (E.world <= 1) return;
+    if (E.world <= 1 || !E.publish) return;
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -557,6 +557,8 @@ dx_fit_grouped_kernel(const FitArgs P) {
         g = (int64_t)__shfl_sync((SW == 32) ? 0xffffffffu : (((1u << SW) - 1u) << ((lane / SW) * SW)), q, (lane / SW) * SW);
     }
     if (g >= P.n_genes) break;
+    // second launch after the lane-resident kernel: only the genes it left marked (niter = -1) are fitted here
+    if (P.only_deferred && P.niter_out[g] >= 0) continue;
 
     Slot s;
     s.sl = lane % SW;
@@ -921,7 +923,7 @@ cudaError_t dx_launch_fit_grouped(int64_t n_genes, int K, int p, int ps,
     FitArgs A;
     A.epi.wald_coef = -1;
     A.epi.theta = A.epi.sd = A.epi.pval = A.epi.logp = nullptr;
-    A.epi.world = 1; A.epi.rank = 0; A.epi.gene_offset = 0; A.epi.slot_bytes = 0; A.epi.done_ctas = nullptr;
+    A.epi.world = 1; A.epi.rank = 0; A.epi.publish = 1; A.epi.gene_offset = 0; A.epi.slot_bytes = 0; A.epi.done_ctas = nullptr;
     for (int r = 0; r < DX_EX_MAX_WORLD; ++r) A.epi.peer[r] = nullptr;
     if (epi) {
         A.epi.wald_coef = epi->wald_coef;
@@ -943,8 +945,16 @@ cudaError_t dx_launch_fit_grouped(int64_t n_genes, int K, int p, int ps,
     A.a_var = a_var; A.b_var = b_var; A.fim_inv = fim_inv; A.ll_out = ll; A.jac_out = jac; A.niter_out = niter; A.flags_out = flags;
     A.nent = p * (p + 1) / 2;
     const char* impl_env = getenv("DXB200_FIT_IMPL");      // test hook: "g" forces the general kernel (read at every launch)
-    if (!(impl_env && impl_env[0] == 'g') && dx_fit_lane_eligible(K, p, ps, opts) && (reinterpret_cast<uintptr_t>(tail) & 15u) == 0)
-        return dx_launch_fit_lane(A, 0, stream);
+    A.only_deferred = 0;
+    if (!(impl_env && impl_env[0] == 'g') && dx_fit_lane_eligible(K, p, ps, opts) && (reinterpret_cast<uintptr_t>(tail) & 15u) == 0) {
+        // lane-resident kernel (it stores its p-values but leaves the exchange flag alone), then the general kernel for the
+        // genes it left marked (long overflow lists), which publishes for the fit as a whole
+        FitArgs B = A;
+        B.epi.publish = 0;
+        cudaError_t e = dx_launch_fit_lane(B, 0, stream);
+        if (e != cudaSuccess) return e;
+        A.only_deferred = 1;
+    }
     static const char* nz_env = getenv("DXB200_FIT_NZ");         // tuning hook (development only)
     A.nz_max = nz_env ? atoi(nz_env) : 96;   // capacity of the non-zero design-product list (0.9 KB); denser designs use the dense loop
     A.table_doubles = K * p + K * ps + 2 * K + A.nz_max + (2 * ((A.nent + 7) & ~7) + 2 * ((A.nent + 1 + 3) & ~3) + A.nz_max + 7) / 8 + 2;

@@ -2,22 +2,28 @@
 // (/root/reference/diffxpy/testing/tests.py:222-248 -> Estimator.initialize / train_sequence("DEFAULT") / finalize;
 // restated in oracle/nb_glm.py, method_b="newton") for the designs the headline workloads use:
 //   at most 32 design groups, at most 9 location coefficients, ONE dispersion coefficient shared by all groups
-//   (constant dispersion model, DX_OPT_SCALE_CONST).
+//   (constant dispersion model, DX_OPT_SCALE_CONST), genes whose counts all sit in the tail-count table (integers up to 64;
+//   a gene with overflow entries is marked and left to the general kernel, dx_fit_args.cuh).
 //
-// LPG lanes per gene (1, 2, 4, 8 or 16, chosen by the launcher from the gene count), lane l owns the design groups
-// l, l + LPG, ...  With LPG = 1 a THREAD owns a gene: no shuffles, no lane sits idle while another one factorises, and
-// nearly every issued instruction is fp64 arithmetic on useful data -- the sub-warp-per-gene kernel (dx_fit_grouped.cu)
-// spends 84 % of its issue slots on shuffles, shared-memory round trips and index arithmetic.  What a lane keeps:
+// LPG lanes per gene (1, 2, 4, 8 or 16, chosen by the launcher from the gene count).  With LPG = 1 a THREAD owns a gene:
+// no shuffles, no lane sits idle while another one factorises, and nearly every issued instruction is fp64 arithmetic on
+// useful data -- the sub-warp-per-gene kernel (dx_fit_grouped.cu) spends 84 % of its issue slots on shuffles,
+// shared-memory round trips and index arithmetic.  What a lane keeps:
 //   registers      coefficients a[p], the packed lower triangle of X^T W X (45 doubles at p = 9), X^T W ybar, scalars;
 //                  the LDL^T factorisation, both substitutions and the inverse run on compile-time indices only
-//   shared memory  per gene and group: mu, 1/(r + mu), log1p(mu / r), S_k (sum of the counts); per gene: the pooled
-//                  tail counts C(j) = #{y > j}, j < 64 -- laid out [index][gene slot], so a warp's accesses are
-//                  conflict free; per CTA: the distinct design rows, offsets, group sizes, pseudo-inverse
-// Lanes of a gene add their partial X^T W X / X^T W ybar with an xor butterfly, after which every lane holds the same
-// bits and factorises redundantly (SIMT: no extra issue slots).  A trial state overwrites the stored state in place; the
-// rare rejected step re-evaluates the state it came from.
-// Few genes (a gene range of a multi-GPU run) take a larger LPG: the same work per gene spread over more lanes, so
-// the latency of the launch drops while the SMs stay filled.
+//   shared memory  per gene and group: mu, 1/(r + mu), log1p(mu / r), S_k (sum of the counts), the group's likelihood
+//                  term; per gene: the pooled tail counts C(j) = #{y > j}, j < 64 -- laid out [index][gene slot], so a
+//                  warp's accesses are conflict free; per CTA: the distinct design rows, offsets, group sizes,
+//                  pseudo-inverse, log(j + 1)
+// Few genes (a gene range of a multi-GPU run) take a larger LPG, which shortens the latency of the launch.  The lanes of a
+// gene share only the expensive, order-independent part of the work: lane l evaluates exp / log1p / reciprocals of the
+// design groups l, l + LPG, ... and log / reciprocals of the count bins l, l + LPG, ... and stores the values.  EVERY sum
+// over groups or bins is then formed by every lane on its own, from those stored values, in ascending index order with
+// the same instructions (this file is compiled without implicit multiply-add contraction).  So all lanes of a gene hold
+// identical bits without a single shuffle, and -- the point -- the results do not depend on LPG: a gene gets bit-identical
+// coefficients, likelihood, Fisher inverse and p-value whether it is fitted as one of 20 000 genes on one GPU or as one of
+// 2 500 on each of eight.  A trial state overwrites the stored state in place; the rare rejected step re-evaluates the
+// state it came from.
 #include <cstdlib>
 #include "dx_common.cuh"
 #include "dx_internal.h"
@@ -27,11 +33,6 @@ namespace {
 
 extern __shared__ __align__(16) double smem_l[];
 
-template <int L> __device__ __forceinline__ double fl_sum(double v, unsigned m) {
-#pragma unroll
-    for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
-    return v;
-}
 template <int L> __device__ __forceinline__ int fl_max_i(int v, unsigned m) {
 #pragma unroll
     for (int o = L / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(m, v, o));
@@ -114,39 +115,12 @@ __device__ __forceinline__ double fl_log1p(double x) {
 
 __host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }       // lower triangle, j <= i
 
-// ---- overflow entries (counts above 64, non-integer values), constant dispersion: rarely executed, kept out of line ----
-// unreduced lane partial of sum_ovf w [lgamma(r + y) - lgamma(r)]
-__device__ __noinline__ double fl_ovf_T(const float* __restrict__ rec0, int n, int ostep, double r, int sl, int lpg) {
-    const double lr = dx_log(r);
-    double part = 0.0;
-#pragma unroll 1
-    for (int t = sl; t < n; t += lpg) {
-        const float* rec = rec0 + t * ostep;
-        const double y = (double)__ldg(rec);
-        const double w = ostep == 2 ? (double)__float_as_uint(__ldg(rec + 1)) : 1.0;
-        part += w * (dx_lgamma_ratio(r, y) + y * lr);
-    }
-    return part;
-}
-// unreduced lane partials of sum_ovf w [psi(r + y) - psi(r)] and sum_ovf w [psi1(r + y) - psi1(r)]
-__device__ __noinline__ void fl_ovf_DE(const float* __restrict__ rec0, int n, int ostep, double r, int sl, int lpg,
-                                       double& D, double& E) {
-    const double psi_r = dx_digamma(r), psi1_r = dx_trigamma(r);
-#pragma unroll 1
-    for (int t = sl; t < n; t += lpg) {
-        const float* rec = rec0 + t * ostep;
-        const double y = (double)__ldg(rec);
-        const double w = ostep == 2 ? (double)__float_as_uint(__ldg(rec + 1)) : 1.0;
-        D += w * (dx_digamma(r + y) - psi_r);
-        E += w * (dx_trigamma(r + y) - psi1_r);
-    }
-}
-
 struct LaneLayout {          // shared-memory layout of one launch (doubles unless noted)
     int sp;                  // padded number of gene slots per CTA (stride between consecutive indices of a gene array)
     int spc;                 // the same for the uint32 tail-count array
-    int t_xl, t_off, t_isf, t_nk, t_pinv, t_lgrp;      // CTA tables (offsets in doubles)
-    int t_state;             // [4 K][sp]: mu | 1/(r+mu) | log1p(mu/r) | S
+    int t_xl, t_off, t_isf, t_nk, t_pinv, t_lgrp, t_logj;      // CTA tables (offsets in doubles)
+    int t_state;             // [5 K][sp]: mu | 1/(r+mu) | log1p(mu/r) | S | likelihood term
+    int t_bval;              // [64][sp] per-bin logarithms / reciprocals handed from the evaluating lane to all lanes (LPG > 1)
     int t_cj;                // uint32 [64][spc]
     int total_bytes;
 };
@@ -165,8 +139,10 @@ __host__ __device__ inline LaneLayout lane_layout(int K, int p, int KL, bool clo
     L.t_nk = o; o += K;
     L.t_pinv = o; o += closed_form ? p * KL : 0;
     L.t_lgrp = o; o += (K + 7) / 8;
+    L.t_logj = o; o += DX_HIST_BINS;
     o = (o + 1) & ~1;
-    L.t_state = o; o += 4 * K * L.sp;
+    L.t_state = o; o += 5 * K * L.sp;
+    L.t_bval = o; o += (lpg > 1) ? DX_HIST_BINS * L.sp : 0;
     L.t_cj = o; o += (DX_HIST_BINS * L.spc + 1) / 2;
     L.total_bytes = o * 8;
     return L;
@@ -202,7 +178,9 @@ dx_fit_lane_kernel(const FitArgs P) {
         lgrp[k] = (unsigned char)(P.loc_group ? P.loc_group[k] : k);
     }
     if (closed_form) for (int i = tid; i < p * KL; i += blockDim.x) smem_l[L.t_pinv + i] = P.pinv_loc[i];
+    for (int j = tid; j < DX_HIST_BINS; j += blockDim.x) smem_l[L.t_logj + j] = dx_log((double)j + 1.0);
     __syncthreads();
+    const double* logj = smem_l + L.t_logj;
     double n_total = 0.0;
     for (int k = 0; k < K; ++k) n_total += nkt[k];
     const double xs0 = P.xu_scale[0];
@@ -214,6 +192,8 @@ dx_fit_lane_kernel(const FitArgs P) {
     double* st_irm = st_mu + (size_t)K * SP;
     double* st_l1p = st_irm + (size_t)K * SP;
     double* st_S = st_l1p + (size_t)K * SP;
+    double* st_t = st_S + (size_t)K * SP;
+    double* bval = smem_l + L.t_bval + slot;                    // [j * SP]  (LPG > 1 only)
     uint32_t* cj = reinterpret_cast<uint32_t*>(smem_l + L.t_cj) + slot;      // [j * SPC]
 
     for (;;) {
@@ -222,7 +202,12 @@ dx_fit_lane_kernel(const FitArgs P) {
     batch = __shfl_sync(DX_FULL_MASK, batch, 0);
     if ((int64_t)batch * GPW >= P.n_genes) break;
     const int64_t g = (int64_t)batch * GPW + lane / LPG;
-    if (g < P.n_genes) {
+    bool take = g < P.n_genes;
+    if (take && P.ovf_count[g] > DX_LANE_MAX_OVF) {          // overflow entries: this gene goes to the general kernel (dx_fit_args.cuh)
+        if (sl == 0) P.niter_out[g] = -1;
+        take = false;
+    }
+    if (take) {
 
     // ---- sufficient statistics of the gene ---------------------------------------------------------------------------
     const uint32_t* __restrict__ tail = P.tail_all + g * (int64_t)K * DX_HIST_BINS;
@@ -263,64 +248,26 @@ dx_fit_lane_kernel(const FitArgs P) {
         }
     }
     const int ymax = fl_max_i<LPG>(ymax_l, mask);
-    double lgc = 0.0;                                     // sum_i lgamma(y_i + 1) = sum_j C(j) log(j + 1)
 #pragma unroll 1
     for (int j = sl; j < ymax; j += LPG) {                // pooled tail counts: lane <-> count bin
         unsigned acc = 0u;
 #pragma unroll 4
         for (int k = 0; k < K; ++k) acc += __ldg(tail + k * DX_HIST_BINS + j);
         cj[j * SPC] = acc;
-        if (j) lgc = fma((double)acc, fl_log((double)j + 1.0), lgc);
     }
-    // overflow entries: plain list (value, group) or the records of dx_pack_overflow (layout in dx_overflow.cu)
-    int novf = P.ovf_count[g];
-    const float* oval = P.ovf_val + P.indptr[g];
-    const uint8_t* ogrp = P.ovf_group + P.indptr[g];
-    const float* oval_r = oval;
-    int novf_r = novf, ostep = 1;
-    if (novf > 0) {
-        const float* ohead = nullptr;
-        if (P.ovf_packed) {
-            const int n_a = P.ovf_packed[2 * g], n_b = P.ovf_packed[2 * g + 1];
-            if (n_a > 0) {
-                ohead = oval;
-                oval += 8 * K; ogrp += 8 * K;
-                oval_r = oval + 2 * n_a;
-                novf = n_a; novf_r = n_b; ostep = 2;
-            }
-        }
-        if (ohead) {
+    __syncwarp(mask);
+    // from here on every lane forms every sum itself, in ascending index order
+    double lgc = 0.0;                                     // sum_i lgamma(y_i + 1) = sum_j C(j) log(j + 1)
 #pragma unroll 1
-            for (int k = sl; k < K; k += LPG) {
-                const float* h = ohead + 8 * k;
-                const double sy = __hiloint2double(__float_as_int(__ldg(h + 1)), __float_as_int(__ldg(h + 0)));
-                const double sq = __hiloint2double(__float_as_int(__ldg(h + 3)), __float_as_int(__ldg(h + 2)));
-                const double sg = __hiloint2double(__float_as_int(__ldg(h + 5)), __float_as_int(__ldg(h + 4)));
-                const double cn = __hiloint2double(__float_as_int(__ldg(h + 7)), __float_as_int(__ldg(h + 6)));
-                if (cn > 0.0) { st_S[k * SP] += sy; st_mu[k * SP] += sq; lgc += sg; }
-            }
-        } else {
-            // every lane walks the whole list and keeps the entries of its own groups (ascending order: deterministic sums)
+    for (int j = 1; j < ymax; ++j) lgc = fma((double)cj[j * SPC], logj[j], lgc);
+    double sum_all = 0.0, Sisf = 0.0, Qisf = 0.0;       // sum S_k, sum S_k / sf_k, sum Q_k / sf_k^2
 #pragma unroll 1
-            for (int t = 0; t < novf; ++t) {
-                const int k = __ldg(ogrp + t);
-                if (k % LPG == sl && k < K) {
-                    const double y = (double)__ldg(oval + t);
-                    st_S[k * SP] += y; st_mu[k * SP] += y * y; lgc += dx_lgamma(y + 1.0);
-                }
-            }
-        }
-    }
-    double Ssum = 0.0, Sisf = 0.0, Qisf = 0.0;          // lane partials: sum S_k, sum S_k / sf_k, sum Q_k / sf_k^2
-#pragma unroll 1
-    for (int k = sl; k < K; k += LPG) {
+    for (int k = 0; k < K; ++k) {
         const double sk = st_S[k * SP], q = st_mu[k * SP], f = isft[k];
-        Ssum += sk; Sisf = fma(sk, f, Sisf); Qisf = fma(q * f, f, Qisf);
+        sum_all += sk; Sisf = fma(sk, f, Sisf); Qisf = fma(q * f, f, Qisf);
     }
-    lgc = fl_sum<LPG>(lgc, mask);
-    const double sum_all = fl_sum<LPG>(Ssum, mask);
     int flags = 0;
-    if (sum_all == 0.0 && novf == 0) flags |= DX_FLAG_ALL_ZERO;
+    if (sum_all == 0.0) flags |= DX_FLAG_ALL_ZERO;
     __syncwarp(mask);
 
     // ---- initialize (batchglm init_par): every lane holds all coefficients --------------------------------------------
@@ -344,7 +291,7 @@ dx_fit_lane_kernel(const FitArgs P) {
             }
 #pragma unroll 1
             for (int lg = 0; lg < KL; ++lg) st_l1p[lg * SP] = dx_log(st_irm[lg * SP] / st_l1p[lg * SP] + DX_TINY);
-        } else {
+        } else {          // (the same sums in the same order, location rows spread over the lanes)
 #pragma unroll 1
             for (int lg = sl; lg < KL; lg += LPG) {
                 double num = 0.0, den = 0.0;
@@ -370,8 +317,8 @@ dx_fit_lane_kernel(const FitArgs P) {
         for (int i = 0; i < PMAX; ++i) if (i < p) a[i] = dx_clip(P.a_var[(int64_t)i * P.stride + g], DX_ETA_MIN, DX_ETA_MAX);
     }
     if (opts.init_b == DX_INIT_STANDARD) {
-        const double m = fl_sum<LPG>(Sisf, mask) / n_total;
-        const double v = fl_sum<LPG>(Qisf, mask) / n_total - m * m;
+        const double m = Sisf / n_total;
+        const double v = Qisf / n_total - m * m;
         const double denom = fmax(v - m, 2.2227587494850775e-162);
         breg = dx_clip(dx_log(m * m / denom + DX_TINY), DX_ETA_MIN, DX_ETA_MAX);
     } else if (opts.init_b == DX_INIT_GIVEN) {
@@ -380,29 +327,37 @@ dx_fit_lane_kernel(const FitArgs P) {
 
     // ---- state evaluation ---------------------------------------------------------------------------------------------
     // W design groups (or count bins) are evaluated side by side: independent dependency chains for the scheduler
-    constexpr int W = (LPG <= 4) ? 4 : 2;
-    // T(r) = sum_j C(j) log(r + j) + sum_ovf [lgamma(r + y) - lgamma(r)] - sum_i lgamma(y_i + 1)
+    constexpr int W = (LPG <= 4) ? 4 : (LPG == 8 ? 2 : 1);
+    // T(r) = sum_j C(j) log(r + j) - sum_i lgamma(y_i + 1)
     auto eval_T = [&](double r_) -> double {
         double part = 0.0;
+        if (LPG == 1) {
 #pragma unroll 1
-        for (int j0 = sl; j0 < ymax; j0 += W * LPG) {
-            double c[W], l[W];
+            for (int j0 = 0; j0 < ymax; j0 += W) {
+                double c[W], l[W];
 #pragma unroll
-            for (int u = 0; u < W; ++u) {
-                const int j = j0 + u * LPG;
-                c[u] = (j < ymax) ? (double)cj[j * SPC] : 0.0;
-                l[u] = fl_log(r_ + (double)j);
+                for (int u = 0; u < W; ++u) {
+                    const int j = j0 + u;
+                    c[u] = (j < ymax) ? (double)cj[j * SPC] : 0.0;
+                    l[u] = fl_log(r_ + (double)j);
+                }
+#pragma unroll
+                for (int u = 0; u < W; ++u) part = fma(c[u], l[u], part);
             }
-#pragma unroll
-            for (int u = 0; u < W; ++u) part = fma(c[u], l[u], part);
+        } else {
+            __syncwarp(mask);
+#pragma unroll 1
+            for (int j = sl; j < ymax; j += LPG) bval[j * SP] = fl_log(r_ + (double)j);
+            __syncwarp(mask);
+#pragma unroll 4
+            for (int j = 0; j < ymax; ++j) part = fma((double)cj[j * SPC], bval[j * SP], part);
         }
-        if (novf > 0) part += fl_ovf_T(oval_r, novf_r, ostep, r_, sl, LPG);
-        return fl_sum<LPG>(part, mask) - lgc;
+        return part - lgc;
     };
-    // the groups of this lane at coefficients a_ and dispersion r_: eta, mu, 1/(r + mu), log1p(mu / r) (stored) and the
-    // group part of the log-likelihood, sum_k S_k (eta_k - zeta - l_k) - n_k r l_k (returned, reduced over the gene's lanes)
+    // the groups of this lane at coefficients a_ and dispersion r_: eta, mu, 1/(r + mu), log1p(mu / r) and the group's term
+    // of the log-likelihood, S_k (eta_k - zeta - l_k) - n_k r l_k, are stored; the sum of the terms is returned
     auto eval_state = [&](const double (&a_)[PMAX], double r_, double invr_, double zeta_) -> double {
-        double part = 0.0;
+        __syncwarp(mask);
 #pragma unroll 1
         for (int m0 = 0; m0 < GPL; m0 += W) {
             double e[W], mu_[W], ir[W], l[W];
@@ -429,17 +384,21 @@ dx_fit_lane_kernel(const FitArgs P) {
                 if (kk[u] >= 0) {
                     const int k = kk[u];
                     st_mu[k * SP] = mu_[u]; st_irm[k * SP] = ir[u]; st_l1p[k * SP] = l[u];
-                    part += st_S[k * SP] * (e[u] - zeta_ - l[u]) - nkt[k] * r_ * l[u];
+                    st_t[k * SP] = fma(st_S[k * SP], (e[u] - zeta_) - l[u], -((nkt[k] * r_) * l[u]));
                 }
             }
         }
-        return fl_sum<LPG>(part, mask);
+        __syncwarp(mask);
+        double part = 0.0;
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) part += st_t[k * SP];
+        return part;
     };
     // the same at a new dispersion with mu kept (scale step): 1/(r + mu), log1p(mu / r) are overwritten.  eta_k enters the
     // likelihood only through sum_k S_k eta_k, which a scale step does not change: the r-dependent part is returned,
     // - sum_k [(S_k + n_k r) l_k + S_k zeta]
     auto eval_state_r = [&](double r_, double invr_, double zeta_) -> double {
-        double part = 0.0;
+        __syncwarp(mask);
 #pragma unroll 1
         for (int m0 = 0; m0 < GPL; m0 += W) {
             double mu_[W], ir[W], l[W];
@@ -460,21 +419,25 @@ dx_fit_lane_kernel(const FitArgs P) {
                     const int k = kk[u];
                     const double sk = st_S[k * SP];
                     st_irm[k * SP] = ir[u]; st_l1p[k * SP] = l[u];
-                    part -= fma(nkt[k], r_, sk) * l[u] + sk * zeta_;
+                    st_t[k * SP] = fma(fma(nkt[k], r_, sk), l[u], sk * zeta_);
                 }
             }
         }
-        return fl_sum<LPG>(part, mask);
+        __syncwarp(mask);
+        double part = 0.0;
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) part -= st_t[k * SP];
+        return part;
     };
     // sum_k S_k eta_k from the group part of the likelihood at the stored state
     auto sum_S_eta = [&](double grp_, double r_, double zeta_) -> double {
         double part = 0.0;
-#pragma unroll 1
-        for (int k = sl; k < K; k += LPG) {
+#pragma unroll 2
+        for (int k = 0; k < K; ++k) {
             const double sk = st_S[k * SP];
-            part += fma(nkt[k], r_, sk) * st_l1p[k * SP] + sk * zeta_;
+            part += fma(fma(nkt[k], r_, sk), st_l1p[k * SP], sk * zeta_);
         }
-        return grp_ + fl_sum<LPG>(part, mask);
+        return grp_ + part;
     };
 
     double zeta = dx_clip(xs0 * breg, DX_ETA_MIN, DX_ETA_MAX);
@@ -487,35 +450,50 @@ dx_fit_lane_kernel(const FitArgs P) {
     // gradient wrt b = xs0 G, Hessian wrt b = xs0^2 H
     auto scale_terms = [&](double& G, double& H) {
         double D = 0.0, E = 0.0;
+        if (LPG == 1) {
 #pragma unroll 1
-        for (int j0 = sl; j0 < ymax; j0 += W * LPG) {
-            double ci[W], inv[W];
+            for (int j0 = 0; j0 < ymax; j0 += W) {
+                double ci[W], inv[W];
 #pragma unroll
-            for (int u = 0; u < W; ++u) {
-                const int j = j0 + u * LPG;
-                ci[u] = (j < ymax) ? (double)cj[j * SPC] : 0.0;
-                inv[u] = fl_rcp_n(r + (double)j);
+                for (int u = 0; u < W; ++u) {
+                    const int j = j0 + u;
+                    ci[u] = (j < ymax) ? (double)cj[j * SPC] : 0.0;
+                    inv[u] = fl_rcp_n(r + (double)j);
+                }
+#pragma unroll
+                for (int u = 0; u < W; ++u) {
+                    const double t = ci[u] * inv[u];
+                    D += t;
+                    E = fma(-t, inv[u], E);
+                }
             }
-#pragma unroll
-            for (int u = 0; u < W; ++u) {
-                const double t = ci[u] * inv[u];
+        } else {
+            __syncwarp(mask);
+#pragma unroll 1
+            for (int j = sl; j < ymax; j += LPG) bval[j * SP] = fl_rcp_n(r + (double)j);
+            __syncwarp(mask);
+#pragma unroll 4
+            for (int j = 0; j < ymax; ++j) {
+                const double inv = bval[j * SP];
+                const double t = (double)cj[j * SPC] * inv;
                 D += t;
-                E = fma(-t, inv[u], E);
+                E = fma(-t, inv, E);
             }
         }
-        if (novf > 0) fl_ovf_DE(oval_r, novf_r, ostep, r, sl, LPG, D, E);
         double Gs = D, Hs = 0.0;
 #pragma unroll 2
-        for (int k = sl; k < K; k += LPG) {
+        for (int k = 0; k < K; ++k) {
             const double mu = st_mu[k * SP], irm = st_irm[k * SP], l1p = st_l1p[k * SP], S = st_S[k * SP], nk = nkt[k];
-            Gs += fma(nk * mu - S, irm, -nk * l1p);
+            Gs += fma(fma(nk, mu, -S), irm, -(nk * l1p));
             Hs = fma(fma(nk * mu, mu, r * S), irm * irm, Hs);
         }
-        G = r * fl_sum<LPG>(Gs, mask);
-        H = G + r * r * fl_sum<LPG>(E, mask) + r * fl_sum<LPG>(Hs, mask);
+        G = r * Gs;
+        H = fma(r, Hs, fma(r * r, E, G));
     };
 
-    // X^T W X (packed lower triangle) and X^T W ybar at the current state, identical bits in every lane of the gene
+    // X^T W X (packed lower triangle) and X^T W ybar at the current state: every lane runs over all design groups.  The
+    // design rows are the same in every thread, so zero entries are skipped by a uniform branch (categorical designs: 2-3
+    // of 9 entries are non-zero)
     double A[NE], rhs[PMAX];
     auto loc_terms = [&]() {
 #pragma unroll
@@ -523,9 +501,9 @@ dx_fit_lane_kernel(const FitArgs P) {
 #pragma unroll
         for (int i = 0; i < PMAX; ++i) rhs[i] = 0.0;
 #pragma unroll 1
-        for (int k = sl; k < K; k += LPG) {
+        for (int k = 0; k < K; ++k) {
             const double q = r * st_irm[k * SP];
-            const double w1 = nkt[k] * st_mu[k * SP] * q;
+            const double w1 = (nkt[k] * st_mu[k * SP]) * q;
             const double w2 = fma(st_S[k * SP], q, -w1);
             const double* xr = xl + k * p;
             double x[PMAX];
@@ -533,28 +511,13 @@ dx_fit_lane_kernel(const FitArgs P) {
             for (int i = 0; i < PMAX; ++i) x[i] = (i < p) ? xr[i] : 0.0;
 #pragma unroll
             for (int i = 0; i < PMAX; ++i) {
-                if (LPG == 1) {
-                    // one gene per thread: the design row is the same in every thread, so zero entries are skipped by
-                    // a uniform branch (categorical designs: 2-3 of 9 entries are non-zero)
-                    if (x[i] != 0.0) {
-                        rhs[i] = fma(w2, x[i], rhs[i]);
-                        const double t = w1 * x[i];
-#pragma unroll
-                        for (int j = 0; j <= i; ++j) A[tri(i, j)] = fma(t, x[j], A[tri(i, j)]);
-                    }
-                } else {
+                if (x[i] != 0.0) {
                     rhs[i] = fma(w2, x[i], rhs[i]);
                     const double t = w1 * x[i];
 #pragma unroll
                     for (int j = 0; j <= i; ++j) A[tri(i, j)] = fma(t, x[j], A[tri(i, j)]);
                 }
             }
-        }
-        if (LPG > 1) {
-#pragma unroll
-            for (int e = 0; e < NE; ++e) A[e] = fl_sum<LPG>(A[e], mask);
-#pragma unroll
-            for (int i = 0; i < PMAX; ++i) rhs[i] = fl_sum<LPG>(rhs[i], mask);
         }
     };
 
@@ -791,7 +754,7 @@ cudaError_t launch_lane(FitArgs& A, int threads, int grid, size_t smem, cudaStre
     if (e != cudaSuccess) return e;
     e = dx_queue_acquire(stream, &A.queue);
     if (e != cudaSuccess) return e;
-    if (A.epi.world > 1) {
+    if (A.epi.world > 1 && A.epi.publish) {
         e = dx_queue_acquire(stream, &A.epi.done_ctas);
         if (e != cudaSuccess) return e;
     }
@@ -828,10 +791,13 @@ cudaError_t dx_launch_fit_lane(FitArgs& A, int sm_count, cudaStream_t stream) {
     const int smem_cap = 220 * 1024;
     const char* lpg_env = getenv("DXB200_FIT_LPG");        // tuning / test hook: lanes per gene (read at every launch)
     const char* thr_env = getenv("DXB200_FIT_THREADS");    // tuning / test hook: threads per CTA
-    // lanes per gene: as many as keep every gene of the launch resident at once (one CTA per SM, 255 registers per
-    // thread -> at most 256 threads per SM), at most one lane per design group
-    int lpg = 16;
-    while (lpg > 1 && (lpg > A.K || A.n_genes * lpg > (int64_t)sm_count * 256)) lpg >>= 1;
+    // lanes per gene (any choice gives the same bits): a thread per gene is the cheapest in issue slots and wins as soon as
+    // the genes fill the SMs (measured on B200, 16 groups x 9 coefficients: 20k genes 0.26 ms at 1 lane, 0.30 at 2, 0.39 at 4;
+    // 10k genes 0.23 / 0.22 / 0.25; 5k genes 0.22 at 1, 0.175 at 4, 0.195 at 8; 2.5k genes 0.21 at 1, 0.14 at 4 and 8, 0.17 at 16)
+    int lpg = 1;
+    if (A.n_genes * 4 <= (int64_t)sm_count * 256) lpg = 4;
+    else if (A.n_genes * 2 <= (int64_t)sm_count * 256) lpg = 2;
+    while (lpg > 1 && lpg > A.K) lpg >>= 1;
     if (lpg_env) { const int v = atoi(lpg_env); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) lpg = v; }
     // threads per CTA: what the genes need when spread over all SMs, rounded up to whole warps, within the shared memory
     int64_t lanes = A.n_genes * lpg;

@@ -83,6 +83,12 @@ def main():
     print("nnz %d  genes %d  groups %d  p %d" % (nnz, g, k, p))
     for name in a.names:
         # "name@g": the same library with the general K_fit kernel (reserved = 0) -- a reference for the register-resident one
+        # "name:lpg=N": the lane-resident K_fit kernel with N lanes per gene (DXB200_FIT_LPG is read at every launch)
+        os.environ.pop("DXB200_FIT_LPG", None)
+        full_name = name
+        if ":lpg=" in name:
+            name, lpg = name.split(":lpg=")
+            os.environ["DXB200_FIT_LPG"] = lpg
         opts.reserved = 0 if (name.endswith("@g") or a.scale_batch) else a.reserved
         lib = load_variant(name[:-2] if name.endswith("@g") else name)
         tail = torch.zeros((g, k, _lib.DX_HIST_BINS), dtype=torch.int32, device=dev)
@@ -117,7 +123,7 @@ def main():
                  ptr(tail), ptr(ovf_count), ptr(shard.indptr), ptr(ovf_val), ptr(ovf_group), opts, ptr(a_var),
                  ptr(b_var), ptr(fim_inv), ptr(ll), ptr(jac), ptr(niter), ptr(flags), stream_ptr())
 
-        out = [name]
+        out = [full_name]
         for what, fn in (("ingest", ingest), ("fit", fit)):
             if what not in a.what.split(",") and not (what == "ingest"):
                 continue
@@ -150,8 +156,10 @@ def main():
                 da = (ref["a"] - res["a"]).abs().max().item()
                 dll = ((ref["ll"] - res["ll"]).abs() / ref["ll"].abs().clamp(min=1)).max().item()
                 dfim = ((ref["fim"] - res["fim"]).abs() / ref["fim"].abs().clamp(min=1e-300)).nan_to_num(0).max().item()
-                out.append("niter_equal=%s flags_equal=%s max|da|=%.2e rel dll=%.2e rel dfim=%.2e" % (
-                    torch.equal(ref["niter"], res["niter"]), torch.equal(ref["flags"], res["flags"]), da, dll, dfim))
+                bitwise = all(torch.equal(torch.nan_to_num(ref[kk], nan=-7.0), torch.nan_to_num(res[kk], nan=-7.0))
+                              for kk in ("a", "b", "fim", "ll"))
+                out.append("niter_equal=%s flags_equal=%s bitwise_equal=%s max|da|=%.2e rel dll=%.2e rel dfim=%.2e" % (
+                    torch.equal(ref["niter"], res["niter"]), torch.equal(ref["flags"], res["flags"]), bitwise, da, dll, dfim))
         print(" | ".join(out), flush=True)
 
 
