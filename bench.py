@@ -237,6 +237,10 @@ def make_shard(torch, dev, seed, n_genes=N_GENES, n_cells=N_CELLS, chunk=400):
     return shard, cond, batch
 
 
+def g_pieces_ok(shard):
+    return shard.n_genes > 0 and (shard.rows.data_ptr() | shard.vals.data_ptr()) % 16 == 0
+
+
 def slice_shard(torch, shard, lo, hi):
     """Gene range [lo, hi) of a resident shard as its own (16-byte aligned) shard."""
     from diffxpy_b200.device import CountShard
@@ -287,7 +291,12 @@ def main_cuda(args):
         g_lo, g_hi = rank * args.genes, (rank + 1) * args.genes
         nnz_total = None
     gene_order, int_counts = shard.prepare()       # resident-shard metadata (one pass over the values; setup, like the layout itself)
+    pieces, multi_genes = shard.work_list          # K_ingest's units of work (whole genes / parts of large genes), same setup
+    use_pieces = g_pieces_ok(shard) and os.environ.get("DXB200_BENCH_PIECES", "1") == "1"
     ingest_flags = _lib.DX_SHARD_INTEGER_COUNTS if int_counts else 0
+    no_overflow = shard.counts_fit_table          # (same setup pass over the values): every count sits in the tail-count table
+    if no_overflow:
+        ingest_flags |= _lib.DX_SHARD_NO_OVERFLOW
     nnz = shard.nnz
     g = shard.n_genes
     xd = design_for(cond, batch)
@@ -335,8 +344,13 @@ def main_cuda(args):
         e = [ev() for _ in range(5)] if record else None
         if record:
             e[0].record()
-        _lib.call("dx_group_suffstats_ex", g, ptr(shard.indptr), ptr(shard.rows), ptr(shard.vals), ptr(cell_group), k,
-                  ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), ptr(gene_order), ingest_flags, stream_ptr())
+        if use_pieces:
+            _lib.call("dx_group_suffstats_pieces", g, ptr(shard.indptr), ptr(shard.rows), ptr(shard.vals), ptr(cell_group), k,
+                      ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), ptr(pieces), int(pieces.shape[0]),
+                      ptr(multi_genes) if multi_genes.shape[0] else None, int(multi_genes.shape[0]), ingest_flags, stream_ptr())
+        else:
+            _lib.call("dx_group_suffstats_ex", g, ptr(shard.indptr), ptr(shard.rows), ptr(shard.vals), ptr(cell_group), k,
+                      ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), ptr(gene_order), ingest_flags, stream_ptr())
         if record:
             e[1].record()
         # what SuffStats.pack_overflow() does in the estimator: nothing to pack on this workload (gene means <= 1)
@@ -346,7 +360,8 @@ def main_cuda(args):
             e[2].record()
         # K_fit + the Wald row of `condition` per gene (+ N > 1: the p-value goes straight into every rank's exchange slot)
         _lib.call("dx_nb_fit_wald_grouped", g, k, p, ps, ptr(d_xl), ptr(d_xs), None, ptr(d_nk), ptr(d_pinv), None, k,
-                  ptr(tail), ptr(ovf_count), ptr(shard.indptr), ptr(ovf_val), ptr(ovf_group), ptr(ovf_packed), opts,
+                  ptr(tail), ptr(ovf_count), ptr(shard.indptr), None if no_overflow else ptr(ovf_val),
+                  None if no_overflow else ptr(ovf_group), ptr(ovf_packed), opts,
                   ptr(a_var), ptr(b_var), ptr(fim_inv), ptr(ll), ptr(jac), ptr(niter), ptr(flags),
                   1, ptr(rows_out[0]), ptr(rows_out[1]), ptr(rows_out[2]), ptr(rows_out[3]),
                   exchange.peer_ptrs if exchange is not None else None, world, rank,

@@ -17,6 +17,7 @@ DX_MAX_COEF = 32
 
 DX_SHARD_INTEGER_COUNTS = 1
 DX_GROUPS_FIT_U16 = 2
+DX_SHARD_NO_OVERFLOW = 4
 DX_OPT_SCALE_CONST = 1
 DX_IPC_HANDLE_BYTES = 64
 DX_INIT_GIVEN, DX_INIT_STANDARD, DX_INIT_CLOSED_FORM, DX_INIT_ALL_ZERO = 0, 1, 2, 3
@@ -47,6 +48,7 @@ SIGNATURES = {
     "dx_device_sm_count": [C.POINTER(C.c_int)],
     "dx_group_suffstats": [_I64, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P],
     "dx_group_suffstats_ex": [_I64, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _I32, _P],
+    "dx_group_suffstats_pieces": [_I64, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _I64, _P, _I64, _I32, _P],
     "dx_gene_moments": [_I64, _P, _P, _P, _P, _P, _P, _P],
     "dx_nb_fit_grouped": [_I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, C.POINTER(DxFitOpts),
                           _P, _P, _P, _P, _P, _P, _P, _P],

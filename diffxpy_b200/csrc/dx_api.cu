@@ -62,9 +62,28 @@ int dx_group_suffstats_ex(int64_t n_genes, const int64_t* indptr, const int32_t*
     DX_CHECK(n_genes >= 0, "dx_group_suffstats_ex: n_genes < 0");
     DX_CHECK(n_groups >= 1 && n_groups <= DX_MAX_GROUPS, "dx_group_suffstats_ex: n_groups must be in 1..255");
     DX_CHECK(indptr && cell_group && hist && ovf_count, "dx_group_suffstats_ex: null pointer");
-    DX_CHECK((flags & ~(DX_SHARD_INTEGER_COUNTS | DX_GROUPS_FIT_U16)) == 0, "dx_group_suffstats_ex: unknown flag");
+    DX_CHECK((flags & ~(DX_SHARD_INTEGER_COUNTS | DX_GROUPS_FIT_U16 | DX_SHARD_NO_OVERFLOW)) == 0, "dx_group_suffstats_ex: unknown flag");
     DX_CUDA(dx_launch_ingest(n_genes, indptr, rows, vals, cell_group, n_groups, hist, ovf_count, ovf_val, ovf_group,
                              gene_order, flags, sm_count_cached(), (cudaStream_t)stream), "dx_group_suffstats_ex");
+    return DX_OK;
+}
+
+int dx_group_suffstats_pieces(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,
+                              const uint8_t* cell_group, int32_t n_groups,
+                              uint32_t* hist, int32_t* ovf_count, float* ovf_val, uint8_t* ovf_group,
+                              const int32_t* pieces, int64_t n_pieces, const int32_t* multi_genes, int64_t n_multi,
+                              int32_t flags, void* stream) {
+    DX_CHECK(n_genes >= 0, "dx_group_suffstats_pieces: n_genes < 0");
+    DX_CHECK(n_groups >= 1 && n_groups <= DX_MAX_GROUPS, "dx_group_suffstats_pieces: n_groups must be in 1..255");
+    DX_CHECK(indptr && cell_group && hist && ovf_count, "dx_group_suffstats_pieces: null pointer");
+    DX_CHECK(pieces && n_pieces >= n_genes && n_multi >= 0 && (n_multi == 0 || multi_genes),
+             "dx_group_suffstats_pieces: the work list must hold at least one piece per gene");
+    DX_CHECK((reinterpret_cast<uintptr_t>(pieces) & 15u) == 0, "dx_group_suffstats_pieces: the work list must be 16-byte aligned");
+    DX_CHECK((flags & ~(DX_SHARD_INTEGER_COUNTS | DX_GROUPS_FIT_U16 | DX_SHARD_NO_OVERFLOW)) == 0,
+             "dx_group_suffstats_pieces: unknown flag");
+    DX_CUDA(dx_launch_ingest(n_genes, indptr, rows, vals, cell_group, n_groups, hist, ovf_count, ovf_val, ovf_group,
+                             nullptr, flags, sm_count_cached(), (cudaStream_t)stream, pieces, n_pieces, multi_genes, n_multi),
+            "dx_group_suffstats_pieces");
     return DX_OK;
 }
 

@@ -582,7 +582,7 @@ dx_fit_grouped_kernel(const FitArgs P) {
     const int sl = s.sl;
     const unsigned mask = s.mask;
     s.tail = P.tail_all + g * (int64_t)K * DX_HIST_BINS;
-    s.novf = P.ovf_count[g];
+    s.novf = P.ovf_val ? P.ovf_count[g] : 0;          // (no list: the caller vouches that no gene has overflow entries)
     s.oval = P.ovf_val + P.indptr[g];
     s.ogrp = P.ovf_group + P.indptr[g];
     s.oval_r = s.oval; s.novf_r = s.novf; s.ostep = 1; s.ohead = nullptr;
@@ -949,6 +949,7 @@ cudaError_t dx_launch_fit_grouped(int64_t n_genes, int K, int p, int ps,
     if (!(impl_env && impl_env[0] == 'g') && dx_fit_lane_eligible(K, p, ps, opts) && (reinterpret_cast<uintptr_t>(tail) & 15u) == 0) {
         // lane-resident kernel (it stores its p-values but leaves the exchange flag alone), then the general kernel for the
         // genes it left marked (long overflow lists), which publishes for the fit as a whole
+        if (!ovf_val) return dx_launch_fit_lane(A, 0, stream);      // no overflow lists at all: nothing can be left over
         FitArgs B = A;
         B.epi.publish = 0;
         cudaError_t e = dx_launch_fit_lane(B, 0, stream);

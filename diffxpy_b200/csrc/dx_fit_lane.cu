@@ -203,7 +203,7 @@ dx_fit_lane_kernel(const FitArgs P) {
     if ((int64_t)batch * GPW >= P.n_genes) break;
     const int64_t g = (int64_t)batch * GPW + lane / LPG;
     bool take = g < P.n_genes;
-    if (take && P.ovf_count[g] > DX_LANE_MAX_OVF) {          // overflow entries: this gene goes to the general kernel (dx_fit_args.cuh)
+    if (take && P.ovf_val && P.ovf_count[g] > DX_LANE_MAX_OVF) {          // overflow entries: this gene goes to the general kernel (dx_fit_args.cuh)
         if (sl == 0) P.niter_out[g] = -1;
         take = false;
     }

@@ -262,7 +262,7 @@ constexpr int NS = DX_TMA_NS;     // ring stages per warp
 constexpr int TILE = DX_TMA_TILE; // elements per stage
 constexpr int TU = TILE / 32;     // elements per lane and tile
 constexpr int NG = 8;             // gene descriptors in flight per warp (>= NS + 2)
-constexpr int DX_INGEST_MODE_GENES = 0, DX_INGEST_MODE_SPLIT = 1, DX_INGEST_MODE_REDO = 2;
+constexpr int DX_INGEST_MODE_GENES = 0, DX_INGEST_MODE_SPLIT = 1, DX_INGEST_MODE_REDO = 2, DX_INGEST_MODE_PIECES = 3;
 
 __device__ __forceinline__ uint32_t dx_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void dx_mbar_init(uint32_t bar, uint32_t count) {
@@ -309,7 +309,8 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
                      const float* __restrict__ vals, const uint8_t* __restrict__ cell_group, int K, int ysh, int NW, int NWA,
                      uint32_t* __restrict__ hist_out, int32_t* __restrict__ ovf_count,
                      float* __restrict__ ovf_val, uint8_t* __restrict__ ovf_group, unsigned int* __restrict__ queue,
-                     const int32_t* __restrict__ gene_order, int warp_bytes, int mode) {
+                     const int32_t* __restrict__ gene_order, int warp_bytes, int mode, int split_rpw,
+                     const int4* __restrict__ pieces, int64_t n_pieces) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* base = smem_raw + (size_t)warp * warp_bytes;
@@ -357,7 +358,7 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
         sp_lo = __ldg(indptr);
         sp_hi = __ldg(indptr + n_genes);
         const long long span = sp_hi - sp_lo;
-        const long long want = span / ((long long)gridDim.x * (blockDim.x >> 5) * 6) + 1;      // ~6 ranges per warp
+        const long long want = span / ((long long)gridDim.x * (blockDim.x >> 5) * split_rpw) + 1;      // ~split_rpw ranges per warp
         sp_seg = ((want + TILE - 1) / TILE) * TILE;
         if (sp_seg < 4 * TILE) sp_seg = 4 * TILE;
         if (sp_seg > 128 * TILE) sp_seg = 128 * TILE;
@@ -366,6 +367,7 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
         if (i_tiles == 0) {
             unsigned gq = 0;
             long long st_ = 0, en_ = 0;
+            int piece_multi = (mode == DX_INGEST_MODE_SPLIT) ? 1 : 0;      // 1: tail counts are added to the output (part of a gene)
             if (mode == DX_INGEST_MODE_SPLIT) {
                 for (;;) {
                     if (sp_pos >= sp_end) {                      // next range of the shard
@@ -391,6 +393,18 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
                     sp_pos = en_;
                     if (en_ > st_) break;                        // (genes without entries yield no piece)
                 }
+            } else if (mode == DX_INGEST_MODE_PIECES) {
+                // the queue hands out the pieces of the resident shard's work list (dx_group_suffstats_pieces): whole genes,
+                // and equal parts of the genes that are too large to be one unit of work
+                unsigned q = 0;
+                if (lane == 0) q = atomicAdd(queue, 1u);
+                q = __shfl_sync(DX_FULL_MASK, q, 0);
+                if ((int64_t)q >= n_pieces) { done_issue = true; return; }
+                const int4 pc = __ldg(pieces + q);              // gene, first element (relative to the gene), elements, part of a gene?
+                gq = (unsigned)pc.x;
+                st_ = __ldg(indptr + gq) + pc.y;
+                en_ = st_ + pc.z;
+                piece_multi = pc.w;
             } else {
                 for (;;) {
                     if (lane == 0) gq = atomicAdd(queue, 1u);
@@ -404,7 +418,7 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
             }
             if (lane == 0) {
                 GeneDesc d;
-                d.start = st_; d.end = en_; d.gene = (int)gq; d.pad = 0;
+                d.start = st_; d.end = en_; d.gene = (int)gq; d.pad = piece_multi;
                 s_gene[g_head % NG] = d;
             }
             ++g_head;
@@ -557,7 +571,7 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
                 const bool isbin = ((unsigned)(y - 1) < (unsigned)DX_HIST_BINS) && (__int2float_rn(y) == v[u]);
                 const bool ovf = !isbin && v[u] != 0.0f && k[u] < (unsigned)K;
                 const unsigned bal = __ballot_sync(DX_FULL_MASK, ovf);
-                if (ovf && mode != DX_INGEST_MODE_SPLIT) {      // (split pieces only count: the redo pass writes the list)
+                if (ovf && !s_gene[m.slot].pad) {      // (parts of a gene only count: the redo pass writes the list)
                     const int64_t pos = obase + ovf_base + __popc(bal & ((1u << lane) - 1u));
                     ovf_val[pos] = v[u];
                     ovf_group[pos] = (uint8_t)k[u];
@@ -585,7 +599,7 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
             }
             const unsigned tot_lo = __shfl_sync(DX_FULL_MASK, plo, 31), tot_hi = __shfl_sync(DX_FULL_MASK, phi, 31);
             const unsigned t_hi = tot_hi - phi + hi, t_lo = tot_hi + (tot_lo - plo + lo);
-            if (mode == DX_INGEST_MODE_SPLIT) {          // a piece of the gene: tail counts are additive
+            if (gd.pad) {          // a part of the gene: tail counts are additive
                 if (t_hi) atomicAdd(out + kk * DX_HIST_BINS + 32 + lane, t_hi);
                 if (t_lo) atomicAdd(out + kk * DX_HIST_BINS + lane, t_lo);
             } else {
@@ -593,7 +607,7 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
                 out[kk * DX_HIST_BINS + lane] = t_lo;
             }
         }
-        if (mode == DX_INGEST_MODE_SPLIT) {
+        if (gd.pad) {
             if (lane == 0 && ovf_base) atomicAdd(ovf_count + g, (int32_t)ovf_base);
         } else if (lane == 0) {
             ovf_count[g] = (int32_t)ovf_base;
@@ -658,10 +672,20 @@ cudaError_t dx_queue_acquire(cudaStream_t stream, unsigned int** out) {
     return cudaMemsetAsync(*out, 0, sizeof(unsigned int), stream);
 }
 
+// rows of the tail-count table (and the overflow counts) of the genes that are counted in parts
+__global__ void __launch_bounds__(128)
+dx_zero_genes_kernel(const int32_t* __restrict__ genes, int K, uint32_t* __restrict__ hist, int32_t* __restrict__ ovf_count) {
+    const int64_t g = genes[blockIdx.x];
+    uint4* row = reinterpret_cast<uint4*>(hist + g * (int64_t)K * DX_HIST_BINS);
+    for (int i = threadIdx.x; i < K * DX_HIST_BINS / 4; i += 128) row[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x == 0) ovf_count[g] = 0;
+}
+
 cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,
                              const uint8_t* cell_group, int K, uint32_t* hist, int32_t* ovf_count,
                              float* ovf_val, uint8_t* ovf_group, const int32_t* gene_order, int flags, int sm_count,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, const int32_t* pieces, int64_t n_pieces, const int32_t* multi_genes,
+                             int64_t n_multi) {
     if (n_genes <= 0) return cudaSuccess;
     const int YP = dx_ingest_private_bins(K);
     int ysh = -1;
@@ -695,10 +719,37 @@ cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32
         // duration, so the shard is cut into equal ranges of non-zeros instead (pieces of genes, tail counts added with
         // atomics into a zeroed table); genes with overflow entries are then redone gene-wise, which writes their lists in
         // the canonical order.  DXB200_INGEST_SPLIT=0 / 1 forces the mode (development hook).
+        if (pieces && n_pieces > 0 && (reinterpret_cast<uintptr_t>(pieces) & 15u) == 0) {
+            // work list prepared with the resident shard: genes that are parts of the list are zeroed first, added to by
+            // their parts, and -- if they turn out to have overflow entries -- counted once more as whole genes, which
+            // writes their lists in the canonical order
+            if (n_multi > 0) {
+                dx_zero_genes_kernel<<<(unsigned)n_multi, 128, 0, stream>>>(multi_genes, K, hist, ovf_count);
+                e = cudaGetLastError();
+                if (e != cudaSuccess) return e;
+            }
+            kern<<<(unsigned)sm_count, warps * 32, smem, stream>>>(n_genes, indptr, rows, vals, cell_group, K, ysh, NW, NWA, hist,
+                                                                   ovf_count, ovf_val, ovf_group, queue, nullptr, warp_bytes,
+                                                                   DX_INGEST_MODE_PIECES, 0, reinterpret_cast<const int4*>(pieces),
+                                                                   n_pieces);
+            e = cudaGetLastError();
+            if (e != cudaSuccess || n_multi <= 0 || (flags & DX_SHARD_NO_OVERFLOW)) return e;
+            unsigned int* queue2 = nullptr;
+            e = dx_queue_acquire(stream, &queue2);
+            if (e != cudaSuccess) return e;
+            int64_t grid2 = (n_multi + warps - 1) / warps;
+            if (grid2 > sm_count) grid2 = sm_count;
+            kern<<<(unsigned)grid2, warps * 32, smem, stream>>>(n_multi, indptr, rows, vals, cell_group, K, ysh, NW, NWA, hist,
+                                                                ovf_count, ovf_val, ovf_group, queue2, multi_genes, warp_bytes,
+                                                                DX_INGEST_MODE_REDO, 0, nullptr, 0);
+            return cudaGetLastError();
+        }
         const char* split_env = getenv("DXB200_INGEST_SPLIT");
         bool split = n_genes < 2 * (int64_t)sm_count * warps;
         if (split_env) split = split_env[0] == '1';
         if (split) {
+            const char* rpw_env = getenv("DXB200_INGEST_RPW");          // tuning hook: ranges per warp of the split mode
+            const int split_rpw = (rpw_env && atoi(rpw_env) >= 1 && atoi(rpw_env) <= 64) ? atoi(rpw_env) : 2;
             // a piece never holds more than 128 tiles: its counts always fit 16-bit on-chip bins (the shared-memory
             // layout sized for 32-bit bins holds them as well)
             auto kern_split = io ? dx_ingest_tma_kernel<true, true> : dx_ingest_tma_kernel<false, true>;
@@ -710,9 +761,9 @@ cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32
             if (e != cudaSuccess) return e;
             kern_split<<<(unsigned)sm_count, warps * 32, smem, stream>>>(n_genes, indptr, rows, vals, cell_group, K, ysh, NW, NWA,
                                                                          hist, ovf_count, ovf_val, ovf_group, queue, nullptr,
-                                                                         warp_bytes, DX_INGEST_MODE_SPLIT);
+                                                                         warp_bytes, DX_INGEST_MODE_SPLIT, split_rpw, nullptr, 0);
             e = cudaGetLastError();
-            if (e != cudaSuccess) return e;
+            if (e != cudaSuccess || (flags & DX_SHARD_NO_OVERFLOW)) return e;
             unsigned int* queue2 = nullptr;
             e = dx_queue_acquire(stream, &queue2);
             if (e != cudaSuccess) return e;
@@ -720,14 +771,14 @@ cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32
             if (grid2 > n_genes) grid2 = n_genes;
             kern<<<(unsigned)grid2, warps * 32, smem, stream>>>(n_genes, indptr, rows, vals, cell_group, K, ysh, NW, NWA, hist,
                                                                 ovf_count, ovf_val, ovf_group, queue2, nullptr, warp_bytes,
-                                                                DX_INGEST_MODE_REDO);
+                                                                DX_INGEST_MODE_REDO, 0, nullptr, 0);
             return cudaGetLastError();
         }
         int64_t grid = sm_count;                    // persistent CTAs; the warps pull genes from the queue
         if (grid > n_genes) grid = n_genes;
         kern<<<(unsigned)grid, warps * 32, smem, stream>>>(n_genes, indptr, rows, vals, cell_group, K, ysh, NW, NWA, hist,
                                                            ovf_count, ovf_val, ovf_group, queue, gene_order, warp_bytes,
-                                                           DX_INGEST_MODE_GENES);
+                                                           DX_INGEST_MODE_GENES, 0, nullptr, 0);
         return cudaGetLastError();
     }
     // ---- CTA-per-gene variant (any K, any alignment) -------------------------------------------------------------

@@ -12,7 +12,8 @@ cudaError_t dx_queue_acquire(cudaStream_t stream, unsigned int** out);
 cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,
                              const uint8_t* cell_group, int K, uint32_t* hist, int32_t* ovf_count,
                              float* ovf_val, uint8_t* ovf_group, const int32_t* gene_order, int flags, int sm_count,
-                             cudaStream_t stream);
+                             cudaStream_t stream, const int32_t* pieces = nullptr, int64_t n_pieces = 0,
+                             const int32_t* multi_genes = nullptr, int64_t n_multi = 0);
 cudaError_t dx_launch_gene_moments(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,
                                    const double* inv_sf, double* sum1, double* sum2, cudaStream_t stream);
 // what K_fit does for a gene after finalize (both nullable parts): the single-coefficient Wald row, and on several GPUs

@@ -81,6 +81,7 @@ class CountShard:
         self._nnz = None
         self._order = None
         self._int = None
+        self._pieces = None
 
     @property
     def nnz(self):
@@ -105,8 +106,63 @@ class CountShard:
             self._int = bool(((v >= 0) & (v < 16777216.0) & (v == torch.floor(v))).all().item()) if v.numel() else True
         return self._int
 
+    @property
+    def counts_fit_table(self):
+        """True when every stored value is an integer in 1..64: no gene has overflow entries, every count sits in the
+        tail-count table (DX_SHARD_NO_OVERFLOW: K_ingest skips the pass that writes overflow lists of cut genes, K_fit the
+        launch for genes with overflow entries)."""
+        if getattr(self, "_fit64", None) is None:
+            v = self.vals
+            self._fit64 = bool(self.integer_counts and (v.numel() == 0 or float(v.max().item()) <= 64.0))
+        return self._fit64
+
+    INGEST_TILE = 256          # elements per bulk-copy stage of K_ingest: pieces start on multiples of it
+    INGEST_WARPS = 20          # resident warps per SM of K_ingest (16 design groups)
+
+    @property
+    def work_list(self):
+        """(pieces int32[n][4], multi_genes int32[m]) for dx_group_suffstats_pieces: K_ingest's units of work, largest
+        first.  A gene is one piece unless it holds more than 60 % of a warp's share of the shard (non-zeros / resident warps),
+        in which case it is cut into equal parts of about a quarter of that share (multiples of 256 elements, at least 4096).
+        With 20k genes on one GPU no gene is that large and the list is the largest-first gene order; with 2.5k genes (an
+        eighth of the matrix) most genes are cut, and the pass stays balanced."""
+        if self._pieces is None:
+            dev = self.device
+            counts = (self.indptr[1:] - self.indptr[:-1])
+            g = self.n_genes
+            if g == 0:
+                self._pieces = (torch.zeros((0, 4), dtype=torch.int32, device=dev), torch.zeros(0, dtype=torch.int32, device=dev))
+                return self._pieces
+            sm = C.c_int(0)
+            _lib.call("dx_device_sm_count", C.byref(sm))
+            n_warps = max(1, sm.value) * self.INGEST_WARPS
+            tile = self.INGEST_TILE
+            share = -(-int(self.nnz) // n_warps)                      # non-zeros per warp of an evenly spread pass
+            target = max(4096, share // 4)
+            target = -(-target // tile) * tile
+            cut_above = max((3 * target) // 2, (6 * share) // 10)     # genes beyond 60 % of a warp's share are cut
+            n_p = torch.where(counts > cut_above, (counts + target - 1) // target, torch.ones_like(counts))
+            part = ((counts + n_p - 1) // n_p + tile - 1) // tile * tile           # elements per part of a cut gene
+            n_p = torch.where(n_p > 1, (counts + part - 1) // torch.clamp(part, min=1), n_p)
+            n_p = torch.clamp(n_p, min=1)
+            gene = torch.repeat_interleave(torch.arange(g, device=dev), n_p)
+            first = torch.cumsum(n_p, 0) - n_p
+            j = torch.arange(gene.shape[0], device=dev) - first[gene]
+            start = j * part[gene]
+            length = torch.minimum(part[gene], counts[gene] - start)
+            length = torch.where(n_p[gene] > 1, length, counts[gene])
+            start = torch.where(n_p[gene] > 1, start, torch.zeros_like(start))
+            multi = (n_p[gene] > 1)
+            order = torch.argsort(length, descending=True, stable=True)
+            pieces = torch.stack([gene, start, length, multi.to(torch.int64)], dim=1)[order].to(torch.int32).contiguous()
+            multi_genes = torch.nonzero(n_p > 1, as_tuple=False)[:, 0].to(torch.int32).contiguous()
+            self._pieces = (pieces, multi_genes)
+        return self._pieces
+
     def prepare(self):
         """Materialise the cached shard properties (setup time, like the CSR -> CSC conversion)."""
+        self.work_list
+        self.counts_fit_table
         return self.gene_order, self.integer_counts
 
     @property
@@ -204,11 +260,21 @@ class CountShard:
         ovf_val = torch.empty(max(self.vals.shape[0], 1), dtype=torch.float32, device=dev)
         ovf_group = torch.empty(max(self.vals.shape[0], 1), dtype=torch.uint8, device=dev)
         flags = _lib.DX_SHARD_INTEGER_COUNTS if self.integer_counts else 0
+        if self.counts_fit_table:
+            flags |= _lib.DX_SHARD_NO_OVERFLOW
         if int(torch.bincount(cell_group.to(torch.int64), minlength=256)[:255].max().item()) <= 65535:
             flags |= _lib.DX_GROUPS_FIT_U16
-        _lib.call("dx_group_suffstats_ex", g, ptr(self.indptr), ptr(self.rows), ptr(self.vals), ptr(cell_group),
-                  int(n_groups), ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), ptr(self.gene_order), flags,
-                  stream_ptr())
+        pieces, multi = self.work_list
+        import os
+        if g > 0 and (self.rows.data_ptr() | self.vals.data_ptr()) % 16 == 0 and n_groups <= 32 and \
+                os.environ.get("DXB200_INGEST_PIECES", "1") != "0":          # (test hook: "0" = the gene-wise entry point)
+            _lib.call("dx_group_suffstats_pieces", g, ptr(self.indptr), ptr(self.rows), ptr(self.vals), ptr(cell_group),
+                      int(n_groups), ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), ptr(pieces), int(pieces.shape[0]),
+                      ptr(multi) if multi.shape[0] else None, int(multi.shape[0]), flags, stream_ptr())
+        else:
+            _lib.call("dx_group_suffstats_ex", g, ptr(self.indptr), ptr(self.rows), ptr(self.vals), ptr(cell_group),
+                      int(n_groups), ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), ptr(self.gene_order), flags,
+                      stream_ptr())
         return SuffStats(self, tail, ovf_count, ovf_val, ovf_group, n_groups)
 
     def gene_moments(self, inv_sf=None):

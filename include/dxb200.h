@@ -102,10 +102,28 @@ int dx_group_suffstats(int64_t n_genes, const int64_t* indptr, const int32_t* ro
  *          16-bit bins, which lets more warps stay resident */
 #define DX_SHARD_INTEGER_COUNTS 1
 #define DX_GROUPS_FIT_U16 2      /* no design group has more than 65535 cells (verified by the caller): 16-bit on-chip bins */
+#define DX_SHARD_NO_OVERFLOW 4   /* every stored value is an integer in 1..64 (verified by the caller): no gene has overflow
+                                    entries, so the pass that rewrites the overflow lists of genes counted in parts is skipped */
 int dx_group_suffstats_ex(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,
                           const uint8_t* cell_group, int32_t n_groups,
                           uint32_t* hist, int32_t* ovf_count, float* ovf_val, uint8_t* ovf_group,
                           const int32_t* gene_order, int32_t flags, void* stream);
+
+/* Same, driven by a work list that is prepared once with the resident shard (like gene_order): the unit of work is a
+ * PIECE, a whole gene or one of several equal parts of a gene that is too large to be one unit -- with few genes per GPU
+ * (a gene range of a multi-GPU run) the largest gene would otherwise set the duration of the pass.
+ *   pieces[n_pieces][4] int32, 16-byte aligned: {gene, first element relative to the gene's start (a multiple of 256),
+ *                       number of elements, 1 if the gene has several pieces else 0}; every gene appears at least once
+ *                       (an empty gene as one piece of 0 elements); the queue hands them out in list order (largest
+ *                       first shortens the tail)
+ *   multi_genes[n_multi] the genes with several pieces: their rows are zeroed first, their parts add tail counts with
+ *                       atomics, and those that turn out to hold overflow entries are counted once more as whole genes
+ *                       (so the overflow lists are the same as in the gene-wise pass).  Results do not depend on the list. */
+int dx_group_suffstats_pieces(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,
+                              const uint8_t* cell_group, int32_t n_groups,
+                              uint32_t* hist, int32_t* ovf_count, float* ovf_val, uint8_t* ovf_group,
+                              const int32_t* pieces, int64_t n_pieces, const int32_t* multi_genes, int64_t n_multi,
+                              int32_t flags, void* stream);
 
 /* ---- K_fit (grouped): the whole batchglm training schedule + finalize, one warp per gene ----------
  * Replaces Estimator.initialize / train_sequence / finalize (tests.py:222-248) when the rows of
@@ -158,7 +176,8 @@ int dx_nb_fit_grouped_packed(int64_t n_genes, int32_t n_groups, int32_t p_loc, i
  * launch.  peer_bufs: HOST array of `world` device pointers (own buffer at [rank]); world == 1: no exchange, peer_bufs
  * may be null.
  * opts->reserved & DX_OPT_SCALE_CONST (p_scale == 1 and the same dispersion design value in every group, verified by
- * the caller) with n_groups <= 32 and p_loc <= 16 selects the register-resident kernel (dx_fit_fast.cu). */
+ * the caller) with n_groups <= 32 and p_loc <= 16 selects the register-resident kernel (dx_fit_fast.cu).  * ovf_val / ovf_group may be NULL when the caller knows that no gene has overflow entries (every stored value an integer in
+ * 1..64, DX_SHARD_NO_OVERFLOW): the launch that fits genes with overflow entries is then skipped. */
 int dx_nb_fit_wald_grouped(int64_t n_genes, int32_t n_groups, int32_t p_loc, int32_t p_scale,
                            const double* xu_loc, const double* xu_scale, const double* offset, const double* n_k,
                            const double* pinv_loc, const int32_t* loc_group, int32_t n_loc_groups,

@@ -118,7 +118,9 @@ def _assert_same_fit(fast, gen):
     np.testing.assert_allclose(fast["a"][:, reg], gen["a"][:, reg], rtol=1e-6, atol=1e-6)
     np.testing.assert_allclose(fast["b"][:, reg], gen["b"][:, reg], rtol=1e-5, atol=1e-5)
     scale = np.abs(gen["fi"]).max(axis=(1, 2), keepdims=True)
-    assert np.all((np.abs(fast["fi"] - gen["fi"]) <= 1e-4 * scale + 1e-300)[reg])      # (the dispersion agrees to 1e-5 + 1e-5 b)
+    both_nan = np.isnan(fast["fi"]) & np.isnan(gen["fi"])          # (a singular Fisher information is NaN in both)
+    scale = np.nan_to_num(scale, nan=1.0)
+    assert np.all((both_nan | (np.abs(fast["fi"] - gen["fi"]) <= 1e-4 * scale + 1e-300))[reg])      # (the dispersion agrees to 1e-5 + 1e-5 b)
     np.testing.assert_allclose(fast["sd"][reg], gen["sd"][reg], rtol=1e-6)
     ok = reg & (gen["pv"] > 1e-11)
     np.testing.assert_allclose(fast["lp"][ok], gen["lp"][ok], rtol=1e-5, atol=1e-9)
@@ -366,22 +368,36 @@ def test_ingest_split_mode_equals_gene_mode(lib, k, monkeypatch):
     grp[::501] = 255
     grp_d = torch.from_numpy(grp).cuda()
     res = {}
-    for mode in ("0", "1"):
-        monkeypatch.setenv("DXB200_INGEST_SPLIT", mode)
+    # "0" / "1": the gene-wise entry point in its one-warp-per-gene and equal-ranges modes; "p": the work-list entry point
+    # (dx_group_suffstats_pieces, what CountShard.group_suffstats calls by default: here the genes above 6144 entries are cut)
+    for mode in ("0", "1", "p"):
+        if mode == "p":
+            monkeypatch.delenv("DXB200_INGEST_SPLIT")
+            monkeypatch.delenv("DXB200_INGEST_PIECES")
+        else:
+            monkeypatch.setenv("DXB200_INGEST_SPLIT", mode)
+            monkeypatch.setenv("DXB200_INGEST_PIECES", "0")
         shard = CountShard.from_host(x)
+        if mode == "p":
+            pieces, multi = shard.work_list
+            pc = pieces.cpu().numpy()
+            assert multi.shape[0] >= 5 and pc[:, 3].sum() > multi.shape[0]          # several genes are cut into parts
+            assert np.array_equal(np.bincount(pc[:, 0], weights=pc[:, 2], minlength=len(lens)).astype(np.int64), np.array(lens))
         suff = shard.group_suffstats(grp_d, k)
         torch.cuda.synchronize()
         res[mode] = (suff.tail.cpu().numpy().view(np.uint32), suff.ovf_count.cpu().numpy(), suff.ovf_val.cpu().numpy(),
                      suff.ovf_group.cpu().numpy(), shard.indptr.cpu().numpy())
-    monkeypatch.delenv("DXB200_INGEST_SPLIT")
-    np.testing.assert_array_equal(res["0"][0], res["1"][0])
-    np.testing.assert_array_equal(res["0"][1], res["1"][1])
     indptr = res["0"][4]
+    for other in ("1", "p"):
+        np.testing.assert_array_equal(res["0"][0], res[other][0])
+        np.testing.assert_array_equal(res["0"][1], res[other][1])
+        for gi in range(len(lens)):
+            c = res["0"][1][gi]
+            sl = slice(indptr[gi], indptr[gi] + c)
+            np.testing.assert_array_equal(res["0"][2][sl], res[other][2][sl])
+            np.testing.assert_array_equal(res["0"][3][sl], res[other][3][sl])
     for gi in range(len(lens)):
         c = res["0"][1][gi]
-        sl = slice(indptr[gi], indptr[gi] + c)
-        np.testing.assert_array_equal(res["0"][2][sl], res["1"][2][sl])
-        np.testing.assert_array_equal(res["0"][3][sl], res["1"][3][sl])
         col = dense[:, gi]
         isbin = (col >= 1) & (col <= 64) & (col == np.floor(col))
         for kk in range(0, k, max(1, k // 4)):

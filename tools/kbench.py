@@ -48,6 +48,7 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--what", default="ingest,fit")
     ap.add_argument("--flags", type=int, default=3, help="dx_group_suffstats_ex flags (1 integer counts, 2 groups fit u16)")
+    ap.add_argument("--pieces", action="store_true", help="dx_group_suffstats_pieces with the shard's work list")
     ap.add_argument("--plain", action="store_true", help="use dx_group_suffstats (no gene order / integer flag)")
     ap.add_argument("--scale-batch", action="store_true", help="scale model '~1+batch' (8 dispersion coefficients, configs[2])")
     ap.add_argument("--pack", action="store_true", help="dx_pack_overflow after the ingest + dx_nb_fit_grouped_packed")
@@ -103,7 +104,12 @@ def main():
         packed = torch.zeros((g, 2), dtype=torch.int32, device=dev)
 
         def ingest():
-            if a.plain or not hasattr(lib, "dx_group_suffstats_ex"):
+            if a.pieces:
+                pieces, multi = shard.work_list
+                call(lib, "dx_group_suffstats_pieces", g, ptr(shard.indptr), ptr(shard.rows), ptr(shard.vals), ptr(cell_group), k,
+                     ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), ptr(pieces), int(pieces.shape[0]),
+                     ptr(multi) if multi.shape[0] else None, int(multi.shape[0]), (a.flags if is_int else a.flags & 2), stream_ptr())
+            elif a.plain or not hasattr(lib, "dx_group_suffstats_ex"):
                 call(lib, "dx_group_suffstats", g, ptr(shard.indptr), ptr(shard.rows), ptr(shard.vals), ptr(cell_group), k,
                      ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), stream_ptr())
             else:
