@@ -6,6 +6,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 #include "dx_common.cuh"
 #include "dx_internal.h"
@@ -33,6 +34,22 @@ bool bad_opts(const dx_fit_opts* o) {
 
 #define DX_CHECK(cond, msg) do { if (!(cond)) return fail(DX_ERR_INVALID, msg); } while (0)
 #define DX_CUDA(call, where) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail_cuda(e__, where); } while (0)
+
+// ---- pageable host memory -> device, staged through pinned buffers by several host threads ---------------------------
+// Every thread owns a slice of the array, two pinned 4 MB buffers and a stream: it copies (and converts) a piece into a
+// buffer while the DMA of its previous piece is in flight.  One thread copies ~9 GB/s, eight keep PCIe 5 x16 (~52 GB/s)
+// busy.  The caller's stream is ordered after all of them.  Called through ctypes the whole transfer runs without the
+// Python GIL, so an interpreter thread can build design matrices meanwhile (diffxpy_b200/device.py: prefetch).
+namespace {
+constexpr int UP_THREADS = 8;
+constexpr size_t UP_BUF = 4u << 20;
+struct UpLane { void* pin[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr}; cudaStream_t st = nullptr; cudaEvent_t done = nullptr; };
+std::mutex g_up_mutex;
+UpLane g_up[UP_THREADS];
+bool g_up_ready = false;
+
+template <typename S, typename D> void up_convert(D* dst, const S* src, size_t n) { for (size_t i = 0; i < n; ++i) dst[i] = (D)src[i]; }
+}  // namespace
 
 extern "C" {
 
@@ -84,6 +101,81 @@ int dx_group_suffstats_pieces(int64_t n_genes, const int64_t* indptr, const int3
     DX_CUDA(dx_launch_ingest(n_genes, indptr, rows, vals, cell_group, n_groups, hist, ovf_count, ovf_val, ovf_group,
                              nullptr, flags, sm_count_cached(), (cudaStream_t)stream, pieces, n_pieces, multi_genes, n_multi),
             "dx_group_suffstats_pieces");
+    return DX_OK;
+}
+
+int dx_upload(void* dst_device, const void* src_host, int64_t n_elems, int32_t src_kind, void* stream) {
+    // src_kind: 0 = bytes copied as they are (n_elems bytes); 1 = float64 -> float32; 2 = int64 -> int32
+    DX_CHECK(dst_device && src_host && n_elems >= 0 && src_kind >= 0 && src_kind <= 2, "dx_upload: bad arguments");
+    if (n_elems == 0) return DX_OK;
+    std::lock_guard<std::mutex> lock(g_up_mutex);
+    int dev = 0;
+    DX_CUDA(cudaGetDevice(&dev), "dx_upload");
+    if (!g_up_ready) {
+        for (int k = 0; k < UP_THREADS; ++k) {
+            for (int b = 0; b < 2; ++b) {
+                DX_CUDA(cudaHostAlloc(&g_up[k].pin[b], UP_BUF, cudaHostAllocDefault), "dx_upload: pinned staging buffer");
+                DX_CUDA(cudaEventCreateWithFlags(&g_up[k].ev[b], cudaEventDisableTiming | cudaEventBlockingSync), "dx_upload");
+            }
+            DX_CUDA(cudaStreamCreateWithFlags(&g_up[k].st, cudaStreamNonBlocking), "dx_upload");
+            DX_CUDA(cudaEventCreateWithFlags(&g_up[k].done, cudaEventDisableTiming), "dx_upload");
+        }
+        g_up_ready = true;
+    }
+    const size_t dst_size = src_kind == 0 ? 1 : 4, src_size = src_kind == 0 ? 1 : 8;
+    const size_t per_buf = UP_BUF / dst_size;                       // elements per staging buffer
+    const size_t n = (size_t)n_elems;
+    size_t slice = (n + UP_THREADS - 1) / UP_THREADS;
+    slice = (slice + 63) / 64 * 64;
+    cudaError_t errs[UP_THREADS];
+    std::thread workers[UP_THREADS];
+    int used = 0;
+    for (int k = 0; k < UP_THREADS; ++k) {
+        errs[k] = cudaSuccess;
+        const size_t lo = (size_t)k * slice, hi = std::min(n, lo + slice);
+        if (lo >= hi) break;
+        ++used;
+        workers[k] = std::thread([=, &errs]() {
+            cudaSetDevice(dev);
+            UpLane& L = g_up[k];
+            int b = 0;
+            bool busy[2] = {false, false};
+            for (size_t pos = lo; pos < hi; pos += per_buf, b ^= 1) {
+                const size_t m = std::min(per_buf, hi - pos);
+                if (busy[b]) { cudaError_t e = cudaEventSynchronize(L.ev[b]); if (e != cudaSuccess) { errs[k] = e; return; } }
+                const char* src = static_cast<const char*>(src_host) + pos * src_size;
+                if (src_kind == 0) memcpy(L.pin[b], src, m);
+                else if (src_kind == 1) up_convert(static_cast<float*>(L.pin[b]), reinterpret_cast<const double*>(src), m);
+                else up_convert(static_cast<int32_t*>(L.pin[b]), reinterpret_cast<const int64_t*>(src), m);
+                cudaError_t e = cudaMemcpyAsync(static_cast<char*>(dst_device) + pos * dst_size, L.pin[b], m * dst_size,
+                                                cudaMemcpyHostToDevice, L.st);
+                if (e == cudaSuccess) e = cudaEventRecord(L.ev[b], L.st);
+                if (e != cudaSuccess) { errs[k] = e; return; }
+                busy[b] = true;
+            }
+            errs[k] = cudaEventRecord(L.done, L.st);
+        });
+    }
+    for (int k = 0; k < used; ++k) workers[k].join();
+    for (int k = 0; k < used; ++k) DX_CUDA(errs[k], "dx_upload");
+    for (int k = 0; k < used; ++k) DX_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, g_up[k].done, 0), "dx_upload");
+    return DX_OK;
+}
+
+int dx_csr_to_csc_work_bytes(int64_t n_cells, int32_t n_genes_out, int64_t* bytes) {
+    DX_CHECK(bytes && n_cells >= 0 && n_genes_out >= 0, "dx_csr_to_csc_work_bytes: bad arguments");
+    *bytes = (int64_t)dx_transpose_work_bytes_impl(n_cells, n_genes_out, sm_count_cached());
+    return DX_OK;
+}
+
+int dx_csr_to_csc(int64_t n_cells, const int64_t* indptr, const int32_t* cols, const float* vals,
+                  int32_t gene_lo, int32_t n_genes_out, int64_t* out_indptr, int32_t* out_rows, float* out_vals,
+                  void* work, void* stream) {
+    DX_CHECK(n_cells >= 0 && gene_lo >= 0 && n_genes_out >= 0, "dx_csr_to_csc: bad sizes");
+    DX_CHECK(indptr && out_indptr && work, "dx_csr_to_csc: null pointer");
+    DX_CHECK((int64_t)n_genes_out * 4 <= 220 * 1024, "dx_csr_to_csc: more than 56320 genes in the range (one shared-memory counter per gene)");
+    DX_CUDA(dx_launch_csr_to_csc(n_cells, indptr, cols, vals, gene_lo, n_genes_out, out_indptr, out_rows, out_vals, work,
+                                 sm_count_cached(), (cudaStream_t)stream), "dx_csr_to_csc");
     return DX_OK;
 }
 

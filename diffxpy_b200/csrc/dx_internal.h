@@ -67,3 +67,9 @@ cudaError_t dx_launch_bh_sorted(int64_t n, const double* p_sorted, const int64_t
                                 cudaStream_t s);
 cudaError_t dx_launch_peer_allgather(int64_t n, const double* src, void* const* peer_bufs, int world, int rank,
                                      int64_t slot_bytes, double* dst, int sm_count, cudaStream_t stream);
+
+// K8 (dx_transpose.cu): cell-major CSR -> gene-major shard of the gene range [lo, lo + n_out)
+size_t dx_transpose_work_bytes_impl(int64_t n_cells, int n_out, int sm_count);
+cudaError_t dx_launch_csr_to_csc(int64_t n_cells, const int64_t* indptr, const int32_t* cols, const float* vals, int lo, int n_out,
+                                 int64_t* out_ptr, int32_t* out_rows, float* out_vals, void* work, int sm_count,
+                                 cudaStream_t stream);

@@ -11,11 +11,13 @@ This is the drop-in boundary: diffxpy's ``_fit``
 import logging
 
 import numpy as np
+import pandas as pd
 import scipy.sparse
 import torch
 
 from . import _lib
 from .device import CountShard, ptr, stream_ptr, cuda_device
+from . import device as dxdevice
 from . import dist as dxdist
 
 logger = logging.getLogger("diffxpy")
@@ -72,8 +74,10 @@ def group_rows(mat):
     with np.errstate(over="ignore"):
         h = (bits * mult[None, :]).sum(axis=1, dtype=np.uint64)
         h ^= h >> np.uint64(29)
-    _, idx, inv = np.unique(h, return_index=True, return_inverse=True)
-    inv = np.asarray(inv).reshape(-1)
+    # hash table instead of a sort: codes in order of first appearance, idx = first row of every distinct hash
+    inv, _ = pd.factorize(h)
+    inv = np.asarray(inv, dtype=np.int64)
+    idx = np.flatnonzero(~pd.Series(h).duplicated().to_numpy())
     reps = mat[idx]
     if idx.shape[0] > 65536:
         return _group_rows_exact(mat)
@@ -273,7 +277,7 @@ class Estimator:
         lo, hi = dxdist.gene_range(g_total, self._world.rank, self._world.size, data=idata.data)
         self._gene_range = (lo, hi)
         with torch.cuda.device(dev):
-            self.shard = CountShard.from_host(idata.data, dev, None if self._world.size == 1 else (lo, hi))
+            self.shard = dxdevice.take(idata.data, dev, None if self._world.size == 1 else (lo, hi))
         # ---- resolve init modes (batchglm init_par) -------------------------------------------------
         init_a, init_b = self._init_a, self._init_b
         a_given = b_given = None
@@ -328,7 +332,10 @@ class Estimator:
             offset = np.ascontiguousarray(uniq[:, p + ps]) if idata.size_factors is not None else None
             n_k = np.bincount(inv, minlength=k).astype(np.float64)
             # distinct rows of the raw location design (batchglm closed form works on design_loc, not on groups)
-            loc_u, loc_inv_cells = group_rows(idata.design_loc)
+            if idata._groups_loc is not None and idata.xh_loc is idata.design_loc:
+                loc_u, loc_inv_cells = idata._groups_loc          # (no constraints: the rows grouped at construction)
+            else:
+                loc_u, loc_inv_cells = group_rows(idata.design_loc)
             first_cell = np.zeros(k, dtype=np.int64)
             first_cell[inv[::-1]] = np.arange(n - 1, -1, -1)
             loc_group = loc_inv_cells[first_cell].astype(np.int32)
@@ -356,6 +363,7 @@ class Estimator:
                 if loc_u.shape[0] > 500:
                     raise ValueError("large least-square problem in init, likely defined a numeric predictor as categorical")
                 plan.update(loc_u=loc_u, loc_inv_cells=loc_inv_cells)
+        dxdevice._trace("initialize() done (design groups uploaded)")
         plan["train_loc"] = bool(train_loc)
         plan["train_scale"] = not self._quick_scale
         self._plan = plan

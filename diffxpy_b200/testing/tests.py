@@ -92,12 +92,16 @@ def _fit(
     constructor_args = {}
     if quick_scale is not None:
         constructor_args["quick_scale"] = quick_scale
+    from ..device import _trace
+    _trace("_fit(): InputDataGLM built")
     estim = Estimator(input_data=input_data, init_a=init_a, init_b=init_b, dtype=dtype, **constructor_args)
     estim.initialize()
     train_args = dict(train_args)
     estim.train_sequence(training_strategy=training_strategy, **train_args)
+    _trace("_fit(): trained")
     if close_session:
         estim.finalize()
+    _trace("_fit(): finalized (results on the host)")
     return estim
 
 
@@ -169,6 +173,27 @@ def lrt(
     return de_test
 
 
+def _start_upload(data):
+    """Begin uploading ``data`` (device.prefetch) with the gene range the estimator of this rank will ask for."""
+    from .. import device as dxdevice
+    from .. import dist as dxdist
+    try:
+        if isinstance(data, InputDataGLM):
+            return
+        shape = _shape_of_data(data)
+        w = dxdist.world("auto")
+        gr = None if w.size == 1 else dxdist.gene_range(shape[1], w.rank, w.size, data=data)
+        dxdevice.prefetch(data, gr)
+    except Exception:          # noqa: BLE001  (an optimisation only: the estimator uploads itself if this did not)
+        pass
+
+
+def _shape_of_data(data):
+    if hasattr(data, "X") and not hasattr(data, "shape"):
+        return data.X.shape
+    return data.shape
+
+
 def wald(
         data,
         factor_loc_totest: Union[str, List[str]] = None,
@@ -228,6 +253,9 @@ def wald(
         as_numeric = [as_numeric]
 
     gene_names = parse_gene_names(data, gene_names)
+    _start_upload(data)          # the matrix moves to the GPU while the design matrices are built on the host
+    from ..device import _trace
+    _trace("wald(): upload started")
     if dmat_loc is None and dmat_scale is None:
         sample_description = parse_sample_description(data, sample_description)
     size_factors = parse_size_factors(size_factors=size_factors, data=data, sample_description=sample_description)

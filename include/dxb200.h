@@ -125,6 +125,25 @@ int dx_group_suffstats_pieces(int64_t n_genes, const int64_t* indptr, const int3
                               const int32_t* pieces, int64_t n_pieces, const int32_t* multi_genes, int64_t n_multi,
                               int32_t flags, void* stream);
 
+/* ---- pageable host array -> device array, staged through pinned buffers by eight host threads (each with its own stream;
+ * the caller's stream is ordered after them).  src_kind 0: n_elems bytes as they are; 1: float64 -> float32; 2: int64 ->
+ * int32 (what scipy matrices may hold).  Blocks until the host array has been read; the device copy completes in stream
+ * order.  This is the upload of the count matrix diffxpy hands over as host memory (utils.py:20-33). */
+int dx_upload(void* dst_device, const void* src_host, int64_t n_elems, int32_t src_kind, void* stream);
+
+/* ---- K8: cell-major CSR -> gene-major shard (the layout every kernel above streams) ---------------
+ * Replaces the per-chunk densification of column blocks from the row-major matrix inside batchglm's InputDataGLM
+ * (constructed at tests.py:177-191; data arrives as scipy CSR / AnnData.X, utils.py:20-33).  Device pointers.
+ *   indptr[n_cells + 1] int64, cols[nnz] int32 (a cell holds a gene at most once: canonical CSR), vals[nnz] float32
+ *   gene range [gene_lo, gene_lo + n_genes_out): the entries of other genes are skipped (gene-sharded runs)
+ *   out_indptr[n_genes_out + 1] int64, out_rows / out_vals sized for the entries of the range (<= nnz); cells ascending
+ *   inside every gene (stable, deterministic, no atomics on the output)
+ *   work: dx_csr_to_csc_work_bytes(n_cells, n_genes_out) bytes.  n_genes_out <= 56320. */
+int dx_csr_to_csc_work_bytes(int64_t n_cells, int32_t n_genes_out, int64_t* bytes);
+int dx_csr_to_csc(int64_t n_cells, const int64_t* indptr, const int32_t* cols, const float* vals,
+                  int32_t gene_lo, int32_t n_genes_out, int64_t* out_indptr, int32_t* out_rows, float* out_vals,
+                  void* work, void* stream);
+
 /* ---- K_fit (grouped): the whole batchglm training schedule + finalize, one warp per gene ----------
  * Replaces Estimator.initialize / train_sequence / finalize (tests.py:222-248) when the rows of
  * [design_loc | design_scale | log size factor] take n_groups <= 255 distinct values.

@@ -252,6 +252,30 @@ def test_ingest_csr_csc_dense_inputs_agree(de):
     np.testing.assert_array_equal(outs[0], outs[2])
 
 
+@pytest.mark.parametrize("shape,density", [((3000, 700), 0.12), ((257, 40000), 0.002), ((1, 5), 1.0), ((4000, 3), 0.5)])
+def test_k8_csr_to_csc_bit_exact(de, shape, density):
+    """dx_csr_to_csc against scipy's tocsc(): same pointers, cells ascending inside every gene, same values -- whole matrix
+    and gene ranges (what a gene-sharded run keeps), with empty cells and empty genes."""
+    from diffxpy_b200.device import CountShard
+    rng = np.random.default_rng(shape[0] + shape[1])
+    x = scipy.sparse.random(shape[0], shape[1], density=density, format="csr", random_state=rng,
+                            data_rvs=lambda k: rng.integers(1, 90, k).astype(np.float32)).astype(np.float32)
+    x.sort_indices()
+    if shape[0] > 10:
+        x = scipy.sparse.vstack([x[:5], scipy.sparse.csr_matrix((3, shape[1]), dtype=np.float32), x[5:]]).tocsr()   # empty cells
+    want = x.tocsc()
+    want.sort_indices()
+    ranges = [None, (0, shape[1] // 2), (shape[1] // 3, shape[1])] if shape[1] > 3 else [None]
+    for gr in ranges:
+        shard = CountShard.from_host(x, gene_range=gr)
+        lo, hi = (0, shape[1]) if gr is None else gr
+        sub = want[:, lo:hi]
+        np.testing.assert_array_equal(shard.indptr.cpu().numpy(), sub.indptr.astype(np.int64))
+        np.testing.assert_array_equal(shard.rows.cpu().numpy()[:sub.nnz], sub.indices)
+        np.testing.assert_array_equal(shard.vals.cpu().numpy()[:sub.nnz], sub.data)
+        assert shard.gene_offset == lo and shard.n_cells == x.shape[0]
+
+
 # ---------------------------------------------------------------------------------------------------
 # K_fit (grouped) against the oracle and the committed goldens
 # ---------------------------------------------------------------------------------------------------

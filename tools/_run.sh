@@ -1,1 +1,1 @@
-python tools/diag_k2.py 2>&1 | tail -8
+python tools/api_profile.py 2>&1 | grep -E "dxb200|ms per call" | head -40
