@@ -294,8 +294,10 @@ int dx_nb_fit_percell(int64_t n_genes, int64_t n_cells, int32_t p_loc, int32_t p
                       double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
                       int32_t* niter, int32_t* flags, void* stream) {
     DX_CHECK(n_genes >= 0 && n_cells >= 1, "dx_nb_fit_percell: bad sizes");
-    DX_CHECK(p_loc >= 1 && p_loc <= DX_MAX_COEF && p_scale >= 1 && p_scale <= DX_MAX_COEF,
-             "dx_nb_fit_percell: coefficient counts must be in 1..32");
+    DX_CHECK(p_loc >= 1 && p_loc <= DX_MAX_COEF, "dx_nb_fit_percell: location coefficients must be in 1..32");
+    DX_CHECK(p_scale >= 1 && p_scale <= DX_MAX_SCALE_COEF_PERCELL,
+             "dx_nb_fit_percell: a scale model with numeric covariates takes 1..8 coefficients (categorical scale models of "
+             "any width collapse into design groups and use dx_nb_fit_grouped)");
     DX_CHECK(!bad_opts(opts), "dx_nb_fit_percell: bad options");
     DX_CHECK(opts->init_a == DX_INIT_GIVEN && opts->init_b == DX_INIT_GIVEN,
              "dx_nb_fit_percell: start values must be given (DX_INIT_GIVEN)");

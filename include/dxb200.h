@@ -49,6 +49,7 @@ extern "C" {
 #define DX_MAX_GROUPS 255    /* distinct design rows handled by the grouped path; group id 255 = skip cell */
 #define DX_SKIP_GROUP 255
 #define DX_MAX_COEF 32       /* max coefficients of the location / scale model */
+#define DX_MAX_SCALE_COEF_PERCELL 8   /* per-cell path: max coefficients of a scale model with numeric covariates */
 
 /* init modes: batchglm init_par (tests.py:36-37, 222-229) */
 #define DX_INIT_GIVEN 0        /* a_var / b_var hold the start values */
@@ -235,8 +236,11 @@ int dx_exchange_status(const void* local_buf, int32_t* failed_rank_plus_one);
 int dx_peer_allgather_f64(int64_t n, const double* src, void* const* peer_bufs, int32_t world, int32_t rank,
                           int64_t slot_bytes, double* dst, void* stream);
 
-/* ---- K_fit (per cell): same schedule, one CTA per gene, streams all cells every step --------------
- * General path: arbitrary numeric design, per-cell size factors (tests.py:177-191 arguments).
+/* ---- K_fit (per cell): same schedule for designs that do not collapse into groups ----------------
+ * General path: arbitrary numeric design, per-cell size factors (tests.py:177-191 arguments).  A CTA owns a tile of
+ * genes and walks the cells once per model evaluation; X^T W X is a register-blocked fp64 contraction of per-(cell, gene)
+ * weights with the design-column products, which are shared by all genes of the tile (csrc/dx_fit_tile.cu).
+ * p_loc <= DX_MAX_COEF (32), p_scale <= DX_MAX_SCALE_COEF_PERCELL (8).
  *   design_loc[p_loc][n_cells], design_scale[p_scale][n_cells] (coefficient-major, constraints applied)
  *   log_sf[n_cells] nullable.  a_var / b_var must hold the start values (DX_INIT_GIVEN).
  */
