@@ -46,6 +46,7 @@ _I64, _I32, _F64 = C.c_int64, C.c_int32, C.c_double
 # name -> argtypes; every function returns int
 SIGNATURES = {
     "dx_device_sm_count": [C.POINTER(C.c_int)],
+    "dx_fit_percell_counters": [C.POINTER(C.c_uint64), _I32],
     "dx_group_suffstats": [_I64, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P],
     "dx_group_suffstats_ex": [_I64, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _I32, _P],
     "dx_group_suffstats_pieces": [_I64, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _I64, _P, _I64, _I32, _P],

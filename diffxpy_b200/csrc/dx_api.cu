@@ -309,6 +309,13 @@ int dx_nb_fit_percell(int64_t n_genes, int64_t n_cells, int32_t p_loc, int32_t p
     return DX_OK;
 }
 
+int dx_fit_percell_counters(uint64_t* out4, int32_t reset) {
+    DX_CHECK(out4, "dx_fit_percell_counters: null out");
+    DX_CUDA(cudaDeviceSynchronize(), "dx_fit_percell_counters");
+    DX_CUDA(dx_fit_percell_counters_impl(reinterpret_cast<unsigned long long*>(out4), reset), "dx_fit_percell_counters");
+    return DX_OK;
+}
+
 int dx_wald_test(int64_t n, const double* theta, const double* sd, double* pval, double* log_pval, void* stream) {
     DX_CHECK(n >= 0 && theta && sd && pval, "dx_wald_test: bad arguments");
     DX_CUDA(dx_launch_wald(n, theta, sd, pval, log_pval, (cudaStream_t)stream), "dx_wald_test");

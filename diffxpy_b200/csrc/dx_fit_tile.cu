@@ -40,6 +40,9 @@ enum { IC_FLAGS = 0, IC_LOCCONV, IC_FULLY, IC_HAVE, IC_DOK, IC_NSTATE, IC_NIT, I
 enum { NS_DONE = 0, NS_DERIV = 1, NS_LINE = 2 };
 enum { PASS_LOC = 0, PASS_SCALE = 1 };
 
+// diagnostics: passes over the cells and gene tiles since the last reset (dx_fit_percell_counters)
+__device__ unsigned long long g_tile_counters[4];          // location passes, dispersion passes, dispersion epochs, gene tiles
+
 struct TileArgs {
     int64_t n_genes, N;
     int p, ps;
@@ -58,7 +61,8 @@ struct Lay {          // shared-memory layout (offsets in doubles)
     int b, bt, qb, sb, gb;          // [ps][GT]
     int hg;                         // [GT][ps * ps]  -(Hessian) of the dispersion step (general scale model)
     int sc, ic, ent;                // per-gene scalars, ints, entry ranges
-    int gt, t0, t1;                 // [GT][TB] tables G(r, y), psi differences (constant dispersion model)
+    int gt, lf;                     // [GT][TB] table G(r, y) (constant dispersion model); log(y!) for y < TB
+    int t0, t1;                     // [GT][TB] psi differences: inside the region (the dispersion pass has no product table)
     int rn;                         // [p][GT] sum over the non-zero cells of y q x_j
     int pair;                       // uint8 entry -> (j, k) tables
     int tile;                       // start of the region shared by the passes and the small dense algebra between them
@@ -72,36 +76,39 @@ __host__ __device__ inline Lay make_layout(int p, int ps) {
     constexpr int ZW = 32 * NE, ZWS = SCONST ? 0 : 96, ZWM = (ZW > ZWS) ? ZW : ZWS;
     constexpr int WST = GT + 2, XST = CT + 1, KS = NWP / (GT / MG);
     Lay L;
+    // everything whose size does not depend on (p, ps) comes first: those offsets are compile-time constants in the kernel
     int o = 0;
-    L.a = o; o += p * GT; L.qa = o; o += p * GT; L.delta = o; o += p * GT; L.rhs = o; o += p * GT;
-    L.b = o; o += ps * GT; L.bt = o; o += ps * GT; L.qb = o; o += ps * GT; L.sb = o; o += ps * GT; L.gb = o; o += ps * GT;
-    L.hg = o; o += SCONST ? 0 : GT * ps * ps;
     L.sc = o; o += SC_COUNT * GT;
     L.ic = o; o += (IC_COUNT * GT + 1) / 2;
     L.ent = o; o += 2 * GT;
     L.gt = o; o += SCONST ? GT * TB : 0;
-    L.t0 = o; o += SCONST ? GT * TB : 0;
-    L.t1 = o; o += SCONST ? GT * TB : 0;
-    L.rn = o; o += p * GT;
+    L.lf = o; o += TB;
     L.pair = o; o += (2 * ZW + 2 * 96 + 7) / 8;
     o = (o + 1) & ~1;
     L.tile = o;
     int t = 0;
-    L.Z = t; t += CT * ZWM;
+    L.Z = t; L.t0 = t; L.t1 = t + GT * TB;
+    t += (SCONST && CT * ZWM < 2 * GT * TB) ? 2 * GT * TB : CT * ZWM;
     L.W = t; t += CT * WST + 8;
     L.S = t; t += CT * WST;
-    L.X = t; t += p * XST; t = (t + 1) & ~1;
-    L.D = t; t += SCONST ? 0 : ps * XST; t = (t + 1) & ~1;
     L.Ls = t; t += CT;
     L.Y = t; t += GT * CT / 2;
     L.NZ = t; t += GT * (CT + 8) / 8;
+    t = (t + 1) & ~1;
     const int pm = (p > ps) ? p : ps;
     L.scratch = GT * ZWM;
     int need = L.scratch + NWP * (pm * pm + 2 * pm);          // extraction / solves next to the reduced pass result
     if (need < NWP * 2 * pm * pm) need = NWP * 2 * pm * pm;   // finalize: factor and inverse per warp
     if (need < KS * GT * ZWM) need = KS * GT * ZWM;           // partial sums of the cell slices
     if (t < need) t = need;
-    L.total_bytes = (L.tile + t) * 8;
+    o = L.tile + t;
+    // sizes that depend on the design width (X, D relative to the region like the other pass arrays)
+    L.X = o - L.tile; o += p * XST; o = (o + 1) & ~1;
+    L.D = o - L.tile; o += SCONST ? 0 : ps * XST; o = (o + 1) & ~1;
+    L.a = o; o += p * GT; L.qa = o; o += p * GT; L.delta = o; o += p * GT; L.rhs = o; o += p * GT; L.rn = o; o += p * GT;
+    L.b = o; o += ps * GT; L.bt = o; o += ps * GT; L.qb = o; o += ps * GT; L.sb = o; o += ps * GT; L.gb = o; o += ps * GT;
+    L.hg = o; o += SCONST ? 0 : GT * ps * ps;
+    L.total_bytes = o * 8;
     return L;
 }
 
@@ -194,8 +201,8 @@ __device__ bool newton_direction(double* H, double* Lb, const double* g, double*
     return true;
 }
 
-template <int NE, int MG, int GT, int CT, int PMAXC, bool SCONST>
-__global__ void __launch_bounds__(NT, 1) dx_fit_tile_kernel(const TileArgs A) {
+template <int NE, int MG, int GT, int CT, int PMAXC, int MINB, bool SCONST>
+__global__ void __launch_bounds__(NT, MINB) dx_fit_tile_kernel(const TileArgs A) {
     constexpr int ZW = 32 * NE, WST = GT + 2, XST = CT + 1;
     constexpr int NGH = GT / MG, KS = NWP / NGH, GP1 = GT / NWP, CP1 = CT / 32;
     constexpr int XPT = (PMAXC * CT + NT - 1) / NT, DPT = SCONST ? 1 : (8 * CT + NT - 1) / NT;
@@ -212,7 +219,8 @@ __global__ void __launch_bounds__(NT, 1) dx_fit_tile_kernel(const TileArgs A) {
     double* const sc = sm + L.sc;
     int* const ic = reinterpret_cast<int*>(sm + L.ic);
     int64_t* const ent = reinterpret_cast<int64_t*>(sm + L.ent);
-    double* const Gt = sm + L.gt; double* const T0 = sm + L.t0; double* const T1 = sm + L.t1;
+    double* const Gt = sm + L.gt; double* const T0 = sm + L.tile + L.t0; double* const T1 = sm + L.tile + L.t1;
+    double* const lfact = sm + L.lf;
     double* const rn_s = sm + L.rn;
     uint8_t* const pa = reinterpret_cast<uint8_t*>(sm + L.pair);
     uint8_t* const pb = pa + ZW; uint8_t* const pas = pb + ZW; uint8_t* const pbs = pas + 96;
@@ -242,6 +250,7 @@ __global__ void __launch_bounds__(NT, 1) dx_fit_tile_kernel(const TileArgs A) {
         else if (e >= 64 && e < 64 + ps) { j = e - 64; k = 254; }
         pas[e] = (uint8_t)j; pbs[e] = (uint8_t)k;
     }
+    for (int j = tid; j < TB; j += NT) lfact[j] = lgamma((double)j + 1.0);
     const bool train_loc = A.opts.train_loc != 0, train_scale = A.opts.train_scale != 0;
     const int freq = train_scale ? (train_loc ? A.opts.update_b_freq : 1) : 0x7fffffff;
     const double z_const = SCONST ? __ldg(A.ds) : 0.0;
@@ -260,6 +269,7 @@ __global__ void __launch_bounds__(NT, 1) dx_fit_tile_kernel(const TileArgs A) {
         constexpr int NEW = (KIND == PASS_LOC) ? NE : 2;          // slots [0, NEW) are weighted by Ws, the rest by Ss
         constexpr int ZWK = 32 * NEK;
         const double* const dsrc_tile = (KIND == PASS_LOC) ? Xs : Ds;
+        if (tid == 0) atomicAdd(&g_tile_counters[KIND], 1ull);
         __syncthreads();
         // per-gene constants of the pass
         if (SCONST) {
@@ -303,11 +313,13 @@ __global__ void __launch_bounds__(NT, 1) dx_fit_tile_kernel(const TileArgs A) {
 #pragma unroll
             for (int i = 0; i < (GEMM ? NEK : 1); ++i) acc[m][i] = 0.0;
         double llacc[GP1], gacc[GP1], hacc[GP1], zmx[GP1], rnz[GP1];
-        int64_t cur[GP1], eend[GP1];
+        // score over the non-zero cells: lane <-> coefficient; up to 16 coefficients the two half-warps take alternate cells
+        const int nz_s = (p <= 16) ? 2 : 1, nz_j = (p <= 16) ? (lane & 15) : lane, nz_h = (p <= 16) ? (lane >> 4) : 0;
+        int cur[GP1];          // entries consumed so far (offset from the gene's first entry)
 #pragma unroll
         for (int u = 0; u < GP1; ++u) {
             llacc[u] = 0.0; gacc[u] = 0.0; hacc[u] = 0.0; zmx[u] = -INFINITY; rnz[u] = 0.0;
-            cur[u] = ent[warp * GP1 + u]; eend[u] = ent[GT + warp * GP1 + u];
+            cur[u] = 0;
         }
         // register prefetch of the next cell tile: design rows, offsets, candidate entries of the sparse columns
         double xr[XPT], dr[DPT], lr = 0.0;
@@ -329,17 +341,14 @@ __global__ void __launch_bounds__(NT, 1) dx_fit_tile_kernel(const TileArgs A) {
             if (tid < CT) lr = (A.log_sf && c0 + tid < N) ? A.log_sf[c0 + tid] : 0.0;
 #pragma unroll
             for (int u = 0; u < GP1; ++u) {
-                const int64_t e = cur[u] + lane;
-                const bool in = e < eend[u];
+                const int64_t e = ent[warp * GP1 + u] + cur[u] + lane;
+                const bool in = e < ent[GT + warp * GP1 + u];
                 yrow[u] = in ? A.rows[e] : 0x7fffffff;
                 yval[u] = in ? A.vals[e] : 0.0f;
             }
         };
         prefetch(0);
         __syncthreads();          // tables and constants visible
-        double rr[GP1], irr[GP1];
-#pragma unroll
-        for (int u = 0; u < GP1; ++u) { rr[u] = SCG(SC_R, warp * GP1 + u); irr[u] = SCG(SC_INVR, warp * GP1 + u); }
 
 #pragma unroll 1
         for (int64_t c0 = 0; c0 < N; c0 += CT) {
@@ -377,9 +386,9 @@ __global__ void __launch_bounds__(NT, 1) dx_fit_tile_kernel(const TileArgs A) {
                 int tot = n;
                 cur[u] += n;
                 while (n == 32) {                       // more than 32 entries of this gene inside the cell tile
-                    const int64_t e = cur[u] + lane;
+                    const int64_t e = ent[warp * GP1 + u] + cur[u] + lane;
                     hit = false;
-                    if (e < eend[u]) {
+                    if (e < ent[GT + warp * GP1 + u]) {
                         const int64_t row = A.rows[e];
                         if (row < c1) { yrow_s[(int)(row - c0)] = A.vals[e]; nzl[tot + lane] = (uint8_t)(row - c0); hit = true; }
                     }
@@ -393,7 +402,7 @@ __global__ void __launch_bounds__(NT, 1) dx_fit_tile_kernel(const TileArgs A) {
             if (c1 < N) prefetch(c1);
             if (GEMM) {
                 // product table of the cell tile, shared by all genes of the CTA: a warp per cell, lane <-> entry
-#pragma unroll 2
+#pragma unroll 4
                 for (int c = warp; c < tn; c += NWP) {
 #pragma unroll
                     for (int i = 0; i < NEK; ++i) {
@@ -453,10 +462,11 @@ __global__ void __launch_bounds__(NT, 1) dx_fit_tile_kernel(const TileArgs A) {
                     for (int u = 0; u < GP1; ++u) {
                         const int g = warp * GP1 + u;
                         const double y = (double)Ys[g * CT + c];
-                        const double e = dx_clip(eta[v][u], DX_ETA_MIN, DX_ETA_MAX);
+                        double e = eta[v][u];
+                        if ((__double2hiint(e) & 0x7fffffff) > 0x4071b000) e = dx_clip(e, DX_ETA_MIN, DX_ETA_MAX);          // |e| > 283 (or NaN)
                         const double mu = fl_exp(e);
                         double r, invr;
-                        if (SCONST) { r = rr[u]; invr = irr[u]; }
+                        if (SCONST) { r = SCG(SC_R, g); invr = SCG(SC_INVR, g); }
                         else {
                             const double zc = dx_clip(zeta[v][u], DX_ETA_MIN, DX_ETA_MAX);
                             if (valid) zmx[u] = fmax(zmx[u], zc);
@@ -513,12 +523,17 @@ __global__ void __launch_bounds__(NT, 1) dx_fit_tile_kernel(const TileArgs A) {
                     for (int u = 0; u < GP1; ++u) {
                         const uint8_t* nzl = NZl + (warp * GP1 + u) * (CT + 8);
                         const double* scol = Ss + warp * GP1 + u;
-                        const double* xrow = Xs + ((lane < p) ? lane : 0) * XST;
+                        const double* xrow = Xs + ((nz_j < p) ? nz_j : 0) * XST;
+                        const int n = nzn[u];
+                        int i = nz_h;
 #pragma unroll 1
-                        for (int i = 0; i < nzn[u]; ++i) {
-                            const int c = nzl[i];
-                            rnz[u] = fma(scol[c * WST], xrow[c], rnz[u]);
+                        for (; i + nz_s < n; i += 2 * nz_s) {
+                            const int ca = nzl[i], cb = nzl[i + nz_s];
+                            const double sa = scol[ca * WST], xa = xrow[ca], sb2 = scol[cb * WST], xb = xrow[cb];
+                            rnz[u] = fma(sa, xa, rnz[u]);
+                            rnz[u] = fma(sb2, xb, rnz[u]);
                         }
+                        if (i < n) { const int ca = nzl[i]; rnz[u] = fma(scol[ca * WST], xrow[ca], rnz[u]); }
                     }
                 }
             }
@@ -569,7 +584,11 @@ __global__ void __launch_bounds__(NT, 1) dx_fit_tile_kernel(const TileArgs A) {
                 if (KIND == PASS_SCALE && SCONST) { SCG(SC_G, g) = gsum; SCG(SC_H, g) = hsum; }
                 if (!SCONST) SCG(SC_ZMAX, g) = zm;
             }
-            if (KIND == PASS_LOC && lane < p) rn_s[lane * GT + g] = rnz[u];
+            if (KIND == PASS_LOC) {
+                double rsum = rnz[u];
+                if (nz_s == 2) rsum += __shfl_xor_sync(DX_FULL_MASK, rsum, 16);
+                if (lane < p) rn_s[lane * GT + g] = rsum;
+            }
         }
         if (GEMM) {
 #pragma unroll
@@ -632,6 +651,7 @@ __global__ void __launch_bounds__(NT, 1) dx_fit_tile_kernel(const TileArgs A) {
         if (g0 >= A.n_genes) return;
         const int ng = (int)((A.n_genes - g0 < GT) ? (A.n_genes - g0) : GT);
         const unsigned valid_mask = (ng >= 32) ? 0xffffffffu : ((1u << ng) - 1u);
+        if (tid == 0) atomicAdd(&g_tile_counters[3], 1ull);
         // ---- start values, per-gene constants ----------------------------------------------------------------------------
         if (tid < GT) {
             const int g = tid;
@@ -653,7 +673,12 @@ __global__ void __launch_bounds__(NT, 1) dx_fit_tile_kernel(const TileArgs A) {
         __syncthreads();
         for (int g = warp; g < GT; g += NWP) {
             double lg = 0.0;
-            for (int64_t e = ent[g] + lane; e < ent[GT + g]; e += 32) lg += lgamma((double)A.vals[e] + 1.0);
+#pragma unroll 4
+            for (int64_t e = ent[g] + lane; e < ent[GT + g]; e += 32) {
+                const double y = (double)A.vals[e];
+                const int yi = (int)y;
+                lg += (yi >= 0 && yi < TB && (double)yi == y) ? lfact[yi] : lgamma(y + 1.0);
+            }
             lg = dx_warp_sum(lg);
             if (lane == 0) SCG(SC_LGAM, g) = lg;
         }
@@ -678,6 +703,7 @@ __global__ void __launch_bounds__(NT, 1) dx_fit_tile_kernel(const TileArgs A) {
             if (b_epoch) {
                 if (train_scale) {
                     // ---- safeguarded Newton in b (oracle _b_step_newton), all active genes in lockstep passes -------------
+                    if (tid == 0) atomicAdd(&g_tile_counters[2], 1ull);
                     if (tid < GT) {
                         const int g = tid;
                         const bool on = (active >> g) & 1u;
@@ -933,18 +959,22 @@ __global__ void __launch_bounds__(NT, 1) dx_fit_tile_kernel(const TileArgs A) {
 #undef ICG
 }
 
-template <int NE, int MG, int GT, int CT, int PMAXC, bool SCONST>
+template <int NE, int MG, int GT, int CT, int PMAXC, int MINB, bool SCONST>
 cudaError_t launch_cfg(const TileArgs& A0, int sm_count, cudaStream_t stream) {
     TileArgs A = A0;
     const Lay L = make_layout<NE, MG, GT, CT, SCONST>(A.p, A.ps);
-    auto kern = dx_fit_tile_kernel<NE, MG, GT, CT, PMAXC, SCONST>;
+    auto kern = dx_fit_tile_kernel<NE, MG, GT, CT, PMAXC, MINB, SCONST>;
     if (L.total_bytes > 227 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes);
     if (e != cudaSuccess) return e;
     e = dx_queue_acquire(stream, &A.queue);
     if (e != cudaSuccess) return e;
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, (size_t)L.total_bytes);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
     int64_t grid = (A.n_genes + GT - 1) / GT;
-    if (grid > sm_count) grid = sm_count;
+    if (grid > (int64_t)sm_count * per_sm) grid = (int64_t)sm_count * per_sm;
     kern<<<(unsigned)grid, NT, (size_t)L.total_bytes, stream>>>(A);
     return cudaGetLastError();
 }
@@ -952,16 +982,32 @@ cudaError_t launch_cfg(const TileArgs& A0, int sm_count, cudaStream_t stream) {
 template <bool SCONST>
 cudaError_t launch_p(const TileArgs& A, int sm_count, cudaStream_t stream) {
     const int need = A.p * (A.p + 1) / 2 + A.p;          // entries of X^T W X (packed) + X^T S
-    //                     NE  MG  GT  CT  PMAXC
-    if (need <= 32)  return launch_cfg<1, 16, 32, 64, 7, SCONST>(A, sm_count, stream);
-    if (need <= 64)  return launch_cfg<2, 16, 32, 64, 9, SCONST>(A, sm_count, stream);
-    if (need <= 96)  return launch_cfg<3, 16, 32, 64, 12, SCONST>(A, sm_count, stream);
-    if (need <= 160) return launch_cfg<5, 8, 32, 64, 16, SCONST>(A, sm_count, stream);
-    if (need <= 352) return launch_cfg<11, 4, 32, 32, 24, SCONST>(A, sm_count, stream);
-    return launch_cfg<18, 2, 16, 32, 32, SCONST>(A, sm_count, stream);
+    // up to 12 coefficients: two CTAs per SM (128 registers, < 113 KB of shared memory each), so that one tile's barriers and
+    // dependency chains are covered by the other's arithmetic; wider designs need the registers for the accumulators
+    //                     NE  MG  GT  CT  PMAXC MINB
+    if (need <= 32)  return launch_cfg<1, 8, 32, 32, 7, 2, SCONST>(A, sm_count, stream);
+    if (need <= 64)  return launch_cfg<2, 8, 32, 32, 9, 2, SCONST>(A, sm_count, stream);
+    if (need <= 96) {
+        const char* env = getenv("DXB200_TILE_MINB");          // tuning hook
+        if (env && atoi(env) == 1) return launch_cfg<3, 16, 32, 64, 12, 1, SCONST>(A, sm_count, stream);
+        return launch_cfg<3, 8, 32, 32, 12, 2, SCONST>(A, sm_count, stream);
+    }
+    if (need <= 160) return launch_cfg<5, 8, 32, 64, 16, 1, SCONST>(A, sm_count, stream);
+    if (need <= 352) return launch_cfg<11, 4, 32, 32, 24, 1, SCONST>(A, sm_count, stream);
+    return launch_cfg<18, 2, 16, 32, 32, 1, SCONST>(A, sm_count, stream);
 }
 
 }  // namespace
+
+cudaError_t dx_fit_percell_counters_impl(unsigned long long* out, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_tile_counters, 4 * sizeof(unsigned long long));
+    if (e != cudaSuccess) return e;
+    if (reset) {
+        const unsigned long long zero[4] = {0, 0, 0, 0};
+        e = cudaMemcpyToSymbol(g_tile_counters, zero, sizeof(zero));
+    }
+    return e;
+}
 
 cudaError_t dx_launch_fit_percell(int64_t n_genes, int64_t n_cells, int p, int ps,
                                   const double* design_loc, const double* design_scale, const double* log_sf,

@@ -42,6 +42,7 @@ cudaError_t dx_launch_fit_percell(int64_t n_genes, int64_t n_cells, int p, int p
                                   const dx_fit_opts* opts,
                                   double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
                                   int32_t* niter, int32_t* flags, int sm_count, cudaStream_t stream);
+cudaError_t dx_fit_percell_counters_impl(unsigned long long* out, int reset);
 cudaError_t dx_launch_wald(int64_t n, const double* theta, const double* sd, double* pval, double* logp, cudaStream_t s);
 cudaError_t dx_launch_wald_from_fit(int64_t G, int p, int coef, const double* a_var, const double* fim_inv,
                                     double* theta, double* sd, double* pval, double* logp, int64_t coef_stride, cudaStream_t s);

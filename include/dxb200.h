@@ -251,6 +251,10 @@ int dx_nb_fit_percell(int64_t n_genes, int64_t n_cells, int32_t p_loc, int32_t p
                       double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
                       int32_t* niter, int32_t* flags, void* stream);
 
+/* diagnostics of the per-cell path (synchronous): out4 = {location passes, dispersion passes, dispersion epochs, gene
+ * tiles} summed over the CTAs since the last reset; a pass = one sweep of a gene tile over all cells. */
+int dx_fit_percell_counters(uint64_t* out4, int32_t reset);
+
 /* ---- column moments of the CSC shard (initialisation of the per-cell path, det.py:775-781 mean) ---
  *   inv_sf[n_cells] nullable: moments of x / size_factor.  sum1, sum2, nnz: [G] */
 int dx_gene_moments(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,

@@ -114,8 +114,9 @@ def cfg3(n_cells=100_000, n_genes=20_000):
             "pval_finite_frac": float(np.mean(np.isfinite(pv)))}
 
 
-def cfg4(n_cells=250_000, n_genes=512):
-    """Wald with a continuous covariate: cubic B-spline basis (11 + intercept), per-cell size factors -> per-cell path."""
+def cfg4(n_cells=int(os.environ.get("DXB200_CFG4_CELLS", "250000")), n_genes=int(os.environ.get("DXB200_CFG4_GENES", "9472"))):
+    """Wald with a continuous covariate: cubic B-spline basis (11 + intercept), per-cell size factors -> per-cell path.
+    9472 genes = one full wave of 32-gene tiles, two CTAs on each of 148 SMs (configs[3] has 30k genes = 3.2 waves)."""
     from scipy.interpolate import BSpline
     shard, cond, batch = bench.make_shard(torch, dev, seed=4, n_genes=n_genes, n_cells=n_cells, chunk=200)
     rng = np.random.default_rng(4)
@@ -132,13 +133,22 @@ def cfg4(n_cells=250_000, n_genes=512):
     def run():
         return _fit("nb", shard, pd.DataFrame(xd, columns=cols), pd.DataFrame(np.ones((n_cells, 1)), columns=["Intercept"]),
                     gene_names=names, size_factors=sf)
+    import ctypes as C
+    cnt = (C.c_uint64 * 4)()
+    _lib.call("dx_fit_percell_counters", cnt, 1)
     est, sec = timed(run, reps=2)
+    _lib.call("dx_fit_percell_counters", cnt, 1)
+    passes = {"location_passes_per_tile": cnt[0] / max(cnt[3], 1), "dispersion_passes_per_tile": cnt[1] / max(cnt[3], 1),
+              "dispersion_epochs_per_tile": cnt[2] / max(cnt[3], 1), "gene_tiles_per_fit": cnt[3] / 3}
     nit = est.niter
     bytes_iter = 8.0 * shard.nnz + n_cells * (xd.shape[1] * 8 + 8) * n_genes      # design + log sf re-read per gene (L2)
     return {"config": "configs[3]: de.test.wald, %d cells x %d genes (of 30k), 12 spline coefficients, size factors" % (n_cells, n_genes),
             "nnz": shard.nnz, "p_loc": int(xd.shape[1]), "seconds": sec, "genes_per_s": n_genes / sec,
             "device_train_ms": est.device_train_ms,
+            "passes": passes,
             "frac_converged": float(np.mean((est.error_codes & 1) != 0)), "mean_niter": float(np.mean(nit)),
+            "niter_percentiles_5_25_50_75_95_100": [float(v) for v in np.percentile(nit, [5, 25, 50, 75, 95, 100])],
+            "mean_of_tile_max_niter(32 genes)": float(np.mean([nit[i:i + 32].max() for i in range(0, len(nit), 32)])),
             "seconds_per_gene_iteration": sec / float(np.sum(nit)),
             "count_stream_gbs_per_iteration": 8.0 * shard.nnz * float(np.mean(nit)) / sec / 1e9}
 
