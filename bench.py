@@ -677,16 +677,28 @@ def main_cuda(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--workload", default="wald", choices=["wald", "lrt", "spline", "rank"],
+                    help="wald (default): the headline configs[1]; lrt / spline / rank: configs[2] / [3] / [4] (bench_workloads.py)")
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--genes", type=int, default=N_GENES, help="genes of the problem (strong) / per GPU (weak)")
+    ap.add_argument("--genes", type=int, default=None, help="genes of the problem (strong) / per GPU (weak)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong (default): ONE 100k x 20k problem split over the GPUs by non-zero count; weak: 20k genes per GPU")
     ap.add_argument("--no-api-e2e", action="store_true")
-    ap.add_argument("--cells", type=int, default=N_CELLS)
+    ap.add_argument("--cells", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.workload != "wald" and args.impl == "cuda":
+        import bench_workloads
+        d_steps, d_warm = bench_workloads.DEFAULT_STEPS[args.workload]
+        args.steps = d_steps if args.steps is None else args.steps
+        args.warmup = max(d_warm if args.warmup is None else args.warmup, 1)
+        return bench_workloads.main(args, sys.modules[__name__])
+    args.steps = 20 if args.steps is None else args.steps
+    args.warmup = 3 if args.warmup is None else args.warmup
+    args.genes = N_GENES if args.genes is None else args.genes
+    args.cells = N_CELLS if args.cells is None else args.cells
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = max(args.warmup, 1)
     if args.impl == "reference":

@@ -47,6 +47,7 @@ struct UpLane { void* pin[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr,
 std::mutex g_up_mutex;
 UpLane g_up[UP_THREADS];
 bool g_up_ready = false;
+cudaEvent_t g_up_start = nullptr;
 
 template <typename S, typename D> void up_convert(D* dst, const S* src, size_t n) { for (size_t i = 0; i < n; ++i) dst[i] = (D)src[i]; }
 }  // namespace
@@ -120,8 +121,13 @@ int dx_upload(void* dst_device, const void* src_host, int64_t n_elems, int32_t s
             DX_CUDA(cudaStreamCreateWithFlags(&g_up[k].st, cudaStreamNonBlocking), "dx_upload");
             DX_CUDA(cudaEventCreateWithFlags(&g_up[k].done, cudaEventDisableTiming), "dx_upload");
         }
+        DX_CUDA(cudaEventCreateWithFlags(&g_up_start, cudaEventDisableTiming), "dx_upload");
         g_up_ready = true;
     }
+    // the destination may still be in use by work queued on the caller's stream (a recycled allocation): the copy lanes
+    // start behind it
+    DX_CUDA(cudaEventRecord(g_up_start, (cudaStream_t)stream), "dx_upload");
+    for (int k = 0; k < UP_THREADS; ++k) DX_CUDA(cudaStreamWaitEvent(g_up[k].st, g_up_start, 0), "dx_upload");
     const size_t dst_size = src_kind == 0 ? 1 : 4, src_size = src_kind == 0 ? 1 : 8;
     const size_t per_buf = UP_BUF / dst_size;                       // elements per staging buffer
     const size_t n = (size_t)n_elems;
@@ -139,7 +145,9 @@ int dx_upload(void* dst_device, const void* src_host, int64_t n_elems, int32_t s
             cudaSetDevice(dev);
             UpLane& L = g_up[k];
             int b = 0;
-            bool busy[2] = {false, false};
+            // the staging buffers may still feed the last copies of the PREVIOUS call (rows, then vals, are uploaded back to
+            // back): every buffer waits for its own event before it is overwritten (a never-recorded event is complete)
+            bool busy[2] = {true, true};
             for (size_t pos = lo; pos < hi; pos += per_buf, b ^= 1) {
                 const size_t m = std::min(per_buf, hi - pos);
                 if (busy[b]) { cudaError_t e = cudaEventSynchronize(L.ev[b]); if (e != cudaSuccess) { errs[k] = e; return; } }

@@ -156,25 +156,38 @@ __device__ __forceinline__ void dx_chi2_sf(double stat, double df, double* p_ref
     }
 }
 
-// regularized incomplete beta I_x(a, b) (continued fraction, Numerical-Recipes style Lentz)
+// regularized incomplete beta I_x(a, b): the factor F = 2F1(a + b, 1; a + 1; x) of I_x = x^a (1-x)^b / (a B(a,b)) * F.
+// Power series when it is short (all terms positive: sum_n (a+b)_n / (a+1)_n x^n, x < 1/2 and (a+b) x < 200: at most a few hundred terms -- the Welch
+// test at a million degrees of freedom: a = 1/2, b = df/2, x = t^2 / (df + t^2), i.e. ~t^2/2 + 40 terms instead of ~sqrt(df)
+// rounds of the continued fraction with four divisions each); else the continued fraction (Numerical-Recipes style Lentz).
 __device__ __forceinline__ double dx_betacf(double a, double b, double x) {
+    if (x < 0.5 && (a + b) * x < 200.0) {
+        double term = 1.0, sum = 1.0;
+        const double ab = a + b, a1 = a + 1.0;
+        for (int n = 0; n < 4000; ++n) {
+            term *= (ab + (double)n) / (a1 + (double)n) * x;
+            sum += term;
+            if (term < sum * 1e-17) return sum;
+        }
+    }
     const double fpmin = 1e-300;
     const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    // (reciprocals instead of divisions: the recurrence is a serial chain of up to thousands of rounds when a is large)
     double c = 1.0, d = 1.0 - qab * x / qap;
     if (fabs(d) < fpmin) d = fpmin;
-    d = 1.0 / d;
+    d = __drcp_rn(d);
     double h = d;
     for (int m = 1; m < 5000; ++m) {
         const double m2 = 2.0 * m;
-        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+        double aa = m * (b - m) * x * __drcp_rn((qam + m2) * (a + m2));
         d = 1.0 + aa * d; if (fabs(d) < fpmin) d = fpmin;
-        c = 1.0 + aa / c; if (fabs(c) < fpmin) c = fpmin;
-        d = 1.0 / d;
+        c = 1.0 + aa * __drcp_rn(c); if (fabs(c) < fpmin) c = fpmin;
+        d = __drcp_rn(d);
         h *= d * c;
-        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+        aa = -(a + m) * (qab + m) * x * __drcp_rn((a + m2) * (qap + m2));
         d = 1.0 + aa * d; if (fabs(d) < fpmin) d = fpmin;
-        c = 1.0 + aa / c; if (fabs(c) < fpmin) c = fpmin;
-        d = 1.0 / d;
+        c = 1.0 + aa * __drcp_rn(c); if (fabs(c) < fpmin) c = fpmin;
+        d = __drcp_rn(d);
         const double del = d * c;
         h *= del;
         if (fabs(del - 1.0) < 1e-16) break;

@@ -241,7 +241,40 @@ dx_two_group_kernel(int64_t G, int K, int ga, int gb, double n0, double n1, cons
             } else {
                 __syncthreads();
             }
-            if (tid == 0) {
+            if (novf == 0) {
+                // counts only (the usual case): the tie blocks are the 65 count values in ascending order -- block b holds
+                // cnt0[b] + cnt1[b] cells -- so rank sum and tie term are a prefix sum and two integer reductions over the
+                // bins (exact: the same integers as the serial merge below, in any order)
+                __shared__ long long s_scan[TG_T];
+                __shared__ long long s_r[TG_T / 32], s_t[TG_T / 32];
+                const long long ta = (tid <= DX_HIST_BINS) ? (long long)s_cnt[0][tid] : 0;
+                const long long tt = (tid <= DX_HIST_BINS) ? ta + (long long)s_cnt[1][tid] : 0;
+                s_scan[tid] = tt;
+                __syncthreads();
+                for (int o = 1; o < TG_T; o <<= 1) {
+                    const long long add = (tid >= o) ? s_scan[tid - o] : 0;
+                    __syncthreads();
+                    s_scan[tid] += add;
+                    __syncthreads();
+                }
+                const long long cum = s_scan[tid] - tt;          // cells in the blocks below
+                long long rr = ta * (2 * cum + tt + 1), ti = tt * tt * tt - tt;
+                rr = dx_warp_sum_ll(rr); ti = dx_warp_sum_ll(ti);
+                if (lane == 0) { s_r[warp] = rr; s_t[warp] = ti; }
+                __syncthreads();
+                if (tid == 0) {
+                    for (int w = 0; w < TG_T / 32; ++w) { r1x2 += s_r[w]; tie += s_t[w]; }
+                    const double n = n0 + n1;
+                    const double u1 = 0.5 * (double)r1x2 - n0 * (n0 + 1.0) * 0.5;
+                    const double mu = n0 * n1 * 0.5;
+                    const double s = sqrt(n0 * n1 / 12.0 * ((n + 1.0) - (double)tie / (n * (n - 1.0))));
+                    double num = u1 - mu;
+                    num -= 0.5 * (double)((num > 0.0) - (num < 0.0));
+                    const double z = num / s;
+                    p_rank = dx_clip(erfc(fabs(z) * 0.70710678118654752440), 0.0, 1.0);
+                    if (isnan(z)) p_rank = NAN;
+                }
+            } else if (tid == 0) {
                 // serial merge of tie blocks in ascending value order (exact integers)
                 long long cum = 0;
                 int i = 0;
@@ -281,12 +314,21 @@ dx_two_group_kernel(int64_t G, int K, int ga, int gb, double n0, double n1, cons
     if (tid == 0) {
         double* o = out + g * DX_TG_NCOL;
         o[DX_TG_MEAN0] = mean0; o[DX_TG_MEAN1] = mean1; o[DX_TG_VAR0] = var0; o[DX_TG_VAR1] = var1;
-        o[DX_TG_PVAL_T] = dx_welch_p(mean0, mean1, var0, var1, n0, n1);
+        // (the Welch p-value -- a long serial continued fraction at a million degrees of freedom -- is filled in by
+        // dx_two_group_welch_kernel, a thread per gene, instead of one thread of every CTA)
         o[DX_TG_PVAL_RANK] = p_rank;
         if (u1x2_out) u1x2_out[g] = r1x2 - (long long)(n0 * (n0 + 1.0));
         if (tie_out) tie_out[g] = tie;
         if (flags_out) flags_out[g] = flags;
     }
+}
+
+// Welch t-test p-values of the rows dx_two_group_kernel wrote (stats.py:116-178 arithmetic from the moments): a thread per gene
+__global__ void dx_two_group_welch_kernel(int64_t G, double n0, double n1, double* __restrict__ out) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    double* o = out + g * DX_TG_NCOL;
+    o[DX_TG_PVAL_T] = dx_welch_p(o[DX_TG_MEAN0], o[DX_TG_MEAN1], o[DX_TG_VAR0], o[DX_TG_VAR1], n0, n1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1146,6 +1188,9 @@ cudaError_t dx_launch_two_group(int64_t G, int K, int ga, int gb, double n0, dou
     if (G <= 0) return cudaSuccess;
     dx_two_group_kernel<<<(unsigned)G, TG_T, 0, s>>>(G, K, ga, gb, n0, n1, tail, ovf_count, indptr, ovf_val, ovf_group, do_rank,
                                                      out, u1x2, tie, flags);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    dx_two_group_welch_kernel<<<(unsigned)((G + 63) / 64), 64, 0, s>>>(G, n0, n1, out);
     return cudaGetLastError();
 }
 

@@ -43,32 +43,67 @@ def gene_ranges(n_genes, size, weights=None):
     return [(cuts[i], cuts[i + 1]) for i in range(size)]
 
 
+def gene_weights(data):
+    """Per-gene non-zero counts of a host matrix (the weights of the gene cuts), or None when counting would cost a pass
+    over a matrix that is not sparse.  CSC: the gene pointers; CSR (what AnnData holds): one bincount of the column indices."""
+    if data is None or not scipy.sparse.issparse(data):
+        return None
+    if scipy.sparse.isspmatrix_csc(data):
+        return np.diff(data.indptr)
+    if scipy.sparse.isspmatrix_csr(data):
+        return np.bincount(data.indices, minlength=data.shape[1])
+    return None
+
+
 def gene_range(n_genes, rank, size, data=None):
-    weights = None
-    if size > 1 and data is not None and scipy.sparse.issparse(data) and scipy.sparse.isspmatrix_csc(data):
-        weights = np.diff(data.indptr)
+    weights = gene_weights(data) if size > 1 else None
     return gene_ranges(n_genes, size, weights)[rank]
 
 
-def gather_genes(w, tensors, n_genes_total):
-    """All-gather per-gene rows (leading dimension = genes of the local range) into full tables.
-    Ranges may have different lengths: rows are padded to the longest range for the collective."""
+def gather_genes(w, tensors, n_genes_total, counts=None):
+    """All-gather per-gene rows (leading dimension = genes of the local range) into full tables with ONE collective:
+    the rows of all tensors are packed side by side into one byte row per gene, padded to the longest gene range, gathered
+    (``all_gather_into_tensor``: NCCL over NVLink on GPUs, gloo in the CPU tests) and unpacked.  ``counts``: the lengths of
+    all ranks' gene ranges when the caller knows them (the estimator does: every rank computes the same cuts); without it
+    one more tiny collective exchanges them."""
     if w.size == 1:
         return tensors
+    names = list(tensors)
+    any_t = tensors[names[0]]
+    g_local, device = int(any_t.shape[0]), any_t.device
+    if counts is None:
+        local = torch.tensor([g_local], dtype=torch.int64, device=device)
+        gathered = torch.empty(w.size, dtype=torch.int64, device=device)
+        td.all_gather_into_tensor(gathered, local)
+        counts = [int(c) for c in gathered.tolist()]
+    assert len(counts) == w.size and counts[w.rank] == g_local and sum(counts) == n_genes_total, "gene ranges disagree"
+    gmax = max(max(counts), 1)
+    widths, shapes = [], []
+    for name in names:
+        t = tensors[name]
+        assert t.shape[0] == g_local, "every tensor holds one row per local gene"
+        shapes.append(tuple(t.shape[1:]))
+        row = int(np.prod(t.shape[1:], dtype=np.int64)) * t.element_size()
+        widths.append((row + 7) // 8 * 8)          # 8-byte columns keep every field aligned for the typed views
+    send = torch.zeros((gmax, sum(widths)), dtype=torch.uint8, device=device)
+    col = 0
+    for name, wd in zip(names, widths):
+        t = tensors[name].contiguous()
+        raw = t.reshape(g_local, -1).view(torch.uint8) if g_local else t.reshape(0, 0).view(torch.uint8)
+        send[:g_local, col:col + raw.shape[1]] = raw
+        col += wd
+    recv = torch.empty((w.size * gmax, sum(widths)), dtype=torch.uint8, device=device)
+    td.all_gather_into_tensor(recv, send)
+    recv = recv.view(w.size, gmax, sum(widths))
     out = {}
-    any_t = next(iter(tensors.values()))
-    local = torch.tensor([any_t.shape[0]], dtype=torch.int64, device=any_t.device)
-    counts = [torch.zeros_like(local) for _ in range(w.size)]
-    td.all_gather(counts, local)
-    counts = [int(c.item()) for c in counts]
-    gmax = max(counts)
-    for name, t in tensors.items():
-        pad = torch.zeros((gmax,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        pad[:t.shape[0]] = t
-        parts = [torch.empty_like(pad) for _ in range(w.size)]
-        td.all_gather(parts, pad.contiguous())
-        out[name] = torch.cat([parts[r][:counts[r]] for r in range(w.size)], dim=0)
-        assert out[name].shape[0] == n_genes_total, "gathered gene count mismatch"
+    col = 0
+    for name, wd, shp in zip(names, widths, shapes):
+        t = tensors[name]
+        nbytes = int(np.prod(shp, dtype=np.int64)) * t.element_size()
+        parts = [recv[r, :counts[r], col:col + nbytes] for r in range(w.size)]
+        flat = torch.cat(parts, dim=0).contiguous()
+        out[name] = flat.view(t.dtype).reshape((n_genes_total,) + shp)
+        col += wd
     return out
 
 

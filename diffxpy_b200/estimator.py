@@ -274,7 +274,10 @@ class Estimator:
         g_total = idata.num_features
         # gene shard of this rank (contiguous gene ranges, no collective on the data path)
         self._world = dxdist.world(self._distributed)
-        lo, hi = dxdist.gene_range(g_total, self._world.rank, self._world.size, data=idata.data)
+        # (equal non-zero counts for sparse input, CSR or CSC; every rank computes the same cuts from the host matrix)
+        self._gene_ranges = dxdist.gene_ranges(g_total, self._world.size,
+                                               dxdist.gene_weights(idata.data) if self._world.size > 1 else None)
+        lo, hi = self._gene_ranges[self._world.rank]
         self._gene_range = (lo, hi)
         with torch.cuda.device(dev):
             self.shard = dxdevice.take(idata.data, dev, None if self._world.size == 1 else (lo, hi))
@@ -579,7 +582,8 @@ class Estimator:
             packed = dxdist.gather_genes(self._world, {
                 "a_var": r["a_var"].t().contiguous(), "b_var": r["b_var"].t().contiguous(),
                 "fim_inv": r["fim_inv"], "ll": r["ll"], "jac": r["jac"],
-                "niter": r["niter"], "flags": r["flags"]}, self.input_data.num_features)
+                "niter": r["niter"], "flags": r["flags"]}, self.input_data.num_features,
+                counts=[b - a for a, b in self._gene_ranges])
         self._host = dict(
             a_var=np.ascontiguousarray(packed["a_var"].cpu().numpy().T),
             b_var=np.ascontiguousarray(packed["b_var"].cpu().numpy().T),
@@ -677,5 +681,5 @@ class Estimator:
         with torch.cuda.device(self._dev):
             s1, _ = self.shard.gene_moments(None)
             out = dxdist.gather_genes(self._world, {"m": s1 / self.input_data.num_observations},
-                                      self.input_data.num_features)
+                                      self.input_data.num_features, counts=[b - a for a, b in self._gene_ranges])
         return out["m"].cpu().numpy()

@@ -34,6 +34,10 @@ def _worker(rank, size, port, g, weights, outdir):
             "fim": torch.arange(lo, hi, dtype=torch.float64)[:, None, None] * torch.ones(1, 2, 2, dtype=torch.float64),
         }
         full = dxdist.gather_genes(w, rows, g)
+        # the estimator's call: every rank knows all range lengths, so the count exchange is skipped -- same tables
+        known = dxdist.gather_genes(w, rows, g, counts=[b - a for a, b in dxdist.gene_ranges(g, size, weights)])
+        for k in rows:
+            assert torch.equal(full[k], known[k]) and full[k].dtype == rows[k].dtype
         np.save(os.path.join(outdir, "a_%d.npy" % rank), full["a_var"].numpy())
         np.save(os.path.join(outdir, "n_%d.npy" % rank), full["niter"].numpy())
         np.save(os.path.join(outdir, "f_%d.npy" % rank), full["fim"].numpy())
@@ -53,3 +57,15 @@ def test_gather_genes_world_size_2(tmp_path):
         np.testing.assert_array_equal(a[:, 0], np.arange(g))
         np.testing.assert_array_equal(n, np.arange(g))
         np.testing.assert_array_equal(f[:, 1, 1], np.arange(g))
+
+
+def test_gene_weights_from_csr_and_csc_agree():
+    """Gene cuts by non-zero count for the input diffxpy actually receives (CSR, utils.py:20-33) as for gene-major input."""
+    import scipy.sparse
+    rng = np.random.default_rng(0)
+    dense = rng.poisson(0.3, (50, 23)) * (rng.uniform(size=(50, 23)) < np.linspace(0.05, 0.9, 23)[None, :])
+    csr, csc = scipy.sparse.csr_matrix(dense), scipy.sparse.csc_matrix(dense)
+    np.testing.assert_array_equal(dxdist.gene_weights(csr), dxdist.gene_weights(csc))
+    np.testing.assert_array_equal(dxdist.gene_weights(csr), (dense != 0).sum(axis=0))
+    assert dxdist.gene_weights(dense) is None
+    assert dxdist.gene_range(23, 1, 3, data=csr) == dxdist.gene_range(23, 1, 3, data=csc)
