@@ -61,28 +61,34 @@ def _group_rows_exact(mat):
 
 def group_rows(mat):
     """Distinct rows of a float64 matrix and the row -> group map (byte-wise; -0.0 normalised).  Groups are
-    numbered in the byte order of the rows, like ``np.unique`` on the raw records.  Rows are first reduced to
-    a 64-bit multiplicative hash (one cheap 1-D sort instead of a sort of wide records); the grouping is then
-    verified exactly and recomputed the slow way in the (astronomically unlikely) event of a collision."""
+    numbered in the byte order of the rows, like ``np.unique`` on the raw records.  Rows are reduced to a 64-bit
+    multiplicative hash (integer matrix-vector product: no sort of wide records, no 2-d temporary) and grouped with a hash
+    table; a second, independent 64-bit hash must be constant inside every group (a wrong merge would need a simultaneous
+    collision of both, ~n^2 2^-128), else -- and for anything unusual -- the exact method takes over."""
     mat = np.ascontiguousarray(mat + 0.0)
     if mat.shape[1] == 0:
         return mat[:1], np.zeros(mat.shape[0], dtype=np.int64)
     if mat.shape[0] < 4096:
         return _group_rows_exact(mat)
     bits = mat.view(np.uint64)
-    mult = np.resize(_HASH_MULT, mat.shape[1]) * (2 * np.arange(mat.shape[1], dtype=np.uint64) + np.uint64(1))
+    # (0.0 / 1.0 / 2.0 ... differ in their top bits only, which a multiplication pushes out of the word: fold the upper
+    # half onto the lower one first -- a bijection per element, so equal rows stay equal and distinct rows distinct)
+    mixed = bits ^ (bits >> np.uint64(32))
+    odd = 2 * np.arange(mat.shape[1], dtype=np.uint64) + np.uint64(1)
     with np.errstate(over="ignore"):
-        h = (bits * mult[None, :]).sum(axis=1, dtype=np.uint64)
+        h = mixed @ (np.resize(_HASH_MULT, mat.shape[1]) * odd)
         h ^= h >> np.uint64(29)
+        h2 = mixed @ (np.resize(_HASH_MULT[::-1], mat.shape[1]) * (odd + np.uint64(2 * mat.shape[1])))
     # hash table instead of a sort: codes in order of first appearance, idx = first row of every distinct hash
-    inv, _ = pd.factorize(h)
+    inv, uniq_h = pd.factorize(h)
     inv = np.asarray(inv, dtype=np.int64)
-    idx = np.flatnonzero(~pd.Series(h).duplicated().to_numpy())
+    if uniq_h.shape[0] > 65536:
+        return _group_rows_exact(mat)
+    idx = np.empty(uniq_h.shape[0], dtype=np.int64)
+    idx[inv[::-1]] = np.arange(mat.shape[0] - 1, -1, -1)          # (the last write wins: the first row of every code)
+    if not np.array_equal(h2[idx][inv], h2):
+        return _group_rows_exact(mat)
     reps = mat[idx]
-    if idx.shape[0] > 65536:
-        return _group_rows_exact(mat)
-    if not np.array_equal(reps[inv].view(np.uint64), bits):
-        return _group_rows_exact(mat)
     # renumber in the byte order of the representative rows (what the exact method returns)
     uniq, order_inv = _group_rows_exact(reps)
     if uniq.shape[0] != reps.shape[0]:

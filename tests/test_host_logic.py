@@ -288,3 +288,33 @@ def test_anndata_like_inputs_supply_gene_names_and_sample_description():
     assert sf.shape[0] == 4
     with pytest.raises(AssertionError):
         utils.parse_size_factors(np.array([1.0, 0.0, 0.5, 1.5]), adata, sd)
+
+
+def test_group_rows_many_small_integer_columns_match_the_exact_grouping():
+    """0 / 1 / 2-valued designs differ only in the top bits of their float64 patterns; the row hash must still separate
+    them (a weak hash silently falls back to the slow exact path -- or worse, merges rows)."""
+    from diffxpy_b200.estimator import group_rows, _group_rows_exact
+    rng = np.random.default_rng(5)
+    n = 20000
+    cond, batch, extra = rng.integers(0, 2, n), rng.integers(0, 8, n), rng.integers(0, 3, n)
+    onehot = (batch[:, None] == np.arange(1, 8)[None, :]).astype(float)
+    mat = np.concatenate([np.ones((n, 1)), cond[:, None], onehot, onehot, extra[:, None]], axis=1).astype(float)
+    mat[::7, 1] *= -0.0          # -0.0 and 0.0 are the same design value
+    uniq, inv = group_rows(mat)
+    uniq_e, inv_e = _group_rows_exact(np.ascontiguousarray(mat + 0.0))
+    assert uniq.shape[0] == 48
+    np.testing.assert_array_equal(uniq, uniq_e)
+    np.testing.assert_array_equal(inv, inv_e)
+    np.testing.assert_array_equal(uniq[inv], mat + 0.0)
+
+
+def test_bench_workload_helpers():
+    """bench.py --workload lrt / spline / rank: the host-side pieces that run without a GPU."""
+    import importlib
+    bw = importlib.import_module("bench_workloads")
+    assert set(bw.METRICS) == set(bw.DEFAULT_STEPS) == {"lrt", "spline", "rank"}
+    xd, sf = bw.spline_design(5000)
+    assert xd.shape == (5000, 12) and np.linalg.matrix_rank(xd) == 12          # configs[3]: 11 spline columns + intercept
+    assert np.all(xd[:, 0] == 1.0) and np.all(xd[:, 1:] >= 0.0) and np.all((sf >= 0.5) & (sf <= 1.5))
+    peak, src = bw._peaks()
+    assert peak > 1000.0 and "GB/s" in src or "MEASURED_PEAKS" in src
