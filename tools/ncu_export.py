@@ -41,5 +41,11 @@ for rep in sys.argv[2:]:
         except Exception:
             pass
 open(prefix + "_ncu_summary.txt", "w").write("\n".join(lines) + "\n")
-json.dump(traffic, open(os.path.join(os.path.dirname(prefix), "traffic.json"), "w"), indent=1)
+tpath = os.path.join(os.path.dirname(prefix), "traffic.json")
+try:          # keep the hand-written entries (instruction counts, fp64 shares) of kernels this export does not cover
+    merged = json.load(open(tpath))
+except Exception:
+    merged = {}
+merged.update(traffic)
+json.dump(merged, open(tpath, "w"), indent=1)
 print("\n".join(lines[:12])); print(traffic)
