@@ -659,16 +659,19 @@ int dx_ingest_private_bins(int K) {
     return yp;
 }
 
-// dynamic gene queues: a ring of zero-initialised counters so that concurrent launches (different streams)
-// never share one
-__device__ unsigned int g_dx_queue_slots[256];
+// dynamic gene queues: a ring of counters, zeroed on the launch stream right before the kernel that uses one, so that
+// concurrent launches (different streams, a replayed CUDA graph next to eager launches) do not share one.  A slot is handed
+// out again after DX_QUEUE_SLOTS further launches of the process: more launches than that in flight at once would alias
+// (the library itself keeps at most a few dozen in flight per device).
+#define DX_QUEUE_SLOTS 4096
+__device__ unsigned int g_dx_queue_slots[DX_QUEUE_SLOTS];
 
 cudaError_t dx_queue_acquire(cudaStream_t stream, unsigned int** out) {
     static std::atomic<unsigned> seq{0};
     void* base = nullptr;
     cudaError_t e = cudaGetSymbolAddress(&base, g_dx_queue_slots);
     if (e != cudaSuccess) return e;
-    *out = static_cast<unsigned int*>(base) + (seq.fetch_add(1u) & 255u);
+    *out = static_cast<unsigned int*>(base) + (seq.fetch_add(1u) % DX_QUEUE_SLOTS);
     return cudaMemsetAsync(*out, 0, sizeof(unsigned int), stream);
 }
 

@@ -7,7 +7,7 @@
 #define DX_INGEST_THREADS 128
 
 int dx_ingest_private_bins(int K);
-// zero-initialised work-queue counter for one launch (ring of 256 slots, safe across concurrent streams)
+// zero-initialised work-queue counter for one launch (ring of 4096 slots, safe across concurrent streams)
 cudaError_t dx_queue_acquire(cudaStream_t stream, unsigned int** out);
 cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,
                              const uint8_t* cell_group, int K, uint32_t* hist, int32_t* ovf_count,

@@ -40,6 +40,26 @@ def cuda_device(device=None):
 _STAGE = {}     # (device index) -> two pinned staging buffers + their events
 
 
+_WARNED_F32 = [False]
+
+
+def _warn_if_rounded_to_float32(a):
+    """The shard stores values as float32: exact for counts below 2^24, but float64 normalised / log-transformed values are
+    rounded (distinct values may become ties of the rank test; moments change at ~1e-7 relative).  A strided sample of the
+    array decides; the warning is logged once per process."""
+    if _WARNED_F32[0] or a.dtype != np.float64 or a.size == 0:
+        return
+    flat = a.reshape(-1)
+    sample = flat[::max(1, flat.shape[0] // 65536)]
+    if np.any(sample.astype(np.float32).astype(np.float64) != sample):
+        _WARNED_F32[0] = True
+        import logging
+        logging.getLogger("diffxpy").warning(
+            "count shard: float64 values that are not representable in float32 are rounded to float32 on the device "
+            "(raw counts are unaffected; normalised / log-transformed values keep ~7 significant digits, and values that "
+            "differ only beyond that become ties of the rank test)")
+
+
 def upload(arr, dev, dtype=None):
     """Host ndarray -> device tensor of ``dtype``.  Large pageable arrays go through dx_upload: eight host threads stage
     slices of the array through pinned buffers (converting float64 -> float32 / int64 -> int32 on the way), which keeps
@@ -47,6 +67,8 @@ def upload(arr, dev, dtype=None):
     a = np.ascontiguousarray(arr)
     t = torch.from_numpy(a)
     dtype = dtype or t.dtype
+    if dtype == torch.float32:
+        _warn_if_rounded_to_float32(a)
     n = a.size
     kind = None
     if a.ndim == 1 and a.nbytes >= (32 << 20):
@@ -273,6 +295,7 @@ class CountShard:
             raise ValueError("data must be a 2-d (cells x genes) matrix")
         if gene_range is not None:
             arr = arr[:, gene_range[0]:gene_range[1]]
+        _warn_if_rounded_to_float32(arr)
         shard = CountShard.from_dense_device(torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(dev))
         shard.gene_offset = 0 if gene_range is None else gene_range[0]
         return shard

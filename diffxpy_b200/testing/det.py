@@ -91,23 +91,21 @@ class _DifferentialExpressionTest(metaclass=abc.ABCMeta):
             self._qval = self._correction(method=method).copy()
         return self._qval
 
+    @staticmethod
+    def _log10_floor(values, floor):
+        """log10 of p- or q-values for plotting: zeros and underflows are lifted to the smallest positive double first,
+        NaNs become 1 before the clip (so they end at 0 like a p-value of one), and nothing goes below ``floor``
+        (behaviour of det.py:120-160)."""
+        v = np.asarray(values, dtype=float).reshape(-1)
+        out = np.log10(np.maximum(v, np.nextafter(0, 1)))          # (NaN stays NaN through maximum)
+        out = np.where(np.isnan(out), 1.0, out)
+        return np.minimum(np.maximum(out, floor), 0.0)
+
     def log10_pval_clean(self, log10_threshold=-30):
-        """det.py:120-139"""
-        pvals = np.reshape(self.pval, -1).astype(dtype=float)
-        pvals = np.clip(pvals, np.nextafter(0, 1), np.inf)
-        log10_pval_clean = np.log(pvals) / np.log(10)
-        log10_pval_clean[np.isnan(log10_pval_clean)] = 1
-        log10_pval_clean = np.clip(log10_pval_clean, log10_threshold, 0, log10_pval_clean)
-        return log10_pval_clean
+        return self._log10_floor(self.pval, log10_threshold)
 
     def log10_qval_clean(self, log10_threshold=-30):
-        """det.py:141-160"""
-        qvals = np.reshape(self.qval, -1).astype(dtype=float)
-        qvals = np.clip(qvals, np.nextafter(0, 1), np.inf)
-        log10_qval_clean = np.log(qvals) / np.log(10)
-        log10_qval_clean[np.isnan(log10_qval_clean)] = 1
-        log10_qval_clean = np.clip(log10_qval_clean, log10_threshold, 0, log10_qval_clean)
-        return log10_qval_clean
+        return self._log10_floor(self.qval, log10_threshold)
 
     @abc.abstractmethod
     def summary(self, **kwargs) -> pd.DataFrame:
@@ -115,25 +113,26 @@ class _DifferentialExpressionTest(metaclass=abc.ABCMeta):
 
     def _threshold_summary(self, res: pd.DataFrame, qval_thres=None, fc_upper_thres=None, fc_lower_thres=None,
                            mean_thres=None) -> pd.DataFrame:
-        """det.py:166-205"""
-        assert fc_lower_thres > 0 if fc_lower_thres is not None else True, "supply positive fc_lower_thres"
-        assert fc_upper_thres > 0 if fc_upper_thres is not None else True, "supply positive fc_upper_thres"
+        """Row filter of ``summary()`` (rules of det.py:166-205): q-value at most ``qval_thres`` (NaN q-values drop out),
+        fold change outside (fc_lower_thres, fc_upper_thres) on the log2 scale of the table, mean at least ``mean_thres``.
+        All given filters must hold."""
+        for name, thres in (("fc_lower_thres", fc_lower_thres), ("fc_upper_thres", fc_upper_thres)):
+            assert thres is None or thres > 0, "supply positive %s" % name
+        keep = np.ones(res.shape[0], dtype=bool)
         if qval_thres is not None:
-            qvals = res['qval'].values
-            qval_include = np.logical_not(np.isnan(qvals))
-            qval_include[qval_include] = qvals[qval_include] <= qval_thres
-            res = res.iloc[qval_include, :]
-        if fc_upper_thres is not None and fc_lower_thres is None:
-            res = res.iloc[res['log2fc'].values >= np.log(fc_upper_thres) / np.log(2), :]
-        elif fc_upper_thres is None and fc_lower_thres is not None:
-            res = res.iloc[res['log2fc'].values <= np.log(fc_lower_thres) / np.log(2), :]
-        elif fc_upper_thres is not None and fc_lower_thres is not None:
-            res = res.iloc[np.logical_or(
-                res['log2fc'].values <= np.log(fc_lower_thres) / np.log(2),
-                res['log2fc'].values >= np.log(fc_upper_thres) / np.log(2)), :]
+            with np.errstate(invalid="ignore"):
+                keep &= res["qval"].values <= qval_thres          # (False for NaN)
+        log2fc = res["log2fc"].values
+        outside = []
+        if fc_lower_thres is not None:
+            outside.append(log2fc <= np.log2(fc_lower_thres))
+        if fc_upper_thres is not None:
+            outside.append(log2fc >= np.log2(fc_upper_thres))
+        if outside:
+            keep &= np.logical_or.reduce(outside)
         if mean_thres is not None:
-            res = res.iloc[res['mean'].values >= mean_thres, :]
-        return res
+            keep &= res["mean"].values >= mean_thres
+        return res.iloc[keep, :]
 
 
 class _DifferentialExpressionTestSingle(_DifferentialExpressionTest, metaclass=abc.ABCMeta):

@@ -871,3 +871,42 @@ def test_wald_with_size_factors_null_calibration(de):
                        size_factors=sf, gene_names=["g%d" % i for i in range(g)])
     ks = scipy.stats.kstest(res.pval, "uniform").pvalue
     assert ks > 0.05, "null p-values are not uniform: KS p = %g" % ks
+
+
+def test_cfg3_design_full_cell_count_eight_dispersion_coefficients(de):
+    """BASELINE.json configs[2] at the full cell count: '~1+condition+batch' location (9), '~1+batch' scale model
+    (8 dispersion coefficients -> general grouped K_fit, Newton in 8 dimensions), 100k cells, a few genes."""
+    rng = np.random.default_rng(42)
+    n, g = 100_000, 6
+    cond, batch = rng.integers(0, 2, n), rng.integers(0, 8, n)
+    xd = np.concatenate([np.ones((n, 1)), cond[:, None], (batch[:, None] == np.arange(1, 8)[None, :])], axis=1).astype(float)
+    zd = np.delete(xd, 1, axis=1)
+    log_mu = np.log([0.02, 0.1, 0.3, 0.6, 1.0, 3.0])
+    beta_b = rng.normal(0, 0.2, (8, g)); beta_b[0] = 0
+    r_b = np.exp(rng.normal(0.5, 0.3, (8, g)))
+    mu = np.exp(log_mu[None, :] + 0.4 * cond[:, None] * (np.arange(g) % 2)[None, :] + beta_b[batch])
+    y = rng.poisson(rng.gamma(r_b[batch], mu / r_b[batch])).astype(np.float64)
+    est = _fit(de, y, xd, zd)
+    assert est._plan["kind"] == "grouped" and est.b_var.shape[0] == 8
+    ref = onb.fit_nb(y, xd, zd, method_b="newton")
+    sd = np.sqrt(np.einsum("gii->gi", ref["fisher_inv"])).T
+    assert np.all(np.abs(est.a_var - ref["a_var"]) <= 1e-5 * np.abs(ref["a_var"]) + 2e-4 * sd)
+    np.testing.assert_allclose(est.b_var, ref["b_var"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(est.log_likelihood, ref["log_likelihood"], rtol=1e-9)
+    np.testing.assert_array_equal(est.niter, ref["niter"])
+    np.testing.assert_array_equal(est.error_codes, ref["error_codes"])
+
+
+def test_niter_against_the_reference_faithful_brent_oracle(de, golden_dir):
+    """How often the CUDA schedule (Newton scale step) takes exactly as many steps as the reference-faithful oracle
+    (scipy Brent scale step) on the two frozen problems: reported, and required for the bulk of the genes.  The
+    coefficients agree to the north-star tolerance on every gene off the Poisson plateau regardless."""
+    report = {}
+    for name in ("nbglm_cfg1.npz", "nbglm_batch.npz"):
+        gd = np.load(os.path.join(golden_dir, name))
+        est = _fit(de, gd["x"].astype(np.float64), gd["design_loc"], gd["design_scale"])
+        frozen = (gd["newton_error_codes"] & onb.FLAG_SCALE_FROZEN) != 0
+        same = est.niter == gd["brent_niter"]
+        report[name] = (int(same[~frozen].sum()), int((~frozen).sum()), int(same[frozen].sum()), int(frozen.sum()))
+        assert same[~frozen].mean() >= 0.9, "niter differs from the Brent oracle on more than 10 %% of the genes: %s" % (report,)
+    print("identical niter vs Brent oracle (off plateau: same / genes, on plateau: same / genes):", report)

@@ -318,3 +318,46 @@ def test_bench_workload_helpers():
     assert np.all(xd[:, 0] == 1.0) and np.all(xd[:, 1:] >= 0.0) and np.all((sf >= 0.5) & (sf <= 1.5))
     peak, src = bw._peaks()
     assert peak > 1000.0 and "GB/s" in src or "MEASURED_PEAKS" in src
+
+
+def test_result_object_clean_logs_and_threshold_rules():
+    """det.py:120-205 behaviour of the result base class: cleaned log10 p-values and the summary() row filters."""
+    from diffxpy_b200.testing.det import _DifferentialExpressionTest as Base
+    p = np.array([0.0, 1e-320, 1e-40, 1e-5, 0.5, 1.0, np.nan, 2.0])
+    np.testing.assert_allclose(Base._log10_floor(p, -30), [-30, -30, -30, -5, np.log10(0.5), 0, 0, 0], rtol=1e-15)
+    np.testing.assert_allclose(Base._log10_floor(p, -50)[:3], [-50, -50, -40], rtol=1e-15)
+
+    class T(Base):
+        gene_ids = None
+        x = None
+
+        def log_fold_change(self, base=np.e, **kwargs):
+            return None
+
+        def summary(self, **kwargs):
+            return None
+    df = pd.DataFrame({"gene": list("abcdef"), "qval": [0.01, np.nan, 0.2, 0.04, 0.9, 0.03],
+                       "log2fc": [2.0, 3.0, -2.0, 0.1, -3.0, 1.0], "mean": [1.0, 5.0, 0.1, 2.0, 3.0, 0.5]})
+    t = T()
+    assert list(t._threshold_summary(df, qval_thres=0.05)["gene"]) == ["a", "d", "f"]          # NaN q-values drop out
+    assert list(t._threshold_summary(df, fc_upper_thres=2.0)["gene"]) == ["a", "b", "f"]
+    assert list(t._threshold_summary(df, fc_lower_thres=0.5)["gene"]) == ["c", "e"]
+    assert list(t._threshold_summary(df, fc_upper_thres=4.0, fc_lower_thres=0.25)["gene"]) == ["a", "b", "c", "e"]
+    assert list(t._threshold_summary(df, qval_thres=0.05, fc_upper_thres=2.0, mean_thres=0.8)["gene"]) == ["a"]
+    with pytest.raises(AssertionError):
+        t._threshold_summary(df, fc_lower_thres=-1.0)
+
+
+def test_float64_values_rounded_to_float32_are_reported(caplog):
+    """device.py stores float32 values: non-representable float64 input (log-normalised data) is reported once."""
+    import logging
+    from diffxpy_b200 import device
+    device._WARNED_F32[0] = False
+    with caplog.at_level(logging.WARNING, logger="diffxpy"):
+        device._warn_if_rounded_to_float32(np.arange(1000, dtype=np.float64))          # counts: exact
+        assert not caplog.records
+        device._warn_if_rounded_to_float32(np.log1p(np.arange(1000, dtype=np.float64) / 3.0))
+        assert len(caplog.records) == 1 and "float32" in caplog.records[0].getMessage()
+        device._warn_if_rounded_to_float32(np.log1p(np.arange(1000, dtype=np.float64) / 7.0))
+        assert len(caplog.records) == 1          # once per process
+    device._WARNED_F32[0] = False
