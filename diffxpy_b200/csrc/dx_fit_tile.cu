@@ -66,7 +66,8 @@ struct Lay {          // shared-memory layout (offsets in doubles)
     int rn;                         // [p][GT] sum over the non-zero cells of y q x_j
     int pair;                       // uint8 entry -> (j, k) tables
     int tile;                       // start of the region shared by the passes and the small dense algebra between them
-    int Z, W, S, X, D, Ls, Y, NZ;   // inside the region
+    int Z, W, S, X, D, Ls, Y, YI, NZ;   // inside the region; X / D / Ls / Y / YI / NZ exist twice (tile parity): second copy at
+    int stg, xstg;                  // + stg (Ls, Y, YI, NZ) resp. + xstg (X, D)
     int scratch;                    // inside the region, behind the reduced pass result
     int total_bytes;
 };
@@ -93,8 +94,11 @@ __host__ __device__ inline Lay make_layout(int p, int ps) {
     L.S = t; t += CT * WST;
     L.Ls = t; t += CT;
     L.Y = t; t += GT * CT / 2;
+    L.YI = t; t += GT * CT / 8;
     L.NZ = t; t += GT * (CT + 8) / 8;
     t = (t + 1) & ~1;
+    L.stg = t - L.Ls;
+    t += L.stg;
     const int pm = (p > ps) ? p : ps;
     L.scratch = GT * ZWM;
     int need = L.scratch + NWP * (pm * pm + 2 * pm);          // extraction / solves next to the reduced pass result
@@ -105,6 +109,8 @@ __host__ __device__ inline Lay make_layout(int p, int ps) {
     // sizes that depend on the design width (X, D relative to the region like the other pass arrays)
     L.X = o - L.tile; o += p * XST; o = (o + 1) & ~1;
     L.D = o - L.tile; o += SCONST ? 0 : ps * XST; o = (o + 1) & ~1;
+    L.xstg = o - L.tile - L.X;
+    o += L.xstg;
     L.a = o; o += p * GT; L.qa = o; o += p * GT; L.delta = o; o += p * GT; L.rhs = o; o += p * GT; L.rn = o; o += p * GT;
     L.b = o; o += ps * GT; L.bt = o; o += ps * GT; L.qb = o; o += ps * GT; L.sb = o; o += ps * GT; L.gb = o; o += ps * GT;
     L.hg = o; o += SCONST ? 0 : GT * ps * ps;
@@ -226,9 +232,12 @@ __global__ void __launch_bounds__(NT, MINB) dx_fit_tile_kernel(const TileArgs A)
     uint8_t* const pb = pa + ZW; uint8_t* const pas = pb + ZW; uint8_t* const pbs = pas + 96;
     double* const tile = sm + L.tile;
     double* const Zs = tile + L.Z; double* const Ws = tile + L.W; double* const Ss = tile + L.S;
-    double* const Xs = tile + L.X; double* const Ds = tile + L.D; double* const Lsf = tile + L.Ls;
-    float* const Ys = reinterpret_cast<float*>(tile + L.Y);
-    uint8_t* const NZl = reinterpret_cast<uint8_t*>(tile + L.NZ);          // [GT][CT + 8]: non-zero cells of the tile, count first
+    // staging buffers of a cell tile, twice (tile parity): design rows, offsets, dense values of the genes' columns, the
+    // table index of every value (255: outside the tables), the list of the non-zero cells per gene
+    double* const Xs0 = tile + L.X; double* const Ds0 = tile + L.D; double* const Lsf0 = tile + L.Ls;
+    float* const Ys0 = reinterpret_cast<float*>(tile + L.Y);
+    uint8_t* const Yi0 = reinterpret_cast<uint8_t*>(tile + L.YI);
+    uint8_t* const NZl0 = reinterpret_cast<uint8_t*>(tile + L.NZ);
     double* const Cred = tile;
     double* const scratch = tile + L.scratch;
     __shared__ int s_tile;
@@ -268,7 +277,6 @@ __global__ void __launch_bounds__(NT, MINB) dx_fit_tile_kernel(const TileArgs A)
         constexpr int NEK = (KIND == PASS_LOC) ? NE : 3;          // entry slots of the contraction
         constexpr int NEW = (KIND == PASS_LOC) ? NE : 2;          // slots [0, NEW) are weighted by Ws, the rest by Ss
         constexpr int ZWK = 32 * NEK;
-        const double* const dsrc_tile = (KIND == PASS_LOC) ? Xs : Ds;
         if (tid == 0) atomicAdd(&g_tile_counters[KIND], 1ull);
         __syncthreads();
         // per-gene constants of the pass
@@ -338,7 +346,7 @@ __global__ void __launch_bounds__(NT, MINB) dx_fit_tile_kernel(const TileArgs A)
                     dr[i] = (j < ps && c0 + c < N) ? A.ds[(int64_t)j * N + c0 + c] : 0.0;
                 }
             }
-            if (tid < CT) lr = (A.log_sf && c0 + tid < N) ? A.log_sf[c0 + tid] : 0.0;
+            if (tid < CT) lr = (c0 + tid < N) ? (A.log_sf ? A.log_sf[c0 + tid] : 0.0) : DX_ETA_MIN;          // (padding: mu ~ 1e-130)
 #pragma unroll
             for (int u = 0; u < GP1; ++u) {
                 const int64_t e = ent[warp * GP1 + u] + cur[u] + lane;
@@ -347,13 +355,11 @@ __global__ void __launch_bounds__(NT, MINB) dx_fit_tile_kernel(const TileArgs A)
                 yval[u] = in ? A.vals[e] : 0.0f;
             }
         };
-        prefetch(0);
-        __syncthreads();          // tables and constants visible
-
-#pragma unroll 1
-        for (int64_t c0 = 0; c0 < N; c0 += CT) {
-            const int tn = (int)((N - c0 < CT) ? (N - c0) : CT);
-            // ---- phase 0: stage the prefetched rows, densify the sparse columns ----------------------------------------
+        // stage the prefetched tile (registers -> buffers of parity pb), densify the sparse columns, fetch the tile after it
+        int nzn_next[GP1];
+        auto stage = [&](const int pb, const int64_t c0) {
+            double* const Xs = Xs0 + pb * L.xstg; double* const Ds = Ds0 + pb * L.xstg; double* const Lsf = Lsf0 + pb * L.stg;
+            float* const Ys = Ys0 + pb * L.stg * 2; uint8_t* const Yi = Yi0 + pb * L.stg * 8; uint8_t* const NZl = NZl0 + pb * L.stg * 8;
 #pragma unroll
             for (int i = 0; i < XPT; ++i) {
                 const int idx = tid + NT * i, j = idx / CT, c = idx % CT;
@@ -373,15 +379,25 @@ __global__ void __launch_bounds__(NT, MINB) dx_fit_tile_kernel(const TileArgs A)
 #pragma unroll
                 for (int v = 0; v < CP1; ++v) yrow_s[lane + 32 * v] = 0.0f;
             }
+            {
+                uint32_t* yi_w = reinterpret_cast<uint32_t*>(Yi + warp * GP1 * CT);
+                for (int i = lane; i < GP1 * CT / 4; i += 32) yi_w[i] = 0u;
+            }
             __syncwarp();
-            const int64_t c1 = c0 + tn;
-            int nzn[GP1];
+            const int64_t c1 = (N - c0 < CT) ? N : c0 + CT;
 #pragma unroll
             for (int u = 0; u < GP1; ++u) {
                 float* yrow_s = Ys + (warp * GP1 + u) * CT;
+                uint8_t* yi_s = Yi + (warp * GP1 + u) * CT;
                 uint8_t* nzl = NZl + (warp * GP1 + u) * (CT + 8);
+                auto put = [&](const int c, const float v, const int at) {
+                    const int vi = (int)v;
+                    yrow_s[c] = v;
+                    yi_s[c] = (vi >= 0 && vi < TB && (float)vi == v) ? (uint8_t)vi : (uint8_t)255;
+                    nzl[at] = (uint8_t)c;
+                };
                 bool hit = (int64_t)yrow[u] < c1;
-                if (hit) { yrow_s[(int)(yrow[u] - c0)] = yval[u]; nzl[lane] = (uint8_t)(yrow[u] - c0); }
+                if (hit) put((int)(yrow[u] - c0), yval[u], lane);
                 int n = __popc(__ballot_sync(DX_FULL_MASK, hit));
                 int tot = n;
                 cur[u] += n;
@@ -390,16 +406,33 @@ __global__ void __launch_bounds__(NT, MINB) dx_fit_tile_kernel(const TileArgs A)
                     hit = false;
                     if (e < ent[GT + warp * GP1 + u]) {
                         const int64_t row = A.rows[e];
-                        if (row < c1) { yrow_s[(int)(row - c0)] = A.vals[e]; nzl[tot + lane] = (uint8_t)(row - c0); hit = true; }
+                        if (row < c1) { put((int)(row - c0), A.vals[e], tot + lane); hit = true; }
                     }
                     n = __popc(__ballot_sync(DX_FULL_MASK, hit));
                     tot += n;
                     cur[u] += n;
                 }
-                nzn[u] = tot;
+                nzn_next[u] = tot;
             }
-            __syncthreads();
             if (c1 < N) prefetch(c1);
+        };
+        prefetch(0);
+        __syncthreads();          // tables and constants visible
+        stage(0, 0);
+        __syncthreads();
+
+        int pbuf = 0;
+#pragma unroll 1
+        for (int64_t c0 = 0; c0 < N; c0 += CT, pbuf ^= 1) {
+            const int tn = (int)((N - c0 < CT) ? (N - c0) : CT);
+            const double* const Xs = Xs0 + pbuf * L.xstg; const double* const Ds = Ds0 + pbuf * L.xstg;
+            const double* const Lsf = Lsf0 + pbuf * L.stg;
+            const float* const Ys = Ys0 + pbuf * L.stg * 2; const uint8_t* const Yi = Yi0 + pbuf * L.stg * 8;
+            const uint8_t* const NZl = NZl0 + pbuf * L.stg * 8;
+            const double* const dsrc_tile = (KIND == PASS_LOC) ? Xs : Ds;
+            int nzn[GP1];
+#pragma unroll
+            for (int u = 0; u < GP1; ++u) nzn[u] = nzn_next[u];
             if (GEMM) {
                 // product table of the cell tile, shared by all genes of the CTA: a warp per cell, lane <-> entry
 #pragma unroll 4
@@ -462,6 +495,7 @@ __global__ void __launch_bounds__(NT, MINB) dx_fit_tile_kernel(const TileArgs A)
                     for (int u = 0; u < GP1; ++u) {
                         const int g = warp * GP1 + u;
                         const double y = (double)Ys[g * CT + c];
+                        const int yi = Yi[g * CT + c];          // table index of the value (255: not in the tables)
                         double e = eta[v][u];
                         if ((__double2hiint(e) & 0x7fffffff) > 0x4071b000) e = dx_clip(e, DX_ETA_MIN, DX_ETA_MAX);          // |e| > 283 (or NaN)
                         const double mu = fl_exp(e);
@@ -476,34 +510,26 @@ __global__ void __launch_bounds__(NT, MINB) dx_fit_tile_kernel(const TileArgs A)
                         const double inv = fl_rcp_n(r + mu);
                         const double q = r * inv;
                         const double l1p = fl_log1p(mu * invr);
-                        const int yi = (int)y;
-                        const bool tab = SCONST && yi >= 0 && yi < TB && (double)yi == y;
                         double G = 0.0, d0 = 0.0, d1 = 0.0;
                         if (SCONST) {
-                            const int yc = min(max(yi, 0), TB - 1);
-                            G = Gt[g * TB + yc];
-                            if (KIND == PASS_SCALE) { d0 = T0[g * TB + yc]; d1 = T1[g * TB + yc]; }
+                            G = Gt[g * TB + (yi & (TB - 1))];
+                            if (KIND == PASS_SCALE) { d0 = T0[g * TB + (yi & (TB - 1))]; d1 = T1[g * TB + (yi & (TB - 1))]; }
                         }
-                        if (!tab && y != 0.0) {
+                        if (SCONST ? (yi == 255) : (y != 0.0)) {          // counts beyond the tables, non-integer values, per-cell r
                             G = g_ratio_slow(r, y);
                             if (KIND == PASS_SCALE) psi_diffs_slow(r, y, d0, d1);
                         }
-                        double llp = fma(-r, l1p, G);
-                        if (y != 0.0) llp = fma(y, e - l1p, llp);
-                        if (!valid) llp = 0.0;
-                        llacc[u] += llp;
+                        // (cells that pad a ragged last tile carry the offset -297.8 and a zero design row: mu ~ 1e-130, and every
+                        // term below vanishes against the sums it joins)
+                        llacc[u] += fma(y, e - l1p, fma(-r, l1p, G));
                         if (KIND == PASS_LOC) {
-                            wv[u] = valid ? mu * q : 0.0;
+                            wv[u] = mu * q;
                             sv[u] = y * q;
                         } else {
                             const double gi = r * (d0 - l1p + (mu - y) * inv);
                             const double hi = gi + r * r * d1 + r * (mu * mu + r * y) * (inv * inv);
-                            if (SCONST) {
-                                if (valid) { gacc[u] += gi; hacc[u] += hi; }
-                            } else {
-                                wv[u] = valid ? hi : 0.0;
-                                sv[u] = valid ? gi : 0.0;
-                            }
+                            if (SCONST) { gacc[u] += gi; hacc[u] += hi; }
+                            else { wv[u] = hi; sv[u] = gi; }
                         }
                     }
                     if (GEMM) {
@@ -569,6 +595,9 @@ __global__ void __launch_bounds__(NT, MINB) dx_fit_tile_kernel(const TileArgs A)
                     }
                 }
             }
+            // the next tile is staged into the buffers of the other parity (last read in phase 1 of the previous tile, which
+            // every warp has left): phase 0 shares the interval of the contraction, two barriers per tile instead of three
+            if (c0 + CT < N) stage(pbuf ^ 1, c0 + CT);
             __syncthreads();
         }
         // ---- end of pass: the per-gene sums -------------------------------------------------------------------------------
