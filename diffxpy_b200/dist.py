@@ -88,9 +88,13 @@ def gather_genes(w, tensors, n_genes_total, counts=None):
     send = torch.zeros((gmax, sum(widths)), dtype=torch.uint8, device=device)
     col = 0
     for name, wd in zip(names, widths):
-        t = tensors[name].contiguous()
-        raw = t.reshape(g_local, -1).view(torch.uint8) if g_local else t.reshape(0, 0).view(torch.uint8)
-        send[:g_local, col:col + raw.shape[1]] = raw
+        t = tensors[name]
+        if g_local:
+            ncols = int(np.prod(t.shape[1:], dtype=np.int64))
+            rows = torch.empty((g_local, ncols), dtype=t.dtype, device=device)          # (standard strides, whatever the view
+            rows.copy_(t.reshape(g_local, ncols))                                       # the caller handed over)
+            raw = rows.view(torch.uint8)
+            send[:g_local, col:col + raw.shape[1]] = raw
         col += wd
     recv = torch.empty((w.size * gmax, sum(widths)), dtype=torch.uint8, device=device)
     td.all_gather_into_tensor(recv, send)

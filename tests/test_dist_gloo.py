@@ -31,6 +31,9 @@ def _worker(rank, size, port, g, weights, outdir):
         rows = {
             "a_var": torch.arange(lo, hi, dtype=torch.float64)[:, None] * torch.ones(1, 3, dtype=torch.float64),
             "niter": torch.arange(lo, hi, dtype=torch.int32),
+            # a [g, 1] column that is the transpose of a [1, g] row (how the estimator hands over b_var): unit-size last
+            # dimension with a non-unit stride
+            "b_var": torch.arange(lo, hi, dtype=torch.float64)[None, :].t(),
             "fim": torch.arange(lo, hi, dtype=torch.float64)[:, None, None] * torch.ones(1, 2, 2, dtype=torch.float64),
         }
         full = dxdist.gather_genes(w, rows, g)
@@ -41,6 +44,7 @@ def _worker(rank, size, port, g, weights, outdir):
         np.save(os.path.join(outdir, "a_%d.npy" % rank), full["a_var"].numpy())
         np.save(os.path.join(outdir, "n_%d.npy" % rank), full["niter"].numpy())
         np.save(os.path.join(outdir, "f_%d.npy" % rank), full["fim"].numpy())
+        assert full["b_var"].shape == (g, 1) and torch.equal(full["b_var"][:, 0], torch.arange(g, dtype=torch.float64))
     finally:
         td.destroy_process_group()
 
