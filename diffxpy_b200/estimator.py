@@ -285,8 +285,8 @@ class Estimator:
                                                dxdist.gene_weights(idata.data) if self._world.size > 1 else None)
         lo, hi = self._gene_ranges[self._world.rank]
         self._gene_range = (lo, hi)
-        with torch.cuda.device(dev):
-            self.shard = dxdevice.take(idata.data, dev, None if self._world.size == 1 else (lo, hi))
+        # (the shard itself is taken over at the END of this method: the host work below -- design grouping, rank checks,
+        # pseudo-inverse -- runs while the matrix still uploads in the background, device.prefetch)
         # ---- resolve init modes (batchglm init_par) -------------------------------------------------
         init_a, init_b = self._init_a, self._init_b
         a_given = b_given = None
@@ -372,7 +372,10 @@ class Estimator:
                 if loc_u.shape[0] > 500:
                     raise ValueError("large least-square problem in init, likely defined a numeric predictor as categorical")
                 plan.update(loc_u=loc_u, loc_inv_cells=loc_inv_cells)
-        dxdevice._trace("initialize() done (design groups uploaded)")
+        dxdevice._trace("initialize(): design groups uploaded")
+        with torch.cuda.device(dev):
+            self.shard = dxdevice.take(idata.data, dev, None if self._world.size == 1 else (lo, hi))
+        dxdevice._trace("initialize() done (shard taken over)")
         plan["train_loc"] = bool(train_loc)
         plan["train_scale"] = not self._quick_scale
         self._plan = plan
