@@ -53,6 +53,8 @@ SIGNATURES = {
     "dx_upload": [_P, _P, _I64, _I32, _P],
     "dx_csr_to_csc_work_bytes": [_I64, _I32, C.POINTER(C.c_int64)],
     "dx_csr_to_csc": [_I64, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P],
+    "dx_csr_to_csc_staged_work_bytes": [_I64, _I32, _I64, C.POINTER(C.c_int64)],
+    "dx_csr_to_csc_staged": [_I64, _I64, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _I64, _P],
     "dx_gene_moments": [_I64, _P, _P, _P, _P, _P, _P, _P],
     "dx_nb_fit_grouped": [_I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, C.POINTER(DxFitOpts),
                           _P, _P, _P, _P, _P, _P, _P, _P],

@@ -187,6 +187,26 @@ int dx_csr_to_csc(int64_t n_cells, const int64_t* indptr, const int32_t* cols, c
     return DX_OK;
 }
 
+int dx_csr_to_csc_staged_work_bytes(int64_t n_cells, int32_t n_genes_out, int64_t nnz, int64_t* bytes) {
+    DX_CHECK(bytes && n_cells >= 0 && n_genes_out >= 0 && nnz >= 0, "dx_csr_to_csc_staged_work_bytes: bad arguments");
+    *bytes = (int64_t)dx_transpose_staged_work_bytes_impl(n_cells, n_genes_out, nnz, sm_count_cached());
+    return DX_OK;
+}
+
+int dx_csr_to_csc_staged(int64_t n_cells, int64_t nnz, const int64_t* indptr, const int32_t* cols, const float* vals,
+                         int32_t gene_lo, int32_t n_genes_out, int64_t* out_indptr, int32_t* out_rows, float* out_vals,
+                         void* work, int64_t work_bytes, void* stream) {
+    DX_CHECK(n_cells >= 0 && nnz >= 0 && gene_lo >= 0 && n_genes_out >= 0, "dx_csr_to_csc_staged: bad sizes");
+    DX_CHECK(indptr && out_indptr && work, "dx_csr_to_csc_staged: null pointer");
+    DX_CHECK((int64_t)n_genes_out * 4 <= 220 * 1024, "dx_csr_to_csc_staged: more than 56320 genes in the range");
+    DX_CHECK(n_cells < (1ll << 27), "dx_csr_to_csc_staged: at most 2^27 - 1 cells (the record key holds the cell in 27 bits)");
+    DX_CHECK(work_bytes >= (int64_t)dx_transpose_staged_work_bytes_impl(n_cells, n_genes_out, nnz, sm_count_cached()),
+             "dx_csr_to_csc_staged: workspace smaller than dx_csr_to_csc_staged_work_bytes");
+    DX_CUDA(dx_launch_csr_to_csc_staged(n_cells, nnz, indptr, cols, vals, gene_lo, n_genes_out, out_indptr, out_rows, out_vals,
+                                        work, work_bytes, sm_count_cached(), (cudaStream_t)stream), "dx_csr_to_csc_staged");
+    return DX_OK;
+}
+
 int dx_gene_moments(int64_t n_genes, const int64_t* indptr, const int32_t* rows, const float* vals,
                     const double* inv_sf, double* sum1, double* sum2, void* stream) {
     DX_CHECK(n_genes >= 0 && indptr && sum1 && sum2, "dx_gene_moments: bad arguments");

@@ -74,3 +74,8 @@ size_t dx_transpose_work_bytes_impl(int64_t n_cells, int n_out, int sm_count);
 cudaError_t dx_launch_csr_to_csc(int64_t n_cells, const int64_t* indptr, const int32_t* cols, const float* vals, int lo, int n_out,
                                  int64_t* out_ptr, int32_t* out_rows, float* out_vals, void* work, int sm_count,
                                  cudaStream_t stream);
+// staged variant (append-only streams: no write amplification); n_cells < 2^27, column indices sorted inside a cell
+size_t dx_transpose_staged_work_bytes_impl(int64_t n_cells, int n_out, int64_t nnz, int sm_count);
+cudaError_t dx_launch_csr_to_csc_staged(int64_t n_cells, int64_t nnz, const int64_t* indptr, const int32_t* cols, const float* vals,
+                                        int lo, int n_out, int64_t* out_ptr, int32_t* out_rows, float* out_vals, void* work,
+                                        int64_t work_bytes, int sm_count, cudaStream_t stream);

@@ -289,7 +289,7 @@ class CountShard:
             return CountShard.from_csr_device(
                 torch.from_numpy(np.asarray(csr.indptr, dtype=np.int64)).to(dev),
                 upload(csr.indices, dev, torch.int32), upload(csr.data, dev, torch.float32),
-                csr.shape[1], gene_range)
+                csr.shape[1], gene_range, sorted_cols=True)          # (canonical format: sorted, no duplicates)
         arr = np.asarray(data)
         if arr.ndim != 2:
             raise ValueError("data must be a 2-d (cells x genes) matrix")
@@ -316,9 +316,10 @@ class CountShard:
         return CountShard(indptr, rows, vals, x.shape[0], 0 if gene_range is None else gene_range[0])
 
     @staticmethod
-    def from_csr_device(indptr, cols, vals, n_genes, gene_range=None):
-        """Cell-major CSR on the device -> gene-major shard of the gene range: K8 (dx_csr_to_csc: count per chunk of cells,
-        scan, stable scatter; cells ascending inside a gene).  A cell must hold a gene at most once (canonical CSR)."""
+    def from_csr_device(indptr, cols, vals, n_genes, gene_range=None, sorted_cols=False):
+        """Cell-major CSR on the device -> gene-major shard of the gene range: K8 (dx_csr_to_csc[_staged]: count per chunk of
+        cells, scan, stable placement; cells ascending inside a gene).  A cell must hold a gene at most once; with
+        ``sorted_cols`` (column indices ascending inside every cell: canonical CSR) the staged kernels are used."""
         n_cells = indptr.shape[0] - 1
         dev = vals.device
         lo, hi = (0, int(n_genes)) if gene_range is None else (int(gene_range[0]), int(gene_range[1]))
@@ -326,15 +327,24 @@ class CountShard:
         if n_out > 56320:
             return CountShard._from_csr_device_sorted(indptr, cols, vals, n_genes, gene_range)
         nbytes = C.c_int64(0)
-        _lib.call("dx_csr_to_csc_work_bytes", int(n_cells), n_out, C.byref(nbytes))
-        work = torch.empty((nbytes.value + 7) // 8, dtype=torch.int64, device=dev)
         out_ptr = torch.empty(n_out + 1, dtype=torch.int64, device=dev)
         cap = max(int(cols.shape[0]), 1)
         out_rows = torch.empty(cap, dtype=torch.int32, device=dev)
         out_vals = torch.empty(cap, dtype=torch.float32, device=dev)
-        _lib.call("dx_csr_to_csc", int(n_cells), ptr(indptr.contiguous()), ptr(cols.contiguous()),
-                  ptr(vals.to(torch.float32).contiguous()), lo, n_out, ptr(out_ptr), ptr(out_rows), ptr(out_vals), ptr(work),
-                  stream_ptr())
+        import os
+        staged = sorted_cols and n_cells < (1 << 27) and os.environ.get("DXB200_K8_STAGED", "1") != "0"          # (test hook)
+        if staged:          # append-only segments per gene block first: no write amplification (dx_transpose.cu)
+            _lib.call("dx_csr_to_csc_staged_work_bytes", int(n_cells), n_out, cap, C.byref(nbytes))
+            work = torch.empty((nbytes.value + 7) // 8, dtype=torch.int64, device=dev)
+            _lib.call("dx_csr_to_csc_staged", int(n_cells), cap, ptr(indptr.contiguous()), ptr(cols.contiguous()),
+                      ptr(vals.to(torch.float32).contiguous()), lo, n_out, ptr(out_ptr), ptr(out_rows), ptr(out_vals), ptr(work),
+                      int(work.numel() * 8), stream_ptr())
+        else:
+            _lib.call("dx_csr_to_csc_work_bytes", int(n_cells), n_out, C.byref(nbytes))
+            work = torch.empty((nbytes.value + 7) // 8, dtype=torch.int64, device=dev)
+            _lib.call("dx_csr_to_csc", int(n_cells), ptr(indptr.contiguous()), ptr(cols.contiguous()),
+                      ptr(vals.to(torch.float32).contiguous()), lo, n_out, ptr(out_ptr), ptr(out_rows), ptr(out_vals), ptr(work),
+                      stream_ptr())
         if gene_range is not None:          # only the entries of the range were written: keep those
             total = int(out_ptr[-1].item())
             out_rows, out_vals = out_rows[:total].clone(), out_vals[:total].clone()

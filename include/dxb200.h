@@ -144,6 +144,15 @@ int dx_csr_to_csc_work_bytes(int64_t n_cells, int32_t n_genes_out, int64_t* byte
 int dx_csr_to_csc(int64_t n_cells, const int64_t* indptr, const int32_t* cols, const float* vals,
                   int32_t gene_lo, int32_t n_genes_out, int64_t* out_indptr, int32_t* out_rows, float* out_vals,
                   void* work, void* stream);
+/* Staged variant, same result: the entries first go to append-only segments per (block of 32 genes, chunk of cells), then
+ * from there to their genes, so every write stream stays sector-friendly (dx_csr_to_csc writes 4-byte elements to one open
+ * position per gene and CTA: 7x the algorithmic DRAM traffic on a 100k x 20k matrix).  Needs the column indices sorted
+ * inside every cell (canonical CSR), n_cells < 2^27 and a workspace of dx_csr_to_csc_staged_work_bytes(n_cells,
+ * n_genes_out, nnz) bytes (about 8 nnz). */
+int dx_csr_to_csc_staged_work_bytes(int64_t n_cells, int32_t n_genes_out, int64_t nnz, int64_t* bytes);
+int dx_csr_to_csc_staged(int64_t n_cells, int64_t nnz, const int64_t* indptr, const int32_t* cols, const float* vals,
+                         int32_t gene_lo, int32_t n_genes_out, int64_t* out_indptr, int32_t* out_rows, float* out_vals,
+                         void* work, int64_t work_bytes, void* stream);
 
 /* ---- K_fit (grouped): the whole batchglm training schedule + finalize, one warp per gene ----------
  * Replaces Estimator.initialize / train_sequence / finalize (tests.py:222-248) when the rows of

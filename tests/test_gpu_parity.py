@@ -252,7 +252,8 @@ def test_ingest_csr_csc_dense_inputs_agree(de):
     np.testing.assert_array_equal(outs[0], outs[2])
 
 
-@pytest.mark.parametrize("shape,density", [((3000, 700), 0.12), ((257, 40000), 0.002), ((1, 5), 1.0), ((4000, 3), 0.5)])
+@pytest.mark.parametrize("shape,density", [((3000, 700), 0.12), ((257, 40000), 0.002), ((1, 5), 1.0), ((4000, 3), 0.5),
+                                           ((20000, 300), 0.6), ((700, 2100), 0.9)])
 def test_k8_csr_to_csc_bit_exact(de, shape, density):
     """dx_csr_to_csc against scipy's tocsc(): same pointers, cells ascending inside every gene, same values -- whole matrix
     and gene ranges (what a gene-sharded run keeps), with empty cells and empty genes."""
@@ -267,13 +268,18 @@ def test_k8_csr_to_csc_bit_exact(de, shape, density):
     want.sort_indices()
     ranges = [None, (0, shape[1] // 2), (shape[1] // 3, shape[1])] if shape[1] > 3 else [None]
     for gr in ranges:
-        shard = CountShard.from_host(x, gene_range=gr)
-        lo, hi = (0, shape[1]) if gr is None else gr
-        sub = want[:, lo:hi]
-        np.testing.assert_array_equal(shard.indptr.cpu().numpy(), sub.indptr.astype(np.int64))
-        np.testing.assert_array_equal(shard.rows.cpu().numpy()[:sub.nnz], sub.indices)
-        np.testing.assert_array_equal(shard.vals.cpu().numpy()[:sub.nnz], sub.data)
-        assert shard.gene_offset == lo and shard.n_cells == x.shape[0]
+        for staged in ("1", "0"):          # dx_csr_to_csc_staged (default) and dx_csr_to_csc
+            os.environ["DXB200_K8_STAGED"] = staged
+            try:
+                shard = CountShard.from_host(x, gene_range=gr)
+            finally:
+                del os.environ["DXB200_K8_STAGED"]
+            lo, hi = (0, shape[1]) if gr is None else gr
+            sub = want[:, lo:hi]
+            np.testing.assert_array_equal(shard.indptr.cpu().numpy(), sub.indptr.astype(np.int64))
+            np.testing.assert_array_equal(shard.rows.cpu().numpy()[:sub.nnz], sub.indices)
+            np.testing.assert_array_equal(shard.vals.cpu().numpy()[:sub.nnz], sub.data)
+            assert shard.gene_offset == lo and shard.n_cells == x.shape[0]
 
 
 # ---------------------------------------------------------------------------------------------------
