@@ -12,8 +12,8 @@ is cut into N contiguous ranges of equal non-zero count (strong scaling; genes a
 path); `--scaling weak` gives every GPU its own 20k-gene matrix instead (secondary figure).
 
 One "step" = one full ``de.test.wald`` pass over the shard that is already resident in HBM in gene-major layout, 4 launches:
-K_ingest (the only kernel that streams the count matrix) -> K_pack (compresses long overflow lists; nothing to do on this
-workload) -> K_fit (complete batchglm training schedule per gene; its epilogue computes the Wald row and, with N > 1, stores
+dx_zero_genes_kernel + K_ingest (the only kernel that streams the count matrix; K_pack, which compresses long overflow lists,
+is skipped because the resident shard knows that no count of this workload leaves the tail-count table) -> K_fit (complete batchglm training schedule per gene; its epilogue computes the Wald row and, with N > 1, stores
 the p-value straight into every rank's exchange buffer over NVLink) -> BH q-values in one CTA (with N > 1 it first waits for
 the exchange flags of all ranks: the one exchange of the path).  With N > 1 the step is replayed as one CUDA graph; at N = 1
 it is launched plainly so that the per-kernel CUDA events sit inside the timed region.
@@ -353,15 +353,17 @@ def main_cuda(args):
                       ptr(tail), ptr(ovf_count), ptr(ovf_val), ptr(ovf_group), ptr(gene_order), ingest_flags, stream_ptr())
         if record:
             e[1].record()
-        # what SuffStats.pack_overflow() does in the estimator: nothing to pack on this workload (gene means <= 1)
-        _lib.call("dx_pack_overflow", g, k, 0, ptr(ovf_count), ptr(shard.indptr), ptr(ovf_val), ptr(ovf_group),
-                  ptr(ovf_packed), stream_ptr())
+        # what SuffStats.pack_overflow() does in the estimator: K_pack, unless the resident shard knows that no count leaves the
+        # tail-count table (this workload: gene means <= 1) -- then there is no list to pack and the fit takes a NULL table
+        if not no_overflow:
+            _lib.call("dx_pack_overflow", g, k, 0, ptr(ovf_count), ptr(shard.indptr), ptr(ovf_val), ptr(ovf_group),
+                      ptr(ovf_packed), stream_ptr())
         if record:
             e[2].record()
         # K_fit + the Wald row of `condition` per gene (+ N > 1: the p-value goes straight into every rank's exchange slot)
         _lib.call("dx_nb_fit_wald_grouped", g, k, p, ps, ptr(d_xl), ptr(d_xs), None, ptr(d_nk), ptr(d_pinv), None, k,
                   ptr(tail), ptr(ovf_count), ptr(shard.indptr), None if no_overflow else ptr(ovf_val),
-                  None if no_overflow else ptr(ovf_group), ptr(ovf_packed), opts,
+                  None if no_overflow else ptr(ovf_group), None if no_overflow else ptr(ovf_packed), opts,
                   ptr(a_var), ptr(b_var), ptr(fim_inv), ptr(ll), ptr(jac), ptr(niter), ptr(flags),
                   1, ptr(rows_out[0]), ptr(rows_out[1]), ptr(rows_out[2]), ptr(rows_out[3]),
                   exchange.peer_ptrs if exchange is not None else None, world, rank,
@@ -585,17 +587,17 @@ def main_cuda(args):
     clocks = sampler.summary()
     kern = {"dx_ingest_tma_kernel": {"ms": ingest_ms, "algorithmic_bytes": ingest_bytes,
                                      "gbs": ingest_bytes / (ingest_ms * 1e-3) / 1e9, "frac_of_hbm_peak": ingest_bytes / (ingest_ms * 1e-3) / 1e9 / peak},
-            "dx_pack_overflow_kernel": {"ms": pack_ms},
-            "dx_fit_fast_kernel(+wald epilogue)": {"ms": fit_ms},
-            "dx_bh_fused_kernel": {"ms": bh_ms}}
-    fit_prof = prof.get("dx_fit_fast_kernel")
+            ("dx_pack_overflow_kernel" if not no_overflow else "dx_pack_overflow_kernel (skipped: no count leaves the table)"): {"ms": pack_ms},
+            "dx_fit_lane_kernel(+wald epilogue)": {"ms": fit_ms},
+            "dx_bh_cluster_kernel": {"ms": bh_ms}}
+    fit_prof = prof.get("dx_fit_lane_kernel_profile")
     if isinstance(fit_prof, dict) and fit_prof.get("warp_instructions") and world == 1 and g == fit_prof.get("genes"):
         # K_fit is bounded by instruction issue, not by HBM (it reads 4 KB of statistics per gene): achieved = warp
         # instructions of one launch (ncu, profiles/) / live duration; peak = SMs x 4 schedulers x SM clock
         sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
         issue_peak = sm_count.value * 4 * sm_mhz * 1e6
         ach = fit_prof["warp_instructions"] / (fit_ms * 1e-3)
-        kern["dx_fit_fast_kernel(+wald epilogue)"]["roofline"] = {
+        kern["dx_fit_lane_kernel(+wald epilogue)"]["roofline"] = {
             "bound": "issue", "achieved": ach / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instructions/s",
             "frac": ach / issue_peak, "fp64_pipe_pct": fit_prof.get("fp64_pipe_pct"),
             "source": "profiles/traffic.json (ncu smsp__inst_executed.sum of one launch) / live CUDA-event time"}
@@ -624,9 +626,11 @@ def main_cuda(args):
                "sample": "%d genes x %d cells, 1 pass (oracle port of batchglm's numpy schedule, Newton scale step, "
                          "one process per core)" % (gps, N_CELLS)}
 
-    # own kernels per step: ingest, pack, fit (+ Wald epilogue, + peer stores), BH (one fused kernel up to 32768 p-values,
+    # own kernels per step: ingest, pack, fit (+ Wald epilogue, + peer stores), BH (one cluster kernel up to 32768 p-values,
     # else wait/copy + 7 kernels)
-    launches_per_step = 4 if n_total_genes <= 32768 else (3 + (1 if world > 1 else 0) + 7)
+    # (+ dx_zero_genes_kernel when the work list cuts large genes into parts)
+    launches_per_step = (4 if n_total_genes <= 32768 else (3 + (1 if world > 1 else 0) + 7)) + \
+        (1 if (use_pieces and int(multi_genes.shape[0]) > 0) else 0) - (1 if no_overflow else 0)
     if rank == 0:
         if api_s is not None:
             api_bytes = 8 * nnz_all // world + 8 * (n_cells + 1) + n_cells * (p + 1) * 8

@@ -242,7 +242,7 @@ def run_rank(args, bench):
                 "whole_step": {"achieved": (bytes_in + 32 * g) / (ms * 1e-3) / 1e9, "peak": peak,
                                "frac": (bytes_in + 32 * g) / (ms * 1e-3) / 1e9 / peak}}
     kernels = {"dx_ingest_tma_kernel (2 groups)": {"ms": ingest_ms}, "dx_two_group_kernel + dx_two_group_welch_kernel (U, ties, Welch t from the tail counts)": {"ms": test_ms},
-               "transpose + 2 x dx_bh_fused_kernel": {"ms": bh_ms}}
+               "transpose + 2 x dx_bh_cluster_kernel": {"ms": bh_ms}}
     config = {"workload": "configs[4]: de.test.rank_test + de.test.t_test, %d cells x %d genes, two groups, sparse gene-major shard"
                           % (n_cells, n_genes), "n_cells": n_cells, "genes_total": g, "nnz_total": nnz,
               "density": nnz / (n_cells * g), "l2": "inputs (%.1f GB per pass) larger than L2; no explicit flush" % (8 * nnz / 1e9),

@@ -18,9 +18,16 @@ import torch
 from . import _lib
 
 
+class _NothingPacked:
+    """Marker of SuffStats.pack_overflow() on a shard without overflow entries: the fit takes a NULL record table."""
+
+
+NOTHING_PACKED = _NothingPacked()
+
+
 def ptr(t):
     """Raw device pointer of a tensor (None -> NULL)."""
-    if t is None:
+    if t is None or t is NOTHING_PACKED:
         return None
     assert t.is_contiguous(), "tensor passed to the C ABI must be contiguous"
     return C.c_void_p(t.data_ptr())
@@ -418,6 +425,8 @@ class SuffStats:
     def pack_overflow(self, min_entries=0):
         """K_pack: rewrite long overflow lists (highly expressed genes) as (value, multiplicity) records, in place.
         Afterwards the statistics feed dx_nb_fit_grouped_packed only (not the rank / t tests)."""
+        if self.ovf_packed is None and self.shard.counts_fit_table:
+            self.ovf_packed = NOTHING_PACKED          # every count sits in the tail-count table: no list to pack, no launch
         if self.ovf_packed is None:
             packed = torch.empty((self.tail.shape[0], 2), dtype=torch.int32, device=self.tail.device)
             _lib.call("dx_pack_overflow", self.tail.shape[0], self.n_groups, int(min_entries), ptr(self.ovf_count),
