@@ -1028,7 +1028,22 @@ cudaError_t launch_p(const TileArgs& A, int sm_count, cudaStream_t stream) {
 
 }  // namespace
 
-cudaError_t dx_fit_percell_counters_impl(unsigned long long* out, int reset) {
+// The file is compiled twice (Makefile): DX_TILE_PART 1 holds the instantiations of the constant dispersion model and the
+// entry points, DX_TILE_PART 2 those of the general scale model -- two translation units build side by side instead of one
+// that takes three minutes.  Each part has its own copy of the diagnostics counters.
+#ifndef DX_TILE_PART
+#define DX_TILE_PART 0          // both in one object
+#endif
+
+#define DX_TILE_FILL_ARGS()                                                                                              \
+    TileArgs A;                                                                                                          \
+    A.n_genes = n_genes; A.N = n_cells; A.p = p; A.ps = ps;                                                              \
+    A.dl = design_loc; A.ds = design_scale; A.log_sf = log_sf;                                                           \
+    A.indptr = indptr; A.rows = rows; A.vals = vals; A.opts = *opts;                                                     \
+    A.a_var = a_var; A.b_var = b_var; A.fim_inv = fim_inv; A.ll = ll; A.jac = jac; A.niter = niter; A.flags = flags;     \
+    A.queue = nullptr
+
+static cudaError_t tile_counters(unsigned long long* out, int reset) {
     cudaError_t e = cudaMemcpyFromSymbol(out, g_tile_counters, 4 * sizeof(unsigned long long));
     if (e != cudaSuccess) return e;
     if (reset) {
@@ -1036,6 +1051,41 @@ cudaError_t dx_fit_percell_counters_impl(unsigned long long* out, int reset) {
         e = cudaMemcpyToSymbol(g_tile_counters, zero, sizeof(zero));
     }
     return e;
+}
+
+#if DX_TILE_PART == 2 || DX_TILE_PART == 0
+cudaError_t dx_fit_percell_counters_general(unsigned long long* out, int reset) { return tile_counters(out, reset); }
+
+cudaError_t dx_launch_fit_percell_general(int64_t n_genes, int64_t n_cells, int p, int ps,
+                                          const double* design_loc, const double* design_scale, const double* log_sf,
+                                          const int64_t* indptr, const int32_t* rows, const float* vals,
+                                          const dx_fit_opts* opts,
+                                          double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
+                                          int32_t* niter, int32_t* flags, int sm_count, cudaStream_t stream) {
+    DX_TILE_FILL_ARGS();
+    return launch_p<false>(A, sm_count, stream);
+}
+#else
+cudaError_t dx_fit_percell_counters_general(unsigned long long* out, int reset);
+cudaError_t dx_launch_fit_percell_general(int64_t n_genes, int64_t n_cells, int p, int ps,
+                                          const double* design_loc, const double* design_scale, const double* log_sf,
+                                          const int64_t* indptr, const int32_t* rows, const float* vals,
+                                          const dx_fit_opts* opts,
+                                          double* a_var, double* b_var, double* fim_inv, double* ll, double* jac,
+                                          int32_t* niter, int32_t* flags, int sm_count, cudaStream_t stream);
+#endif
+
+#if DX_TILE_PART == 1 || DX_TILE_PART == 0
+cudaError_t dx_fit_percell_counters_impl(unsigned long long* out, int reset) {
+    unsigned long long a[4], b[4] = {0, 0, 0, 0};
+    cudaError_t e = tile_counters(a, reset);
+    if (e != cudaSuccess) return e;
+#if DX_TILE_PART == 1
+    e = dx_fit_percell_counters_general(b, reset);
+    if (e != cudaSuccess) return e;
+#endif
+    for (int i = 0; i < 4; ++i) out[i] = a[i] + b[i];
+    return cudaSuccess;
 }
 
 cudaError_t dx_launch_fit_percell(int64_t n_genes, int64_t n_cells, int p, int ps,
@@ -1046,12 +1096,11 @@ cudaError_t dx_launch_fit_percell(int64_t n_genes, int64_t n_cells, int p, int p
                                   int32_t* niter, int32_t* flags, int sm_count, cudaStream_t stream) {
     if (n_genes <= 0) return cudaSuccess;
     if (p < 1 || p > 32 || ps < 1 || ps > 8) return cudaErrorNotSupported;
-    TileArgs A;
-    A.n_genes = n_genes; A.N = n_cells; A.p = p; A.ps = ps;
-    A.dl = design_loc; A.ds = design_scale; A.log_sf = log_sf;
-    A.indptr = indptr; A.rows = rows; A.vals = vals; A.opts = *opts;
-    A.a_var = a_var; A.b_var = b_var; A.fim_inv = fim_inv; A.ll = ll; A.jac = jac; A.niter = niter; A.flags = flags;
-    A.queue = nullptr;
     const bool scale_const = (ps == 1) && (opts->reserved & DX_OPT_SCALE_CONST);
-    return scale_const ? launch_p<true>(A, sm_count, stream) : launch_p<false>(A, sm_count, stream);
+    if (!scale_const)
+        return dx_launch_fit_percell_general(n_genes, n_cells, p, ps, design_loc, design_scale, log_sf, indptr, rows, vals, opts,
+                                             a_var, b_var, fim_inv, ll, jac, niter, flags, sm_count, stream);
+    DX_TILE_FILL_ARGS();
+    return launch_p<true>(A, sm_count, stream);
 }
+#endif

@@ -8,7 +8,7 @@ SRC=${SRC:-$ROOT/diffxpy_b200/csrc}
 OUT=$ROOT/diffxpy_b200/variants
 OBJ=/tmp/dxvar_$NAME
 mkdir -p $OUT $OBJ
-for f in dx_api dx_ingest dx_fit_grouped dx_fit_lane dx_fit_tile dx_stats dx_overflow dx_exchange; do
+for f in dx_api dx_ingest dx_fit_grouped dx_fit_lane dx_stats dx_overflow dx_exchange; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr \
     $EXTRA -c $SRC/$f.cu -o $OBJ/$f.o 2> $OBJ/$f.log &
 done
