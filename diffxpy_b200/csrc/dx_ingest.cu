@@ -303,13 +303,15 @@ struct TileInfo {          // registers, per fetched tile
 // (largest first keeps the tail of the launch short).
 // H16: the caller guarantees that no design group has more than 65535 cells, so the per-warp histogram fits 16-bit
 // bins (half the shared memory -> more resident warps).
-template <bool INT_ONLY, bool H16>
+// MODE: how the work queue is read (DX_INGEST_MODE_*): a compile-time parameter, so the instantiation of one mode carries neither
+// the branches nor the registers of the others through the streaming loop.
+template <bool INT_ONLY, bool H16, int MODE>
 __global__ void __launch_bounds__(TW * 32, 1)
 dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const int32_t* __restrict__ rows,
                      const float* __restrict__ vals, const uint8_t* __restrict__ cell_group, int K, int ysh, int NW, int NWA,
                      uint32_t* __restrict__ hist_out, int32_t* __restrict__ ovf_count,
                      float* __restrict__ ovf_val, uint8_t* __restrict__ ovf_group, unsigned int* __restrict__ queue,
-                     const int32_t* __restrict__ gene_order, int warp_bytes, int mode, int split_rpw,
+                     const int32_t* __restrict__ gene_order, int warp_bytes, int /*mode: see MODE*/, int split_rpw,
                      const int4* __restrict__ pieces, int64_t n_pieces) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -354,7 +356,7 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
     long long sp_pos = 0, sp_end = 0, sp_lo = 0, sp_hi = 0;     // current range [sp_pos, sp_end) of the shard [sp_lo, sp_hi)
     long long sp_seg = 0;
     long long sp_gene = 0;
-    if (mode == DX_INGEST_MODE_SPLIT) {
+    if (MODE == DX_INGEST_MODE_SPLIT) {
         sp_lo = __ldg(indptr);
         sp_hi = __ldg(indptr + n_genes);
         const long long span = sp_hi - sp_lo;
@@ -367,8 +369,8 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
         if (i_tiles == 0) {
             unsigned gq = 0;
             long long st_ = 0, en_ = 0;
-            int piece_multi = (mode == DX_INGEST_MODE_SPLIT) ? 1 : 0;      // 1: tail counts are added to the output (part of a gene)
-            if (mode == DX_INGEST_MODE_SPLIT) {
+            int piece_multi = (MODE == DX_INGEST_MODE_SPLIT) ? 1 : 0;      // 1: tail counts are added to the output (part of a gene)
+            if (MODE == DX_INGEST_MODE_SPLIT) {
                 for (;;) {
                     if (sp_pos >= sp_end) {                      // next range of the shard
                         unsigned q = 0;
@@ -393,7 +395,7 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
                     sp_pos = en_;
                     if (en_ > st_) break;                        // (genes without entries yield no piece)
                 }
-            } else if (mode == DX_INGEST_MODE_PIECES) {
+            } else if (MODE == DX_INGEST_MODE_PIECES) {
                 // the queue hands out the pieces of the resident shard's work list (dx_group_suffstats_pieces): whole genes,
                 // and equal parts of the genes that are too large to be one unit of work
                 unsigned q = 0;
@@ -412,7 +414,7 @@ dx_ingest_tma_kernel(int64_t n_genes, const int64_t* __restrict__ indptr, const 
                     if ((int64_t)gq >= n_genes) { done_issue = true; return; }
                     if (gene_order) gq = (unsigned)__ldg(gene_order + gq);
                     // MODE_REDO: second pass after a split launch, only the genes that reported overflow entries
-                    if (mode != DX_INGEST_MODE_REDO || ovf_count[gq] != 0) break;
+                    if (MODE != DX_INGEST_MODE_REDO || ovf_count[gq] != 0) break;
                 }
                 st_ = __ldg(indptr + gq); en_ = __ldg(indptr + gq + 1);
             }
@@ -714,10 +716,17 @@ cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32
         if (e != cudaSuccess) return e;
         const size_t smem = (size_t)warps * warp_bytes;
         const bool io = (flags & DX_SHARD_INTEGER_COUNTS) != 0;
-        auto kern = io ? (h16 ? dx_ingest_tma_kernel<true, true> : dx_ingest_tma_kernel<true, false>)
-                       : (h16 ? dx_ingest_tma_kernel<false, true> : dx_ingest_tma_kernel<false, false>);
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+        // one instantiation per (integer counts, 16-bit bins, queue mode)
+#define DX_TMA_PICK(M) (io ? (h16 ? dx_ingest_tma_kernel<true, true, M> : dx_ingest_tma_kernel<true, false, M>)      \
+                           : (h16 ? dx_ingest_tma_kernel<false, true, M> : dx_ingest_tma_kernel<false, false, M>))
+        auto kern = DX_TMA_PICK(DX_INGEST_MODE_GENES);
+        auto kern_pieces = DX_TMA_PICK(DX_INGEST_MODE_PIECES);
+        auto kern_redo = DX_TMA_PICK(DX_INGEST_MODE_REDO);
+#undef DX_TMA_PICK
+        for (auto kfn : {kern, kern_pieces, kern_redo}) {
+            e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
         // few genes (a gene range of a multi-GPU run): one warp per gene leaves warps idle and the longest gene sets the
         // duration, so the shard is cut into equal ranges of non-zeros instead (pieces of genes, tail counts added with
         // atomics into a zeroed table); genes with overflow entries are then redone gene-wise, which writes their lists in
@@ -731,10 +740,10 @@ cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32
                 e = cudaGetLastError();
                 if (e != cudaSuccess) return e;
             }
-            kern<<<(unsigned)sm_count, warps * 32, smem, stream>>>(n_genes, indptr, rows, vals, cell_group, K, ysh, NW, NWA, hist,
-                                                                   ovf_count, ovf_val, ovf_group, queue, nullptr, warp_bytes,
-                                                                   DX_INGEST_MODE_PIECES, 0, reinterpret_cast<const int4*>(pieces),
-                                                                   n_pieces);
+            kern_pieces<<<(unsigned)sm_count, warps * 32, smem, stream>>>(n_genes, indptr, rows, vals, cell_group, K, ysh, NW, NWA,
+                                                                          hist, ovf_count, ovf_val, ovf_group, queue, nullptr,
+                                                                          warp_bytes, DX_INGEST_MODE_PIECES, 0,
+                                                                          reinterpret_cast<const int4*>(pieces), n_pieces);
             e = cudaGetLastError();
             if (e != cudaSuccess || n_multi <= 0 || (flags & DX_SHARD_NO_OVERFLOW)) return e;
             unsigned int* queue2 = nullptr;
@@ -742,9 +751,9 @@ cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32
             if (e != cudaSuccess) return e;
             int64_t grid2 = (n_multi + warps - 1) / warps;
             if (grid2 > sm_count) grid2 = sm_count;
-            kern<<<(unsigned)grid2, warps * 32, smem, stream>>>(n_multi, indptr, rows, vals, cell_group, K, ysh, NW, NWA, hist,
-                                                                ovf_count, ovf_val, ovf_group, queue2, multi_genes, warp_bytes,
-                                                                DX_INGEST_MODE_REDO, 0, nullptr, 0);
+            kern_redo<<<(unsigned)grid2, warps * 32, smem, stream>>>(n_multi, indptr, rows, vals, cell_group, K, ysh, NW, NWA, hist,
+                                                                     ovf_count, ovf_val, ovf_group, queue2, multi_genes, warp_bytes,
+                                                                     DX_INGEST_MODE_REDO, 0, nullptr, 0);
             return cudaGetLastError();
         }
         const char* split_env = getenv("DXB200_INGEST_SPLIT");
@@ -755,7 +764,8 @@ cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32
             const int split_rpw = (rpw_env && atoi(rpw_env) >= 1 && atoi(rpw_env) <= 64) ? atoi(rpw_env) : 2;
             // a piece never holds more than 128 tiles: its counts always fit 16-bit on-chip bins (the shared-memory
             // layout sized for 32-bit bins holds them as well)
-            auto kern_split = io ? dx_ingest_tma_kernel<true, true> : dx_ingest_tma_kernel<false, true>;
+            auto kern_split = io ? dx_ingest_tma_kernel<true, true, DX_INGEST_MODE_SPLIT>
+                                 : dx_ingest_tma_kernel<false, true, DX_INGEST_MODE_SPLIT>;
             e = cudaFuncSetAttribute(kern_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             e = cudaMemsetAsync(hist, 0, (size_t)n_genes * K * DX_HIST_BINS * sizeof(uint32_t), stream);
@@ -772,9 +782,9 @@ cudaError_t dx_launch_ingest(int64_t n_genes, const int64_t* indptr, const int32
             if (e != cudaSuccess) return e;
             int64_t grid2 = sm_count < 16 ? sm_count : 16;          // usually nothing to redo: a small grid walks the counts
             if (grid2 > n_genes) grid2 = n_genes;
-            kern<<<(unsigned)grid2, warps * 32, smem, stream>>>(n_genes, indptr, rows, vals, cell_group, K, ysh, NW, NWA, hist,
-                                                                ovf_count, ovf_val, ovf_group, queue2, nullptr, warp_bytes,
-                                                                DX_INGEST_MODE_REDO, 0, nullptr, 0);
+            kern_redo<<<(unsigned)grid2, warps * 32, smem, stream>>>(n_genes, indptr, rows, vals, cell_group, K, ysh, NW, NWA, hist,
+                                                                     ovf_count, ovf_val, ovf_group, queue2, nullptr, warp_bytes,
+                                                                     DX_INGEST_MODE_REDO, 0, nullptr, 0);
             return cudaGetLastError();
         }
         int64_t grid = sm_count;                    // persistent CTAs; the warps pull genes from the queue
