@@ -391,6 +391,9 @@ __global__ void __launch_bounds__(NT, MINB) dx_fit_tile_kernel(const TileArgs A)
                 uint8_t* yi_s = Yi + (warp * GP1 + u) * CT;
                 uint8_t* nzl = NZl + (warp * GP1 + u) * (CT + 8);
                 auto put = [&](const int c, const float v, const int at) {
+                    // (a canonical shard -- cells ascending, a cell at most once per gene -- never trips these guards; a
+                    // malformed one must not write outside the tile)
+                    if (c < 0 || at >= CT + 8) return;
                     const int vi = (int)v;
                     yrow_s[c] = v;
                     yi_s[c] = (vi >= 0 && vi < TB && (float)vi == v) ? (uint8_t)vi : (uint8_t)255;
@@ -412,7 +415,7 @@ __global__ void __launch_bounds__(NT, MINB) dx_fit_tile_kernel(const TileArgs A)
                     tot += n;
                     cur[u] += n;
                 }
-                nzn_next[u] = tot;
+                nzn_next[u] = (tot < CT + 8) ? tot : CT + 8;
             }
             if (c1 < N) prefetch(c1);
         };
