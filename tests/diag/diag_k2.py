@@ -1,7 +1,7 @@
 """Diagnostic: two design groups, two coefficients (closed-form start exact, location model not trained)."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle.nb_glm as onb
 from diffxpy_b200 import _lib

@@ -1,7 +1,7 @@
 """Diagnostic: general kernel <32> and lane kernel against the oracle on designs with more than 16 groups."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 import oracle.nb_glm as onb
