@@ -305,7 +305,34 @@ __global__ void __launch_bounds__(NT, MINB) dx_fit_tile_kernel(const TileArgs A)
         }
         const int gh = warp % NGH, ks = warp / NGH;
         const unsigned grp_mask = (MG >= 32) ? mask : ((mask >> (gh * MG)) & ((1u << MG) - 1u));
-        const unsigned p1_mask = (mask >> (warp * GP1)) & ((1u << GP1) - 1u);
+        // Which genes this warp evaluates in phase 1 (slot u <-> gene gu[u]).  Location passes: its own GP1 genes.  Dispersion
+        // passes of the constant dispersion model (no contraction): the genes of the pass are dealt out evenly, ceil(n / 8) to a
+        // warp -- on average half the genes of a tile sit out a Newton pass of the lockstep schedule (they are done with their
+        // line search), and a pass costs as much as its busiest warp.
+        constexpr bool COMPACT = (KIND == PASS_SCALE) && SCONST;
+        int gu[GP1];
+        int ng_w = 0;
+        if (COMPACT) {
+            const int n_pass = __popc(mask);
+            const int gpw = (n_pass + NWP - 1) / NWP;
+#pragma unroll
+            for (int u = 0; u < GP1; ++u) {
+                const int idx = warp * gpw + u;          // position in the ascending list of the genes of the pass
+                int g = 0;
+                if (u < gpw && idx < n_pass) {
+                    unsigned m = mask;
+                    for (int k = 0; k < idx; ++k) m &= m - 1u;          // drop the idx lowest set bits
+                    g = __ffs(m) - 1;
+                    ng_w = u + 1;
+                }
+                gu[u] = g;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < GP1; ++u) gu[u] = warp * GP1 + u;
+            ng_w = ((mask >> (warp * GP1)) & ((1u << GP1) - 1u)) ? GP1 : 0;
+        }
+        const bool p1_mask = ng_w > 0;
         const double* const wbase = Ws + gh * MG;
         const double* const vbase = Ss + gh * MG;
         int zjk[GEMM ? NEK : 1];          // this lane's entries: j | k << 8
@@ -349,8 +376,8 @@ __global__ void __launch_bounds__(NT, MINB) dx_fit_tile_kernel(const TileArgs A)
             if (tid < CT) lr = (c0 + tid < N) ? (A.log_sf ? A.log_sf[c0 + tid] : 0.0) : DX_ETA_MIN;          // (padding: mu ~ 1e-130)
 #pragma unroll
             for (int u = 0; u < GP1; ++u) {
-                const int64_t e = ent[warp * GP1 + u] + cur[u] + lane;
-                const bool in = e < ent[GT + warp * GP1 + u];
+                const int64_t e = ent[gu[u]] + cur[u] + lane;
+                const bool in = u < ng_w && e < ent[GT + gu[u]];
                 yrow[u] = in ? A.rows[e] : 0x7fffffff;
                 yval[u] = in ? A.vals[e] : 0.0f;
             }
@@ -405,9 +432,9 @@ __global__ void __launch_bounds__(NT, MINB) dx_fit_tile_kernel(const TileArgs A)
                 int tot = n;
                 cur[u] += n;
                 while (n == 32) {                       // more than 32 entries of this gene inside the cell tile
-                    const int64_t e = ent[warp * GP1 + u] + cur[u] + lane;
+                    const int64_t e = ent[gu[u]] + cur[u] + lane;
                     hit = false;
-                    if (e < ent[GT + warp * GP1 + u]) {
+                    if (e < ent[GT + gu[u]]) {
                         const int64_t row = A.rows[e];
                         if (row < c1) { put((int)(row - c0), A.vals[e], tot + lane); hit = true; }
                     }
@@ -466,9 +493,14 @@ __global__ void __launch_bounds__(NT, MINB) dx_fit_tile_kernel(const TileArgs A)
                     double xv[CP1], av[GP1];
 #pragma unroll
                     for (int v = 0; v < CP1; ++v) xv[v] = Xs[j * XST + lane + 32 * v];
-                    const double2* ap = reinterpret_cast<const double2*>(qa_s + j * GT + warp * GP1);
+                    if (COMPACT) {
 #pragma unroll
-                    for (int u = 0; u < GP1; u += 2) { const double2 t = ap[u / 2]; av[u] = t.x; av[u + 1] = t.y; }
+                        for (int u = 0; u < GP1; ++u) av[u] = qa_s[j * GT + gu[u]];
+                    } else {
+                        const double2* ap = reinterpret_cast<const double2*>(qa_s + j * GT + warp * GP1);
+#pragma unroll
+                        for (int u = 0; u < GP1; u += 2) { const double2 t = ap[u / 2]; av[u] = t.x; av[u + 1] = t.y; }
+                    }
 #pragma unroll
                     for (int v = 0; v < CP1; ++v)
 #pragma unroll
@@ -496,9 +528,10 @@ __global__ void __launch_bounds__(NT, MINB) dx_fit_tile_kernel(const TileArgs A)
                     double wv[GP1], sv[GP1];
 #pragma unroll
                     for (int u = 0; u < GP1; ++u) {
-                        const int g = warp * GP1 + u;
-                        const double y = (double)Ys[g * CT + c];
-                        const int yi = Yi[g * CT + c];          // table index of the value (255: not in the tables)
+                        if (COMPACT && u >= ng_w) break;          // (warp-uniform)
+                        const int g = gu[u], slot = warp * GP1 + u;
+                        const double y = (double)Ys[slot * CT + c];
+                        const int yi = Yi[slot * CT + c];          // table index of the value (255: not in the tables)
                         double e = eta[v][u];
                         if ((__double2hiint(e) & 0x7fffffff) > 0x4071b000) e = dx_clip(e, DX_ETA_MIN, DX_ETA_MAX);          // |e| > 283 (or NaN)
                         const double mu = fl_exp(e);
@@ -606,7 +639,8 @@ __global__ void __launch_bounds__(NT, MINB) dx_fit_tile_kernel(const TileArgs A)
         // ---- end of pass: the per-gene sums -------------------------------------------------------------------------------
 #pragma unroll
         for (int u = 0; u < GP1; ++u) {
-            const int g = warp * GP1 + u;
+            if (u >= ng_w) break;
+            const int g = gu[u];
             const double l = dx_warp_sum(llacc[u]);
             const double gsum = (KIND == PASS_SCALE && SCONST) ? dx_warp_sum(gacc[u]) : 0.0;
             const double hsum = (KIND == PASS_SCALE && SCONST) ? dx_warp_sum(hacc[u]) : 0.0;
