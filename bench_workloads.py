@@ -58,12 +58,28 @@ def _host_csc(shard):
                                    shape=(shard.n_cells, shard.n_genes))
 
 
+def _pool_warm(_):
+    import oracle.nb_glm  # noqa: F401
+    import oracle.stats  # noqa: F401
+    import scipy.stats  # noqa: F401
+    return os.getpid()
+
+
 def _pool_map(fn, chunks, cores):
+    import gc
     import multiprocessing as mp
-    with mp.get_context("fork").Pool(cores) as pool:
-        t0 = time.perf_counter()
-        out = pool.map(fn, chunks)
-        return out, time.perf_counter() - t0
+    # forked from a process with CUDA state: no child may ever free an object created before the fork (cyclic garbage holding
+    # CUDA tensors would otherwise be destroyed by a child's collector: "initialization error", dead worker, hung pool)
+    gc.collect()
+    gc.freeze()
+    try:
+        with mp.get_context("spawn").Pool(cores) as pool:          # clean workers (no inherited CUDA state)
+            pool.map_async(_pool_warm, range(4 * cores)).get(timeout=600)          # worker start-up is not part of the baseline
+            t0 = time.perf_counter()
+            out = pool.map_async(fn, chunks).get(timeout=900)
+            return out, time.perf_counter() - t0
+    finally:
+        gc.unfreeze()
 
 
 def _one_thread():
