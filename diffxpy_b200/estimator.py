@@ -96,6 +96,30 @@ def group_rows(mat):
     return uniq, order_inv[inv]
 
 
+def join_groupings(parts):
+    """Grouping of the rows of ``np.concatenate([m_0, m_1, ...], axis=1)`` from the groupings ``(uniq_k, inv_k)`` of its column
+    blocks -- the same (uniq, inv) as group_rows() on the concatenation (groups in the byte order of the joint rows: every
+    uniq_k is in byte order, so the joint order is the lexicographic order of the index tuples), without hashing the wide
+    rows again.  None when the number of index tuples is too large for a counting pass."""
+    span = 1
+    for uniq_k, _ in parts:
+        span *= int(uniq_k.shape[0])
+    if span > (1 << 22):
+        return None
+    code = np.zeros(parts[0][1].shape[0], dtype=np.int64)
+    for uniq_k, inv_k in parts:
+        code *= int(uniq_k.shape[0])
+        code += inv_k
+    present = np.flatnonzero(np.bincount(code, minlength=span))          # ascending codes = byte order of the joint rows
+    remap = np.zeros(span, dtype=np.int64)
+    remap[present] = np.arange(present.shape[0])
+    cols, rest = [], present.copy()
+    for uniq_k, _ in reversed(parts):
+        cols.append(uniq_k[rest % int(uniq_k.shape[0])])
+        rest //= int(uniq_k.shape[0])
+    return np.ascontiguousarray(np.concatenate(cols[::-1], axis=1)), remap[code]
+
+
 def few_distinct_rows(mat, limit=4096, probe=8192):
     """group_rows(mat) when the matrix has at most ``limit`` distinct rows, else None (decided on a prefix first, so a
     continuous design costs one small probe instead of a sort of all its rows)."""
@@ -326,12 +350,20 @@ class Estimator:
         cols = [idata.xh_loc, idata.xh_scale]
         if idata.size_factors is not None:
             cols.append(idata.size_factors.reshape(-1, 1))
-        joint = np.concatenate(cols, axis=1)
-        probe = group_rows(joint[:8192])[0].shape[0]
         grouped = False
-        if probe <= _lib.DX_MAX_GROUPS:
-            uniq, inv = group_rows(joint)
+        joined = None
+        if idata.size_factors is None and idata._groups_loc is not None and idata._groups_scale is not None:
+            # both designs were grouped at construction: the joint grouping follows from the two index maps
+            joined = join_groupings([idata._groups_loc, idata._groups_scale])
+        if joined is not None:
+            uniq, inv = joined
             grouped = uniq.shape[0] <= _lib.DX_MAX_GROUPS
+        else:
+            joint = np.concatenate(cols, axis=1)
+            probe = group_rows(joint[:8192])[0].shape[0]
+            if probe <= _lib.DX_MAX_GROUPS:
+                uniq, inv = group_rows(joint)
+                grouped = uniq.shape[0] <= _lib.DX_MAX_GROUPS
         plan = {"a_mode": a_mode, "b_mode": b_mode, "a_given": a_given, "b_given": b_given}
         p, ps = idata.num_loc_params, idata.num_scale_params
         if grouped:

@@ -361,3 +361,22 @@ def test_float64_values_rounded_to_float32_are_reported(caplog):
         device._warn_if_rounded_to_float32(np.log1p(np.arange(1000, dtype=np.float64) / 7.0))
         assert len(caplog.records) == 1          # once per process
     device._WARNED_F32[0] = False
+
+
+def test_join_groupings_equals_group_rows_of_the_concatenation():
+    """Estimator.initialize derives the joint design groups from the groupings of the location and the scale design."""
+    from diffxpy_b200.estimator import group_rows, join_groupings
+    rng = np.random.default_rng(9)
+    n = 30000
+    cond, batch, extra = rng.integers(0, 2, n), rng.integers(0, 8, n), rng.integers(0, 3, n)
+    onehot = (batch[:, None] == np.arange(1, 8)[None, :]).astype(float)
+    loc = np.concatenate([np.ones((n, 1)), cond[:, None], onehot], axis=1).astype(float)
+    scale = np.concatenate([np.ones((n, 1)), onehot[:, :3], -extra[:, None]], axis=1).astype(float)          # negative values too
+    third = rng.choice([0.25, -1.5, 3.0], n)[:, None]
+    for mats in ([loc, scale], [scale, loc], [loc, scale, third], [loc[:, :1], scale[:, :1]]):
+        want_u, want_inv = group_rows(np.concatenate(mats, axis=1))
+        got_u, got_inv = join_groupings([group_rows(m) for m in mats])
+        np.testing.assert_array_equal(got_u, want_u)
+        np.testing.assert_array_equal(got_inv, want_inv)
+    big = [(np.arange(5000.0)[:, None], rng.integers(0, 5000, n)), (np.arange(5000.0)[:, None], rng.integers(0, 5000, n))]
+    assert join_groupings(big) is None          # too many index tuples for a counting pass: the caller hashes the rows
