@@ -129,7 +129,23 @@ def _factor_columns(sample_description, term, as_categorical, full_rank):
     s = sample_description[col]
     if forced or _is_categorical(sample_description, col, as_categorical):
         col = term                      # patsy names the columns after the term as written: C(x)[T.level]
-        levels = _levels(s)
+        codes = None
+        if isinstance(s.dtype, pd.CategoricalDtype):
+            levels = _levels(s)
+        else:
+            # one hash pass over the column gives codes and distinct values; the levels are the sorted values (_levels), the
+            # codes follow by a permutation of the small code range
+            raw, uniq = pd.factorize(s, use_na_sentinel=True)
+            uniq = list(uniq)
+            try:
+                order = sorted(range(len(uniq)), key=lambda i: uniq[i])
+            except TypeError:
+                order = sorted(range(len(uniq)), key=lambda i: str(uniq[i]))
+            levels = [uniq[i] for i in order]
+            perm = np.empty(len(uniq) + 1, dtype=np.int64)
+            perm[np.asarray(order, dtype=np.int64)] = np.arange(len(uniq))
+            perm[len(uniq)] = -1                      # the NA sentinel -1 indexes the last entry
+            codes = perm[np.asarray(raw, dtype=np.int64)]
         if full_rank:
             use = levels
             names = ["%s[%s]" % (col, lv) for lv in use]
@@ -138,7 +154,8 @@ def _factor_columns(sample_description, term, as_categorical, full_rank):
             names = ["%s[T.%s]" % (col, lv) for lv in use]
         # one pass over the column: level codes, then a one-hot scatter (comparing the column with every level in turn
         # costs a string comparison pass per level)
-        codes = pd.Categorical(s, categories=levels).codes.astype(np.int64)
+        if codes is None:
+            codes = pd.Categorical(s, categories=levels).codes.astype(np.int64)
         onehot = np.zeros((len(s), len(levels)), dtype=np.float64)
         ok = codes >= 0
         onehot[np.nonzero(ok)[0], codes[ok]] = 1.0

@@ -319,8 +319,12 @@ class Estimator:
         if isinstance(init_a, str):
             mode = init_a.lower()
             if mode == "auto":
-                vals = np.unique(idata.design_loc)
-                one_hot = len(vals) == 2 and vals.min() == 0.0 and vals.max() == 1.0
+                # (batchglm: the design holds exactly the values 0 and 1 -- read off the distinct rows when they are known,
+                # else with three comparisons instead of a sort of all entries)
+                d = idata._groups_loc[0] if (idata._groups_loc is not None and idata.xh_loc is idata.design_loc) \
+                    else idata.design_loc
+                is0, is1 = d == 0.0, d == 1.0
+                one_hot = bool(np.all(is0 | is1) and is0.any() and is1.any())
                 mode = "closed_form" if one_hot else "standard"
             if mode not in ("closed_form", "standard", "all_zero"):
                 raise ValueError("init_a string %s not recognized" % init_a)
