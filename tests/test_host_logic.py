@@ -380,3 +380,28 @@ def test_join_groupings_equals_group_rows_of_the_concatenation():
         np.testing.assert_array_equal(got_inv, want_inv)
     big = [(np.arange(5000.0)[:, None], rng.integers(0, 5000, n)), (np.arange(5000.0)[:, None], rng.integers(0, 5000, n))]
     assert join_groupings(big) is None          # too many index tuples for a counting pass: the caller hashes the rows
+
+
+def test_factor_coding_one_pass_matches_the_definition():
+    """design_matrix codes a factor with one hash pass: same columns, names and reference level as comparing the column
+    with every sorted level in turn (patsy treatment coding); missing values give all-zero rows."""
+    from diffxpy_b200.data import design as dd
+    rng = np.random.default_rng(11)
+    n = 5000
+    sd = pd.DataFrame({"condition": rng.integers(0, 2, n).astype(str), "batch": rng.integers(0, 8, n).astype(str),
+                       "num": rng.integers(0, 4, n),
+                       "withna": pd.Series(rng.choice(np.array(["a", "b", None], dtype=object), n)),
+                       "cat": pd.Categorical(rng.choice(["lo", "hi", "mid"], n), categories=["lo", "mid", "hi", "unused"])})
+    dm = dd.design_matrix(sd, "~ 1 + condition + batch")
+    c, b = sd["condition"].to_numpy(dtype=object), sd["batch"].to_numpy(dtype=object)
+    want = np.concatenate([np.ones((n, 1)), (c == "1")[:, None],
+                           b[:, None] == np.array([str(i) for i in range(1, 8)], dtype=object)[None, :]], axis=1).astype(float)
+    np.testing.assert_array_equal(np.asarray(dm), want)
+    assert list(dm.design_info.column_names) == ["Intercept", "condition[T.1]"] + ["batch[T.%d]" % i for i in range(1, 8)]
+    dm2 = dd.design_matrix(sd, "~ 1 + num + withna")
+    assert list(dm2.design_info.column_names) == ["Intercept", "num[T.1]", "num[T.2]", "num[T.3]", "withna[T.b]"]
+    x2, w = np.asarray(dm2), sd["withna"].to_numpy(dtype=object)
+    np.testing.assert_array_equal(x2[:, 4], (w == "b").astype(float))          # missing values: all-zero row of the factor
+    np.testing.assert_array_equal(x2[:, 1], (sd["num"].to_numpy() == 1).astype(float))
+    dm3 = dd.design_matrix(sd, "~ 1 + cat")          # an existing categorical keeps its level order; unused levels drop out
+    assert list(dm3.design_info.column_names) == ["Intercept", "cat[T.mid]", "cat[T.hi]"]
